@@ -1,0 +1,369 @@
+// hash_aggregate.cu -- PhysicalAggregatePlan::execute (aggregate/mod.rs:113-222)
+// and the five AggregateOperators (aggregate/{count,sum,avg,min,max}.rs).
+//
+// Group-by: one open-addressing table in HBM/L2 with array-of-struct records
+//   [ key | state words ... ]   (8-byte words)
+// whose state words are pre-initialised to the operators' identities, so a row
+// only needs (1) a probe that claims or finds its key slot with one CAS and
+// (2) one fire-and-forget reduction per state word:
+//   count -> u64 add; sum/avg -> f64 add (+ u64 add); min/max -> u64 min/max on
+//   the OrderedFloat order-preserving encoding (hash_common.cuh), skipped when
+//   a plain load shows the value cannot improve the state.
+// All value columns are accumulated "as f64" exactly like the reference
+// (sum.rs:44 `val as f64`), NULL keys are dropped (mod.rs:63-71), NULL values
+// skipped, and the output carries no key column.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "agg_device.cuh"
+
+namespace {
+
+__global__ void agg_init_kernel(AggParams ap, uint64_t n_records) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    unsigned long long *rec = ap.table + r * ap.rec_words;
+    rec[0] = EMPTY_KEY;
+    for (int a = 0; a < ap.n_aggs; a++) {
+        unsigned long long *s = rec + ap.state_off[a];
+        switch (ap.op[a]) {
+        case NQE_AGG_COUNT: s[0] = 0; break;
+        case NQE_AGG_SUM: s[0] = 0; break; // +0.0
+        case NQE_AGG_AVG: s[0] = 0; s[1] = 0; break;
+        case NQE_AGG_MIN: s[0] = nqe_f64_to_ord(DBL_MAX); break;  // f64::MAX, min.rs:38
+        case NQE_AGG_MAX: s[0] = nqe_f64_to_ord(-DBL_MAX); break; // f64::MIN, max.rs:38
+        }
+    }
+}
+
+// program 0 of ps = group key expression
+__global__ void __launch_bounds__(AG_THREADS)
+group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap) {
+    constexpr int TILE = AG_K * AG_THREADS;
+    const int64_t num_tiles = (ap.n_rows + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * TILE + threadIdx.x;
+        uint32_t inrange = 0;
+#pragma unroll
+        for (int j = 0; j < AG_K; j++)
+            if (e0 + (int64_t)j * AG_THREADS < ap.n_rows) inrange |= 1u << j;
+        RowRegs<AG_K> key;
+        run_program<AG_K>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
+        unsigned long long *rec[AG_K];
+#pragma unroll
+        for (int j = 0; j < AG_K; j++) {
+            rec[j] = nullptr;
+            if ((key.valid >> j) & 1u) { // NULL keys are dropped
+                rec[j] = find_slot(ap, key.v[j]);
+                if (!rec[j]) atomicOr(ap.status, DEV_ERR_TABLE_FULL);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < AG_K; j++)
+            if (rec[j]) update_record(ap, ps, rec[j], e0 + (int64_t)j * AG_THREADS);
+    }
+}
+
+// Global (no GROUP BY) path, mod.rs:123-139: per-thread partial states, warp
+// shuffle reduction, then one reduction per warp into the single record.
+__global__ void __launch_bounds__(AG_THREADS)
+global_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap) {
+    const int lane = threadIdx.x & 31;
+    for (int a = 0; a < ap.n_aggs; a++) {
+        const DevColRef &c = ps.cols[ap.col_slot[a]];
+        const int op = ap.op[a];
+        double sum = 0.0;
+        unsigned long long cnt = 0;
+        unsigned long long ext = op == NQE_AGG_MIN ? nqe_f64_to_ord(DBL_MAX) : nqe_f64_to_ord(-DBL_MAX);
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ap.n_rows; e += (int64_t)gridDim.x * blockDim.x) {
+            if (c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) continue;
+            cnt++;
+            if (op == NQE_AGG_COUNT) continue;
+            const double v = value_as_f64(c.dtype, ld_cached_u64((const uint64_t *)c.values + e));
+            if (op == NQE_AGG_SUM || op == NQE_AGG_AVG) sum += v;
+            else if (op == NQE_AGG_MAX) { const unsigned long long k = nqe_f64_to_ord(v); if (k > ext) ext = k; }
+            else if (v == v) { const unsigned long long k = nqe_f64_to_ord(v); if (k < ext) ext = k; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, ext, o);
+            if (op == NQE_AGG_MIN ? other < ext : other > ext) ext = other;
+        }
+        if (lane == 0) {
+            unsigned long long *s = ap.table + ap.state_off[a];
+            if (op == NQE_AGG_COUNT) red_add_u64(s, cnt);
+            else if (op == NQE_AGG_SUM) red_add_f64(s, sum);
+            else if (op == NQE_AGG_AVG) { red_add_f64(s, sum); red_add_u64(s + 1, cnt); }
+            else if (op == NQE_AGG_MAX) red_max_u64(s, ext);
+            else red_min_u64(s, ext);
+        }
+    }
+}
+
+struct ExtractParams {
+    void *out[AG_MAX];
+    unsigned long long *out_count;
+    int32_t is_global;
+};
+
+// occupied records -> dense output rows (order unspecified, as in the reference)
+__global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_records) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool occ = false;
+    const unsigned long long *rec = nullptr;
+    if (r < n_records) {
+        rec = ap.table + r * ap.rec_words;
+        if (xp.is_global) occ = true;
+        else if (r == n_records - 1) {
+            // the record of key == i64::MIN is occupied iff any state moved off its identity;
+            // word rec[0] is set to a non-EMPTY marker by the first updater (see mark below)
+            occ = rec[0] != EMPTY_KEY;
+        } else occ = rec[0] != EMPTY_KEY;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    unsigned long long base = 0;
+    if (lane == 0 && m) base = atomicAdd(xp.out_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!occ) return;
+    const unsigned long long row = base + __popc(m & ((1u << lane) - 1u));
+    for (int a = 0; a < ap.n_aggs; a++) {
+        const unsigned long long *s = rec + ap.state_off[a];
+        switch (ap.op[a]) {
+        case NQE_AGG_COUNT: ((unsigned long long *)xp.out[a])[row] = s[0]; break;
+        case NQE_AGG_SUM: ((unsigned long long *)xp.out[a])[row] = s[0]; break;
+        case NQE_AGG_AVG: // avg.rs:118: sum / cnt as f64, cnt is u32 (wraps in release builds)
+            ((double *)xp.out[a])[row] = __longlong_as_double((long long)s[0]) / (double)(uint32_t)s[1];
+            break;
+        default: ((double *)xp.out[a])[row] = nqe_ord_to_f64(s[0]); break;
+        }
+    }
+}
+
+// cardinality estimate by linear counting over a strided sample
+__global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int64_t n_rows, int64_t stride,
+                                  int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sample) return;
+    const int64_t e = i * stride;
+    RowRegs<1> key;
+    run_program<1>(ps, 0, e, 1, e < n_rows ? 1u : 0u, 0u, 0u, key, status);
+    if (key.valid & 1u) {
+        const uint32_t h = (uint32_t)(nqe_mix64(key.v[0]) >> 32) & bits_mask;
+        atomicOr(bitmap + (h >> 5), 1u << (h & 31));
+    }
+}
+__global__ void popcount_kernel(const uint32_t *bitmap, int n_words, unsigned long long *out) {
+    unsigned int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) c += __popc(bitmap[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+} // namespace
+
+static const char *agg_fn_name(int op) {
+    static const char *n[] = {"Count", "Sum", "Avg", "min", "Max"};
+    return n[op];
+}
+static const char *dtype_name2(int d) {
+    switch (d) {
+    case NQE_BOOL: return "Boolean"; case NQE_INT64: return "Int64"; case NQE_UINT64: return "UInt64";
+    case NQE_FLOAT64: return "Float64"; default: return "Utf8";
+    }
+}
+
+// validate one aggregate against its argument column dtype and lay out its state
+int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const int32_t *col_dtypes, bool grouped,
+                       AggParams *ap) {
+    if (n_aggs < 0 || n_aggs > AG_MAX) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "at most %d aggregates per plan", AG_MAX);
+    ap->n_aggs = n_aggs;
+    int words = 1;
+    for (int a = 0; a < n_aggs; a++) {
+        const int op = aggs[a].op;
+        if (op < NQE_AGG_COUNT || op > NQE_AGG_MAX) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad aggregate op %d", op);
+        const int dt = col_dtypes[a];
+        if (op != NQE_AGG_COUNT && (dt == NQE_BOOL || dt == NQE_UTF8)) {
+            // update_batch: Err(NotSupported) (sum.rs:91-96); update(row): unimplemented!() (sum.rs:108)
+            return nqe_fail(ctx, grouped ? NQE_ERR_PANIC : NQE_ERR_NOT_SUPPORTED, "%s func for %s is not supported",
+                            agg_fn_name(op), dtype_name2(dt));
+        }
+        ap->op[a] = op;
+        ap->state_off[a] = words;
+        words += op == NQE_AGG_AVG ? 2 : 1;
+    }
+    ap->rec_words = (words + 3) & ~3; // 32-byte multiple
+    return NQE_OK;
+}
+
+int32_t nqe_agg_table_create(nqe_ctx *ctx, AggParams *ap, uint64_t capacity) {
+    const uint64_t n_records = capacity + 1;
+    void *table = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &table, (size_t)n_records * ap->rec_words * 8));
+    ap->table = (unsigned long long *)table;
+    ap->mask = capacity - 1;
+    agg_init_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->stream>>>(*ap, n_records);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
+
+static int32_t read_scratch(nqe_ctx *ctx, int words_n) {
+    cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, words_n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return nqe_fail(ctx, NQE_ERR_CUDA, "aggregate kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return NQE_OK;
+}
+
+// occupied records -> output table columns (count: UInt64, others Float64)
+int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64_t max_groups, nqe_table *t) {
+    ExtractParams xp;
+    memset(&xp, 0, sizeof xp);
+    const uint64_t n_records = is_global ? 1 : ap.mask + 2;
+    int64_t out_cap = is_global ? 1 : (max_groups < (int64_t)n_records ? max_groups : (int64_t)n_records);
+    if (out_cap < 1) out_cap = 1;
+    t->cols.resize(ap.n_aggs);
+    for (int a = 0; a < ap.n_aggs; a++) {
+        NQE_TRY(nqe_column_alloc(ctx, ap.op[a] == NQE_AGG_COUNT ? NQE_UINT64 : NQE_FLOAT64, out_cap, false, &t->cols[a]));
+        xp.out[a] = t->cols[a].values;
+    }
+    NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint64_t), ctx->stream));
+    xp.out_count = (unsigned long long *)ctx->d_scratch;
+    xp.is_global = is_global ? 1 : 0;
+    agg_extract_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->stream>>>(ap, xp, n_records);
+    ctx->launches++;
+    NQE_TRY(read_scratch(ctx, 1));
+    t->nrows = (int64_t)ctx->h_scratch[0];
+    for (auto &c : t->cols) c.length = t->nrows;
+    return NQE_OK;
+}
+
+// capacity for `est` expected groups
+uint64_t nqe_agg_capacity(double est) { return nqe_next_pow2((uint64_t)(est * 2.0) + 1024); }
+
+extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *group_expr,
+                                      const nqe_agg *aggs, int32_t n_aggs, nqe_table **out) {
+    if (!ctx || !in || !out || (!aggs && n_aggs > 0)) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    const int64_t n = in->nrows;
+
+    DevProgramSet ps;
+    memset(&ps, 0, sizeof ps);
+    ExprInfo info[2];
+    if (group_expr) { // program 0: group key
+        const nqe_expr *list[1] = {group_expr};
+        NQE_TRY(nqe_compile_exprs(ctx, in, list, 1, &ps, info));
+        if (info[0].result_dtype != NQE_INT64 && info[0].result_dtype != NQE_UINT64) { // aggregate/mod.rs:217-219
+            if (info[0].result_dtype == NQE_UTF8)
+                return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 group keys are not implemented on the CUDA path yet");
+            return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "group by only support by `Int64`, `UInt64`, `String`");
+        }
+    }
+    AggParams ap;
+    memset(&ap, 0, sizeof ap);
+    ap.n_rows = n;
+    int32_t dts[AG_MAX];
+    if (n_aggs > AG_MAX) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "at most %d aggregates per plan", AG_MAX);
+    for (int a = 0; a < n_aggs; a++) {
+        const int col = aggs[a].column;
+        if (col < 0 || col >= (int)in->cols.size()) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", col);
+        dts[a] = in->cols[col].dtype;
+    }
+    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, group_expr != nullptr, &ap));
+    for (int a = 0; a < n_aggs; a++) { // register the argument columns as column slots
+        const DevColumn &c = in->cols[aggs[a].column];
+        int slot = -1;
+        for (int s = 0; s < ps.n_cols; s++)
+            if (ps.cols[s].values == c.values && ps.cols[s].dtype == c.dtype) slot = s;
+        if (slot < 0) {
+            if (ps.n_cols >= NQE_MAX_COLS) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "too many distinct columns");
+            slot = ps.n_cols++;
+            ps.cols[slot].values = c.values;
+            ps.cols[slot].validity = (const uint32_t *)c.validity;
+            ps.cols[slot].dtype = c.dtype;
+        }
+        ap.col_slot[a] = slot;
+    }
+    ap.status = (uint32_t *)(ctx->d_scratch + 1);
+
+    nqe_table *t;
+    nqe_table_new(ctx, 0, &t);
+    int32_t rc = NQE_OK;
+    OpTimer timer(ctx);
+
+    if (!group_expr) {
+        cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+        rc = nqe_agg_table_create(ctx, &ap, 1); // record 0 is the single global row
+        if (rc == NQE_OK && n > 0 && n_aggs > 0) {
+            int grid = ctx->sm_count * 8;
+            const int64_t need = (n + AG_THREADS - 1) / AG_THREADS;
+            if (grid > need) grid = (int)need;
+            global_aggregate_kernel<<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap);
+            ctx->launches++;
+        }
+    } else {
+        // --- size the table from a sampled cardinality estimate, grow on overflow
+        uint64_t capacity = 1024;
+        if (n > 0) {
+            const int64_t n_sample = n < (1 << 20) ? n : (1 << 20);
+            const int64_t stride = n / n_sample;
+            const uint32_t bits = 1u << 23; // 8 Mi bits = 1 MiB bitmap
+            void *bm = nullptr;
+            rc = nqe_dev_alloc(ctx, &bm, bits / 8);
+            if (rc == NQE_OK) {
+                cudaMemsetAsync(bm, 0, bits / 8, ctx->stream);
+                cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+                agg_sample_kernel<<<(unsigned)((n_sample + 255) / 256), 256, 0, ctx->stream>>>(
+                    ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status);
+                popcount_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t *)bm, bits / 32, (unsigned long long *)ctx->d_scratch);
+                ctx->launches += 2;
+                rc = read_scratch(ctx, 2);
+                nqe_dev_free(ctx, bm);
+            }
+            if (rc == NQE_OK) {
+                const double m = (double)bits, z = m - (double)ctx->h_scratch[0];
+                const double distinct = z > 0 ? -m * log(z / m) : m * 16; // linear counting
+                double est = distinct;
+                if (distinct > 0.5 * (double)n_sample) est = distinct * ((double)n / (double)n_sample); // still growing
+                if (est > (double)n) est = (double)n;
+                capacity = nqe_agg_capacity(est);
+            }
+        }
+        for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
+            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            rc = nqe_agg_table_create(ctx, &ap, capacity);
+            if (rc != NQE_OK) break;
+            if (n > 0) {
+                const int64_t tiles = (n + AG_K * AG_THREADS - 1) / (AG_K * AG_THREADS);
+                int grid = ctx->sm_count * 8;
+                if (grid > tiles) grid = (int)tiles;
+                group_aggregate_kernel<<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap);
+                ctx->launches++;
+            }
+            rc = read_scratch(ctx, 2);
+            if (rc != NQE_OK) break;
+            const uint32_t st = (uint32_t)ctx->h_scratch[1];
+            if (st & DEV_ERR_DIV0) { rc = nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error"); break; }
+            if (st & DEV_ERR_OVERFLOW) { rc = nqe_fail(ctx, NQE_ERR_PANIC, "attempt to divide with overflow"); break; }
+            if (!(st & DEV_ERR_TABLE_FULL)) break;
+            nqe_dev_free(ctx, ap.table);
+            ap.table = nullptr;
+            capacity *= 8;
+            if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
+        }
+    }
+    if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, group_expr == nullptr, n, t);
+    timer.stop();
+    nqe_dev_free(ctx, ap.table);
+    if (rc != NQE_OK) {
+        nqe_table_free(t);
+        return rc;
+    }
+    *out = t;
+    return NQE_OK;
+}

@@ -1,0 +1,585 @@
+// hash_join.cu -- HashJoin::build / probe (hash_join.rs:124-254) and the fused
+// join -> PhysicalAggregatePlan path.
+//
+// Build (hash_join.rs:58-78): the build side's raw key words (validity is ignored,
+// :67) go into one open-addressing multimap of 16-byte slots {key, build row}; a
+// slot is claimed with a CAS on the row word.  A verification pass marks whether
+// any key repeats, so that unique-key (PK-FK) probes stop at the first match.
+//
+// Probe (hash_join.rs:80-103, 236-246): one pass over the probe side.  Every tile
+// counts the matches of its rows, ranks them with warp shuffles + a decoupled
+// look-back across tiles (so the output is probe-row-major like the reference),
+// and writes the joined row -- all build columns gathered at the matching build
+// row, all probe columns from the probe row -- straight to its final position.
+// No (outer_pos, inner_pos) index arrays and no separate `take` pass exist.
+// Within one probe row, matches are emitted in ascending build-row order.
+#include <cstring>
+
+#include "agg_device.cuh"
+#include "hash_common.cuh"
+#include "nqe_internal.cuh"
+
+int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *words, unsigned long long *zeros);
+
+namespace {
+
+constexpr int HJ_THREADS = 256;
+constexpr int HJ_WARPS = HJ_THREADS / 32;
+constexpr int HJ_K = 4;
+constexpr int HJ_MAX_COLS = 16;
+constexpr unsigned long long EMPTY_ROW = ~0ull;
+
+struct Slot {
+    unsigned long long key;
+    unsigned long long row;
+};
+
+struct JoinTable {
+    Slot *slots;
+    uint64_t mask;
+    int32_t has_dups;
+};
+
+struct ColSrc {
+    const void *values;
+    const uint32_t *validity;
+    int32_t dtype;
+    int32_t pad;
+};
+
+__global__ void join_clear_kernel(Slot *slots, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        slots[i].key = 0;
+        slots[i].row = EMPTY_ROW;
+    }
+}
+
+__global__ void join_build_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    for (uint64_t probe = 0; probe <= jt.mask; probe++) {
+        const unsigned long long old = atomicCAS(&jt.slots[s].row, EMPTY_ROW, (unsigned long long)i);
+        if (old == EMPTY_ROW) {
+            jt.slots[s].key = key;
+            return;
+        }
+        s = (s + 1) & jt.mask;
+    }
+    atomicOr(status, DEV_ERR_TABLE_FULL);
+}
+
+// does any key occur more than once on the build side?
+__global__ void join_dups_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    int matches = 0;
+    while (true) {
+        const Slot sl = jt.slots[s];
+        if (sl.row == EMPTY_ROW) break;
+        if (sl.key == key) matches++;
+        s = (s + 1) & jt.mask;
+    }
+    if (matches > 1) *flag = 1u;
+}
+
+__device__ __forceinline__ Slot ld_slot(const Slot *p) {
+    const ulonglong2 v = __ldg((const ulonglong2 *)p);
+    return Slot{v.x, v.y};
+}
+
+// number of matches of `key`, and the smallest matching build row
+__device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigned long long key, unsigned long long *first) {
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    unsigned int c = 0;
+    unsigned long long best = EMPTY_ROW;
+    while (true) {
+        const Slot sl = ld_slot(jt.slots + s);
+        if (sl.row == EMPTY_ROW) break;
+        if (sl.key == key) {
+            c++;
+            if (sl.row < best) best = sl.row;
+            if (!jt.has_dups) break;
+        }
+        s = (s + 1) & jt.mask;
+    }
+    *first = best;
+    return c;
+}
+
+// smallest matching build row strictly greater than `after`
+__device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, unsigned long long key, unsigned long long after) {
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    unsigned long long best = EMPTY_ROW;
+    while (true) {
+        const Slot sl = ld_slot(jt.slots + s);
+        if (sl.row == EMPTY_ROW) break;
+        if (sl.key == key && sl.row > after && sl.row < best) best = sl.row;
+        s = (s + 1) & jt.mask;
+    }
+    return best;
+}
+
+struct ProbeParams {
+    JoinTable jt;
+    const unsigned long long *probe_keys;
+    int64_t n_probe;
+    int32_t n_left, n_right;
+    ColSrc left[HJ_MAX_COLS], right[HJ_MAX_COLS];
+    void *out_values[2 * HJ_MAX_COLS];   // 8-byte values or one byte per row (Boolean)
+    uint8_t *out_valid[2 * HJ_MAX_COLS]; // one byte per row or nullptr
+    int64_t out_cap;
+    unsigned long long *tile_state;
+    unsigned int *ticket;
+    unsigned long long *out_count;
+    int32_t num_tiles;
+};
+
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+
+__device__ __forceinline__ unsigned long long lookback(unsigned long long *state, int tile, unsigned long long my_total, int lane) {
+    if (lane == 0) st_volatile_u64(state + tile, (tile == 0 ? LB_PREFIX : LB_AGG) | my_total);
+    if (tile == 0) return 0;
+    unsigned long long excl = 0;
+    int idx = tile - 1;
+    while (true) {
+        const int my = idx - lane;
+        unsigned long long s;
+        do {
+            s = my >= 0 ? ld_volatile_u64(state + my) : LB_PREFIX;
+        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
+        const unsigned m = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        unsigned long long v = s & LB_MASK;
+        if (m) {
+            const int first = __ffs(m) - 1;
+            if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (m) break;
+        idx -= 32;
+    }
+    if (lane == 0) st_volatile_u64(state + tile, LB_PREFIX | (excl + my_total));
+    return excl;
+}
+
+__device__ __forceinline__ void emit_value(const ColSrc &c, int64_t src_row, void *out_values, uint8_t *out_valid, int64_t pos) {
+    bool valid = true;
+    if (c.validity) valid = (__ldg(c.validity + (src_row >> 5)) >> (src_row & 31)) & 1u;
+    if (c.dtype == NQE_BOOL) {
+        const uint32_t w = __ldg((const uint32_t *)c.values + (src_row >> 5));
+        ((uint8_t *)out_values)[pos] = valid ? (uint8_t)((w >> (src_row & 31)) & 1u) : 0;
+    } else {
+        ((unsigned long long *)out_values)[pos] = valid ? __ldg((const unsigned long long *)c.values + src_row) : 0ull;
+    }
+    if (out_valid) out_valid[pos] = (uint8_t)valid;
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+join_probe_kernel(const __grid_constant__ ProbeParams pp) {
+    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned long long s_cnt[K * HJ_WARPS];
+    __shared__ unsigned long long s_tile_excl;
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd(pp.ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= pp.num_tiles) break;
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K], first[K];
+        unsigned int cnt[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            cnt[j] = e < pp.n_probe ? probe_count(pp.jt, key[j], &first[j]) : 0u;
+        }
+        // ranks: warp inclusive scan of counts per j, then scan of the K*WARPS warp totals
+        unsigned long long excl_in_warp[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            unsigned long long incl = cnt[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            excl_in_warp[j] = incl - cnt[j];
+            if (lane == 31) s_cnt[j * HJ_WARPS + warp] = incl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            constexpr int N = K * HJ_WARPS; // 32
+            static_assert(N == 32, "one entry per lane");
+            const unsigned long long mine = s_cnt[lane];
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_cnt[lane] = incl - mine;
+            const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned long long excl = lookback(pp.tile_state, tile, total, lane);
+            if (lane == 0) {
+                s_tile_excl = excl;
+                if (tile == pp.num_tiles - 1) *pp.out_count = excl + total;
+            }
+        }
+        __syncthreads();
+        const unsigned long long tile_excl = s_tile_excl;
+        const int ncols = pp.n_left + pp.n_right;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (!cnt[j]) continue;
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            unsigned long long pos = tile_excl + s_cnt[j * HJ_WARPS + warp] + excl_in_warp[j];
+            unsigned long long brow = first[j];
+            for (unsigned int m = 0; m < cnt[j]; m++) {
+                if ((int64_t)pos < pp.out_cap) {
+                    for (int c = 0; c < ncols; c++) {
+                        const bool is_left = c < pp.n_left;
+                        const ColSrc &src = is_left ? pp.left[c] : pp.right[c - pp.n_left];
+                        emit_value(src, is_left ? (int64_t)brow : e, pp.out_values[c], pp.out_valid[c], (int64_t)pos);
+                    }
+                }
+                pos++;
+                if (m + 1 < cnt[j]) brow = probe_next(pp.jt, key[j], brow);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- fused join -> group-by aggregate --------------------------------------
+struct JoinAggParams {
+    JoinTable jt;
+    const unsigned long long *probe_keys;
+    int64_t n_probe;
+    ColSrc group;          // group key column
+    int32_t group_left;    // 1: taken from the build row, 0: from the probe row
+    ColSrc val[AG_MAX];
+    int32_t val_left[AG_MAX];
+};
+
+__device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
+    return !c.validity || ((__ldg(c.validity + (r >> 5)) >> (r & 31)) & 1u);
+}
+
+__device__ __forceinline__ void join_agg_match(const JoinAggParams &jp, const AggParams &ap, int64_t brow, int64_t prow) {
+    const int64_t grow = jp.group_left ? brow : prow;
+    if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
+    const unsigned long long gkey = __ldg((const unsigned long long *)jp.group.values + grow);
+    unsigned long long *rec = find_slot(ap, gkey);
+    if (!rec) { atomicOr(ap.status, DEV_ERR_TABLE_FULL); return; }
+    for (int a = 0; a < ap.n_aggs; a++) {
+        const ColSrc &c = jp.val[a];
+        const int64_t r = jp.val_left[a] ? brow : prow;
+        if (!col_valid(c, r)) continue;
+        const uint64_t bits = ap.op[a] == NQE_AGG_COUNT ? 0ull : __ldg((const unsigned long long *)c.values + r);
+        update_state(ap, a, rec, c.dtype, bits);
+    }
+}
+
+__global__ void __launch_bounds__(HJ_THREADS)
+join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_constant__ AggParams ap) {
+    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    const int64_t num_tiles = (jp.n_probe + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * TILE + threadIdx.x;
+        unsigned long long key[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < jp.n_probe ? ld_stream_u64(jp.probe_keys + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            if (e >= jp.n_probe) continue;
+            uint64_t s = nqe_mix64(key[j]) & jp.jt.mask;
+            while (true) {
+                const Slot sl = ld_slot(jp.jt.slots + s);
+                if (sl.row == EMPTY_ROW) break;
+                if (sl.key == key[j]) {
+                    join_agg_match(jp, ap, (int64_t)sl.row, e);
+                    if (!jp.jt.has_dups) break;
+                }
+                s = (s + 1) & jp.jt.mask;
+            }
+        }
+    }
+}
+
+int32_t check_join_keys(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t lk, int32_t rk) {
+    if (lk < 0 || lk >= (int)left->cols.size() || rk < 0 || rk >= (int)right->cols.size())
+        return nqe_fail(ctx, NQE_ERR_LOGICAL, "ColumnExpr must has name or idx"); // key column not found (column.rs:53-55)
+    const int ld = left->cols[lk].dtype, rd = right->cols[rk].dtype;
+    // hash_join.rs:139-162 / :185-226
+    if (ld == NQE_UTF8 || rd == NQE_UTF8)
+        return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 join keys are not implemented on the CUDA path yet");
+    if ((ld != NQE_INT64 && ld != NQE_UINT64) || (rd != NQE_INT64 && rd != NQE_UINT64))
+        return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "join key dtype must be Int64, UInt64 or Utf8");
+    if (ld != rd) return nqe_fail(ctx, NQE_ERR_PANIC, "join key dtypes differ (downcast_ref unwrap on None)");
+    return NQE_OK;
+}
+
+// build the multimap over left->cols[lk]
+int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt) {
+    const int64_t nl = left->nrows;
+    const uint64_t cap = nqe_next_pow2((uint64_t)((double)nl / 0.6) + 16);
+    void *slots = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, cap * sizeof(Slot)));
+    jt->slots = (Slot *)slots;
+    jt->mask = cap - 1;
+    jt->has_dups = 0;
+    uint32_t *status = (uint32_t *)(ctx->d_scratch + 1);
+    uint32_t *dupflag = (uint32_t *)(ctx->d_scratch + 3);
+    join_clear_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(jt->slots, cap);
+    ctx->launches++;
+    if (nl > 0) {
+        const unsigned long long *keys = (const unsigned long long *)left->cols[lk].values;
+        join_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, status);
+        join_dups_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, dupflag);
+        ctx->launches += 2;
+    }
+    cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return nqe_fail(ctx, NQE_ERR_CUDA, "join build failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if ((uint32_t)ctx->h_scratch[1] & DEV_ERR_TABLE_FULL) return nqe_fail(ctx, NQE_ERR_CUDA, "join table overflow");
+    jt->has_dups = (uint32_t)ctx->h_scratch[3] ? 1 : 0;
+    return NQE_OK;
+}
+
+void fill_src(ColSrc *s, const DevColumn &c) {
+    s->values = c.values;
+    s->validity = (const uint32_t *)c.validity;
+    s->dtype = c.dtype;
+    s->pad = 0;
+}
+
+} // namespace
+
+extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t left_key,
+                                 int32_t right_key, nqe_table **out) {
+    if (!ctx || !left || !right || !out) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    NQE_TRY(check_join_keys(ctx, left, right, left_key, right_key));
+    const int nl = (int)left->cols.size(), nr = (int)right->cols.size();
+    if (nl > HJ_MAX_COLS || nr > HJ_MAX_COLS) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "more than %d columns on one join side", HJ_MAX_COLS);
+    for (auto *t : {left, right})
+        for (auto &c : t->cols)
+            if (c.dtype == NQE_UTF8) return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 payload columns are not implemented on the CUDA join path yet");
+
+    OpTimer timer(ctx);
+    NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
+    ProbeParams pp;
+    memset(&pp, 0, sizeof pp);
+    int32_t rc = build_table(ctx, left, left_key, &pp.jt);
+    pp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
+    pp.n_probe = right->nrows;
+    pp.n_left = nl;
+    pp.n_right = nr;
+    for (int c = 0; c < nl; c++) fill_src(&pp.left[c], left->cols[c]);
+    for (int c = 0; c < nr; c++) fill_src(&pp.right[c], right->cols[c]);
+    constexpr int TILE = HJ_K * HJ_THREADS;
+    pp.num_tiles = (int32_t)((pp.n_probe + TILE - 1) / TILE);
+    void *lb = nullptr;
+    if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, &lb, (size_t)(pp.num_tiles + 1) * 8);
+    pp.tile_state = (unsigned long long *)lb;
+    pp.out_count = (unsigned long long *)ctx->d_scratch;
+    pp.ticket = (unsigned int *)(ctx->d_scratch + 2);
+
+    nqe_table *t = nullptr;
+    int64_t cap = pp.n_probe > 0 ? pp.n_probe : 1;
+    int64_t out_rows = 0;
+    std::vector<uint8_t *> bool_bytes, valid_bytes;
+    for (int attempt = 0; rc == NQE_OK && attempt < 2; attempt++) {
+        nqe_table_new(ctx, 0, &t);
+        t->cols.resize(nl + nr);
+        bool_bytes.assign(nl + nr, nullptr);
+        valid_bytes.assign(nl + nr, nullptr);
+        pp.out_cap = cap;
+        for (int c = 0; c < nl + nr && rc == NQE_OK; c++) {
+            const DevColumn &src = c < nl ? left->cols[c] : right->cols[c - nl];
+            rc = nqe_column_alloc(ctx, src.dtype, cap, src.validity != nullptr, &t->cols[c]);
+            if (rc != NQE_OK) break;
+            if (src.dtype == NQE_BOOL) {
+                rc = nqe_dev_alloc(ctx, (void **)&bool_bytes[c], (size_t)cap + 64);
+                pp.out_values[c] = bool_bytes[c];
+            } else {
+                pp.out_values[c] = t->cols[c].values;
+            }
+            pp.out_valid[c] = nullptr;
+            if (rc == NQE_OK && src.validity) {
+                rc = nqe_dev_alloc(ctx, (void **)&valid_bytes[c], (size_t)cap + 64);
+                pp.out_valid[c] = valid_bytes[c];
+            }
+        }
+        if (rc == NQE_OK) {
+            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
+            if (pp.num_tiles > 0) {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_probe_kernel, HJ_THREADS, 0);
+                int grid = ctx->sm_count * (occ > 0 ? occ : 1);
+                if (grid > pp.num_tiles) grid = pp.num_tiles;
+                join_probe_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pp);
+                ctx->launches++;
+            }
+            cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                rc = nqe_fail(ctx, NQE_ERR_CUDA, "join probe failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (rc != NQE_OK) break;
+        out_rows = (int64_t)ctx->h_scratch[0];
+        if (out_rows <= cap) break;
+        // output larger than the first guess (duplicate build keys): exact size is now known
+        for (auto p : bool_bytes) nqe_dev_free(ctx, p);
+        for (auto p : valid_bytes) nqe_dev_free(ctx, p);
+        nqe_table_free(t);
+        t = nullptr;
+        cap = out_rows;
+    }
+    if (rc == NQE_OK) {
+        bool any = false;
+        cudaMemsetAsync(ctx->d_scratch + 8, 0, 32 * sizeof(uint64_t), ctx->stream);
+        for (int c = 0; c < nl + nr && rc == NQE_OK; c++) {
+            if (bool_bytes[c]) { rc = nqe_pack_bytes(ctx, bool_bytes[c], out_rows, (uint32_t *)t->cols[c].values, nullptr); any = true; }
+            if (rc == NQE_OK && valid_bytes[c]) {
+                rc = nqe_pack_bytes(ctx, valid_bytes[c], out_rows, (uint32_t *)t->cols[c].validity,
+                                    (unsigned long long *)(ctx->d_scratch + 8 + c));
+                any = true;
+            }
+        }
+        if (rc == NQE_OK && any) {
+            cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "pack kernel failed");
+        }
+    }
+    timer.stop();
+    for (auto p : bool_bytes) nqe_dev_free(ctx, p);
+    for (auto p : valid_bytes) nqe_dev_free(ctx, p);
+    nqe_dev_free(ctx, lb);
+    nqe_dev_free(ctx, pp.jt.slots);
+    if (rc != NQE_OK) {
+        if (t) nqe_table_free(t);
+        return rc;
+    }
+    t->nrows = out_rows;
+    for (int c = 0; c < nl + nr; c++) {
+        DevColumn &col = t->cols[c];
+        col.length = out_rows;
+        if (col.validity) {
+            col.null_count = (int64_t)ctx->h_scratch[8 + c];
+            if (col.null_count == 0) { // arrow `take`: no nulls selected => no bitmap
+                nqe_dev_free(ctx, col.validity);
+                col.validity = nullptr;
+            }
+        }
+    }
+    *out = t;
+    return NQE_OK;
+}
+
+extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t left_key,
+                                      int32_t right_key, int32_t group_column, const nqe_agg *aggs, int32_t n_aggs,
+                                      nqe_table **out) {
+    if (!ctx || !left || !right || !out || (!aggs && n_aggs > 0)) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    NQE_TRY(check_join_keys(ctx, left, right, left_key, right_key));
+    const int nl = (int)left->cols.size(), nr = (int)right->cols.size();
+    auto col_at = [&](int c) -> const DevColumn * {
+        if (c < 0 || c >= nl + nr) return nullptr;
+        return c < nl ? &left->cols[c] : &right->cols[c - nl];
+    };
+    const DevColumn *g = col_at(group_column);
+    if (!g) return nqe_fail(ctx, NQE_ERR_PANIC, "group column index %d out of range", group_column);
+    if (g->dtype != NQE_INT64 && g->dtype != NQE_UINT64) {
+        if (g->dtype == NQE_UTF8) return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 group keys are not implemented on the CUDA path yet");
+        return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "group by only support by `Int64`, `UInt64`, `String`");
+    }
+    if (n_aggs > AG_MAX) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "at most %d aggregates per plan", AG_MAX);
+    JoinAggParams jp;
+    memset(&jp, 0, sizeof jp);
+    AggParams ap;
+    memset(&ap, 0, sizeof ap);
+    int32_t dts[AG_MAX];
+    for (int a = 0; a < n_aggs; a++) {
+        const DevColumn *c = col_at(aggs[a].column);
+        if (!c) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", aggs[a].column);
+        dts[a] = c->dtype;
+        fill_src(&jp.val[a], *c);
+        jp.val_left[a] = aggs[a].column < nl;
+    }
+    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, true, &ap));
+    fill_src(&jp.group, *g);
+    jp.group_left = group_column < nl;
+    ap.n_rows = right->nrows;
+    ap.status = (uint32_t *)(ctx->d_scratch + 1);
+
+    OpTimer timer(ctx);
+    NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
+    int32_t rc = build_table(ctx, left, left_key, &jp.jt);
+    jp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
+    jp.n_probe = right->nrows;
+    nqe_table *t;
+    nqe_table_new(ctx, 0, &t);
+    // groups come from one column of one side: at most that side's row count
+    const int64_t side_rows = jp.group_left ? left->nrows : right->nrows;
+    uint64_t capacity = nqe_agg_capacity((double)(side_rows < (1 << 20) ? side_rows : (1 << 20)));
+    for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
+        cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+        rc = nqe_agg_table_create(ctx, &ap, capacity);
+        if (rc != NQE_OK) break;
+        if (jp.n_probe > 0) {
+            const int64_t tiles = (jp.n_probe + HJ_K * HJ_THREADS - 1) / (HJ_K * HJ_THREADS);
+            int grid = ctx->sm_count * 8;
+            if (grid > tiles) grid = (int)tiles;
+            join_aggregate_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
+            ctx->launches++;
+        }
+        cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = nqe_fail(ctx, NQE_ERR_CUDA, "join-aggregate kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (!((uint32_t)ctx->h_scratch[1] & DEV_ERR_TABLE_FULL)) break;
+        nqe_dev_free(ctx, ap.table);
+        ap.table = nullptr;
+        capacity *= 8;
+        if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
+    }
+    if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, false, side_rows + 1, t);
+    timer.stop();
+    nqe_dev_free(ctx, ap.table);
+    nqe_dev_free(ctx, jp.jt.slots);
+    if (rc != NQE_OK) {
+        nqe_table_free(t);
+        return rc;
+    }
+    *out = t;
+    return NQE_OK;
+}

@@ -1,0 +1,276 @@
+// misc.cu -- row slicing (PhysicalLimitPlan / PhysicalOffsetPlan), key-radix
+// partitioning for the multi-GPU shuffle, and on-device synthetic columns.
+#include <cstring>
+
+#include "hash_common.cuh"
+#include "nqe_internal.cuh"
+
+namespace {
+
+// dst bit i = src bit (i + shift), i < n
+__global__ void bitmap_slice_kernel(const uint32_t *__restrict__ src, int64_t shift, int64_t n, uint32_t *__restrict__ dst,
+                                    unsigned long long *zeros) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nwords = (n + 31) / 32;
+    unsigned int z = 0;
+    if (w < nwords) {
+        const int64_t b = w * 32 + shift;
+        const int64_t rem = n - w * 32;
+        const int64_t last = b + (rem < 32 ? rem : 32) - 1;
+        const uint32_t lo = src[b >> 5], hi = (last >> 5) != (b >> 5) ? src[(b >> 5) + 1] : 0u;
+        uint32_t v = (b & 31) ? (lo >> (b & 31)) | (hi << (32 - (b & 31))) : lo;
+        if (rem < 32) v &= (1u << rem) - 1u;
+        dst[w] = v;
+        z = (unsigned)(rem < 32 ? rem : 32) - __popc(v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (zeros && (threadIdx.x & 31) == 0 && z) atomicAdd(zeros, (unsigned long long)z);
+}
+
+__global__ void utf8_rebase_kernel(const int32_t *__restrict__ src, int64_t n_plus_1, int32_t base, int32_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_plus_1) dst[i] = src[i] - base;
+}
+
+constexpr int MAX_PARTS = 64;
+
+struct PartParams {
+    const unsigned long long *keys;
+    int64_t n;
+    int32_t n_parts;
+    int32_t n_cols;
+    const unsigned long long *in[16];
+    unsigned long long *out[16];
+    unsigned long long *counts;  // [n_parts]
+    unsigned long long *cursors; // [n_parts] running write positions (start at exclusive prefix)
+};
+
+__device__ __forceinline__ int part_of(unsigned long long key, int n_parts) { return (int)(nqe_mix64(key) % (unsigned)n_parts); }
+
+__global__ void part_hist_kernel(PartParams pp) {
+    __shared__ unsigned int h[MAX_PARTS];
+    if (threadIdx.x < MAX_PARTS) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pp.n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[part_of(pp.keys[i], pp.n_parts)], 1u);
+    __syncthreads();
+    if (threadIdx.x < pp.n_parts && h[threadIdx.x]) atomicAdd(pp.counts + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+}
+
+// Block-local counting sort of a tile by destination, then each destination's
+// run is copied out with consecutive threads writing consecutive rows.
+constexpr int PT_THREADS = 256;
+constexpr int PT_K = 8;
+__global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(PartParams pp) {
+    constexpr int TILE = PT_THREADS * PT_K;
+    __shared__ unsigned int s_cnt[MAX_PARTS], s_start[MAX_PARTS];
+    __shared__ unsigned long long s_base[MAX_PARTS];
+    __shared__ unsigned int s_src[TILE];   // tile-local source row, ordered by destination
+    const int tid = threadIdx.x;
+    const int64_t num_tiles = (pp.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TILE;
+        if (tid < MAX_PARTS) s_cnt[tid] = 0;
+        __syncthreads();
+        int dest[PT_K];
+        unsigned int rank[PT_K];
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            const int64_t e = base + j * PT_THREADS + tid;
+            dest[j] = e < pp.n ? part_of(pp.keys[e], pp.n_parts) : -1;
+            if (dest[j] >= 0) rank[j] = atomicAdd(&s_cnt[dest[j]], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int run = 0;
+            for (int p = 0; p < pp.n_parts; p++) {
+                s_start[p] = run;
+                run += s_cnt[p];
+            }
+        }
+        if (tid < pp.n_parts && s_cnt[tid]) s_base[tid] = atomicAdd(pp.cursors + tid, (unsigned long long)s_cnt[tid]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PT_K; j++)
+            if (dest[j] >= 0) s_src[s_start[dest[j]] + rank[j]] = (unsigned)(j * PT_THREADS + tid) | ((unsigned)dest[j] << 24);
+        __syncthreads();
+        const int64_t n_here = pp.n - base < TILE ? pp.n - base : TILE;
+        for (int i = tid; i < n_here; i += PT_THREADS) {
+            const unsigned int v = s_src[i];
+            const int p = (int)(v >> 24);
+            const unsigned int local = v & 0xffffffu;
+            const unsigned long long dst = s_base[p] + (unsigned)(i - s_start[p]);
+            for (int c = 0; c < pp.n_cols; c++) pp.out[c][dst] = pp.in[c][base + local];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void synth_kernel(int kind, uint64_t seed, int64_t start, int64_t n, uint64_t a, uint64_t b, double scale,
+                             unsigned long long *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = (uint64_t)(start + i);
+        unsigned long long v;
+        if (kind == 0) v = nqe_splitmix(seed + g) % a;
+        else if (kind == 1) v = (unsigned long long)__double_as_longlong(scale * ((double)(nqe_splitmix(seed + g) >> 11) * 0x1.0p-53));
+        else v = (unsigned long long)(((unsigned __int128)g * a) % b);
+        out[i] = v;
+    }
+}
+
+} // namespace
+
+extern "C" int32_t nqe_synth_column(nqe_ctx *ctx, int32_t kind, uint64_t seed, int64_t start, int64_t n,
+                                    uint64_t mod_or_mul, uint64_t mod2, double scale, void *device_out) {
+    if (!ctx || !device_out || n < 0 || kind < 0 || kind > 2) return NQE_ERR_INVALID_ARG;
+    if ((kind == 0 && mod_or_mul == 0) || (kind == 2 && mod2 == 0)) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "zero modulus");
+    cudaSetDevice(ctx->device);
+    if (n == 0) return NQE_OK;
+    int grid = ctx->sm_count * 8;
+    synth_kernel<<<grid, 256, 0, ctx->stream>>>(kind, seed, start, n, mod_or_mul, mod2, scale, (unsigned long long *)device_out);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
+
+extern "C" int32_t nqe_table_slice(nqe_ctx *ctx, const nqe_table *t, int64_t offset, int64_t len, nqe_table **out) {
+    if (!ctx || !t || !out) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    // RecordBatch::slice semantics used by offset.rs:30-51 / limit.rs:32-49 after clamping
+    if (offset < 0) offset = 0;
+    if (offset > t->nrows) offset = t->nrows;
+    if (len < 0) len = 0;
+    if (offset + len > t->nrows) len = t->nrows - offset;
+    nqe_table *r;
+    nqe_table_new(ctx, len, &r);
+    r->cols.resize(t->cols.size());
+    int32_t rc = NQE_OK;
+    cudaMemsetAsync(ctx->d_scratch + 8, 0, 32 * sizeof(uint64_t), ctx->stream);
+    bool any_valid = false;
+    for (size_t i = 0; i < t->cols.size() && rc == NQE_OK; i++) {
+        const DevColumn &s = t->cols[i];
+        DevColumn &d = r->cols[i];
+        rc = nqe_column_alloc(ctx, s.dtype, len, s.validity != nullptr, &d);
+        if (rc != NQE_OK) break;
+        const unsigned grid = (unsigned)(((len + 31) / 32 + 255) / 256);
+        if (s.dtype == NQE_BOOL) {
+            if (len) bitmap_slice_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t *)s.values, offset, len, (uint32_t *)d.values, nullptr);
+        } else if (s.dtype == NQE_UTF8) {
+            int32_t ends[2] = {0, 0};
+            cudaMemcpyAsync(&ends[0], (const int32_t *)s.values + offset, 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(&ends[1], (const int32_t *)s.values + offset + len, 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            d.data_bytes = ends[1] - ends[0];
+            rc = nqe_dev_alloc(ctx, (void **)&d.data, (size_t)d.data_bytes + 64);
+            if (rc != NQE_OK) break;
+            utf8_rebase_kernel<<<(unsigned)((len + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int32_t *)s.values + offset, len + 1, ends[0], (int32_t *)d.values);
+            if (d.data_bytes) cudaMemcpyAsync(d.data, s.data + ends[0], (size_t)d.data_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        } else if (len) {
+            cudaMemcpyAsync(d.values, (const uint64_t *)s.values + offset, (size_t)len * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        if (s.validity && len) {
+            bitmap_slice_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t *)s.validity, offset, len, (uint32_t *)d.validity,
+                                                               (unsigned long long *)(ctx->d_scratch + 8 + (i & 31)));
+            any_valid = true;
+        }
+        ctx->launches++;
+    }
+    if (rc == NQE_OK && cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "slice failed");
+    if (rc == NQE_OK && any_valid) {
+        cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "slice failed");
+    }
+    if (rc != NQE_OK) {
+        nqe_table_free(r);
+        return rc;
+    }
+    for (size_t i = 0; i < r->cols.size(); i++) {
+        DevColumn &d = r->cols[i];
+        if (d.validity) {
+            d.null_count = len ? (int64_t)ctx->h_scratch[8 + (i & 31)] : 0;
+            if (d.null_count == 0) {
+                nqe_dev_free(ctx, d.validity);
+                d.validity = nullptr;
+            }
+        }
+    }
+    *out = r;
+    return NQE_OK;
+}
+
+extern "C" int32_t nqe_radix_partition(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts,
+                                       nqe_table **out, int64_t *counts) {
+    if (!ctx || !in || !out || !counts) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    if (n_parts < 1 || n_parts > MAX_PARTS) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "n_parts must be in [1,%d]", MAX_PARTS);
+    if (key_column < 0 || key_column >= (int)in->cols.size()) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad key column");
+    if (in->cols.size() > 16) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "more than 16 columns");
+    const int kd = in->cols[key_column].dtype;
+    if (kd != NQE_INT64 && kd != NQE_UINT64) return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "partition key must be Int64/UInt64");
+    for (auto &c : in->cols)
+        if (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8 || c.validity)
+            return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "radix partition supports NULL-free 8-byte columns only");
+    const int64_t n = in->nrows;
+    nqe_table *t;
+    nqe_table_new(ctx, n, &t);
+    t->cols.resize(in->cols.size());
+    PartParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.keys = (const unsigned long long *)in->cols[key_column].values;
+    pp.n = n;
+    pp.n_parts = n_parts;
+    pp.n_cols = (int)in->cols.size();
+    int32_t rc = NQE_OK;
+    for (int c = 0; c < pp.n_cols && rc == NQE_OK; c++) {
+        rc = nqe_column_alloc(ctx, in->cols[c].dtype, n, false, &t->cols[c]);
+        pp.in[c] = (const unsigned long long *)in->cols[c].values;
+        pp.out[c] = (unsigned long long *)t->cols[c].values;
+    }
+    OpTimer timer(ctx);
+    unsigned long long *d_counts = (unsigned long long *)ctx->d_scratch; // 64 words
+    pp.counts = d_counts;
+    if (rc == NQE_OK) {
+        cudaMemsetAsync(d_counts, 0, 64 * sizeof(uint64_t), ctx->stream);
+        if (n > 0) {
+            int grid = ctx->sm_count * 8;
+            part_hist_kernel<<<grid, 256, 0, ctx->stream>>>(pp);
+            ctx->launches++;
+        }
+        cudaMemcpyAsync(ctx->h_scratch, d_counts, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partition histogram failed");
+    }
+    if (rc == NQE_OK) {
+        uint64_t run = 0;
+        for (int p = 0; p < n_parts; p++) {
+            counts[p] = (int64_t)ctx->h_scratch[p];
+            ctx->h_scratch[p] = run; // exclusive prefix = initial cursor
+            run += (uint64_t)counts[p];
+        }
+        void *cur = nullptr;
+        rc = nqe_dev_alloc(ctx, &cur, 64 * sizeof(uint64_t));
+        if (rc == NQE_OK) {
+            // h_scratch is pinned; the copy is ordered before the kernel on the stream
+            cudaMemcpyAsync(cur, ctx->h_scratch, 64 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+            pp.cursors = (unsigned long long *)cur;
+            if (n > 0) {
+                const int64_t tiles = (n + PT_THREADS * PT_K - 1) / (PT_THREADS * PT_K);
+                int grid = ctx->sm_count * 4;
+                if (grid > tiles) grid = (int)tiles;
+                part_scatter_kernel<<<grid, PT_THREADS, 0, ctx->stream>>>(pp);
+                ctx->launches++;
+            }
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partition scatter failed");
+            nqe_dev_free(ctx, cur);
+        }
+    }
+    timer.stop();
+    if (rc != NQE_OK) {
+        nqe_table_free(t);
+        return rc;
+    }
+    *out = t;
+    return NQE_OK;
+}

@@ -1,0 +1,204 @@
+"""Device-side tables: Arrow RecordBatch <-> HBM through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import pyarrow as pa
+
+from . import _ffi
+from ._ffi import BOOL, FLOAT64, INT64, UINT64, UTF8, ColumnDesc, NqeError
+
+_PA_TO_NQE = {pa.bool_(): BOOL, pa.int64(): INT64, pa.uint64(): UINT64, pa.float64(): FLOAT64, pa.utf8(): UTF8}
+_NQE_TO_PA = {v: k for k, v in _PA_TO_NQE.items()}
+
+
+def nqe_dtype(t: pa.DataType) -> int:
+    if t == pa.large_utf8():
+        raise NqeError(4, "LargeUtf8 is not an arrow type the reference produces")
+    try:
+        return _PA_TO_NQE[t]
+    except KeyError:
+        # reference: `_ => unimplemented!()` in selection.rs:98 / binary.rs:86
+        raise NqeError(5, f"not implemented: data type {t}")
+
+
+class Context:
+    """One nqe_ctx: one GPU, one stream.  `Context.default()` is created lazily."""
+
+    _default: Optional["Context"] = None
+
+    def __init__(self, device: int = 0):
+        self.lib = _ffi.load()
+        h = C.c_void_p()
+        rc = self.lib.nqe_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise NqeError(rc, "nqe_ctx_create failed: no usable CUDA device (the CUDA path is the only path)")
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context(0)
+        return cls._default
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise NqeError(rc, self.lib.nqe_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self.check(self.lib.nqe_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self.check(self.lib.nqe_ctx_sync(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.lib.nqe_ctx_kernel_launches(self.h)
+
+    @property
+    def last_op_ms(self) -> float:
+        return self.lib.nqe_ctx_last_op_ms(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.nqe_ctx_destroy(self.h)
+            self.h = None
+
+
+def _normalise(arr: pa.Array) -> pa.Array:
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+    if arr.offset != 0:
+        arr = pa.concat_arrays([arr.slice(0, 0), arr])  # re-materialise at offset 0
+        if arr.offset != 0:
+            arr = pa.array(arr.to_pylist(), type=arr.type)
+    return arr
+
+
+class DeviceTable:
+    """A RecordBatch resident in HBM (nqe_table) plus its field names."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p, names: Sequence[str], keepalive=None):
+        self.ctx = ctx
+        self.h = handle
+        self.names = list(names)
+        self._keep = keepalive
+
+    # ---- construction ----------------------------------------------------
+    @classmethod
+    def from_arrow(cls, batch, ctx: Optional[Context] = None) -> "DeviceTable":
+        """Upload a pyarrow RecordBatch / Table (pin + DMA, nqe_table_upload)."""
+        ctx = ctx or Context.default()
+        if isinstance(batch, pa.Table):
+            batch = batch.combine_chunks()
+            arrays = [_normalise(batch.column(i)) for i in range(batch.num_columns)]
+        else:
+            arrays = [_normalise(batch.column(i)) for i in range(batch.num_columns)]
+        names = list(batch.schema.names)
+        n = len(arrays)
+        descs = (ColumnDesc * max(n, 1))()
+        for i, a in enumerate(arrays):
+            dt = nqe_dtype(a.type)
+            bufs = a.buffers()
+            d = descs[i]
+            d.dtype = dt
+            d.length = len(a)
+            d.null_count = a.null_count
+            d.validity = bufs[0].address if (bufs[0] is not None and a.null_count) else None
+            if dt == UTF8:
+                d.values = bufs[1].address if bufs[1] is not None else None
+                d.data = bufs[2].address if len(bufs) > 2 and bufs[2] is not None else None
+                d.data_bytes = bufs[2].size if len(bufs) > 2 and bufs[2] is not None else 0
+                if d.values is None:  # empty array
+                    zero = np.zeros(1, dtype=np.int32)
+                    arrays.append(zero)
+                    d.values = zero.ctypes.data
+            else:
+                d.values = bufs[1].address if bufs[1] is not None else None
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_table_upload(ctx.h, descs, n, C.byref(h)))
+        return cls(ctx, h, names)
+
+    @classmethod
+    def from_device_pointers(cls, ctx: Context, names: Sequence[str], dtypes: Sequence[int], ptrs: Sequence[int],
+                             nrows: int, keepalive=None) -> "DeviceTable":
+        """Wrap NULL-free 8-byte device columns owned by the caller (e.g. torch tensors)."""
+        n = len(ptrs)
+        descs = (ColumnDesc * max(n, 1))()
+        for i in range(n):
+            descs[i].dtype = dtypes[i]
+            descs[i].length = nrows
+            descs[i].null_count = 0
+            descs[i].values = ptrs[i]
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_table_from_device(ctx.h, descs, n, C.byref(h)))
+        return cls(ctx, h, names, keepalive)
+
+    # ---- inspection ------------------------------------------------------
+    @property
+    def num_rows(self) -> int:
+        return self.ctx.lib.nqe_table_num_rows(self.h)
+
+    @property
+    def num_columns(self) -> int:
+        return self.ctx.lib.nqe_table_num_columns(self.h)
+
+    def column_desc(self, i: int) -> ColumnDesc:
+        d = ColumnDesc()
+        self.ctx.check(self.ctx.lib.nqe_table_column(self.h, i, C.byref(d)))
+        return d
+
+    def dtypes(self) -> List[int]:
+        return [self.column_desc(i).dtype for i in range(self.num_columns)]
+
+    def schema(self) -> pa.Schema:
+        return pa.schema([pa.field(nm, _NQE_TO_PA[dt]) for nm, dt in zip(self.names, self.dtypes())])
+
+    # ---- download --------------------------------------------------------
+    def to_arrow(self) -> pa.RecordBatch:
+        n = self.num_rows
+        arrays = []
+        lib = self.ctx.lib
+        for i in range(self.num_columns):
+            d = self.column_desc(i)
+            t = _NQE_TO_PA[d.dtype]
+            has_valid = bool(d.validity) and d.null_count != 0
+            vbytes = (n + 7) // 8
+            valid = np.empty(max(vbytes, 1), dtype=np.uint8) if has_valid else None
+            if d.dtype == UTF8:
+                offs = np.empty(n + 1, dtype=np.int32)
+                data = np.empty(max(d.data_bytes, 1), dtype=np.uint8)
+                self.ctx.check(lib.nqe_table_download_column(
+                    self.ctx.h, self.h, i, offs.ctypes.data, offs.nbytes,
+                    valid.ctypes.data if has_valid else None, valid.nbytes if has_valid else 0,
+                    data.ctypes.data, data.nbytes))
+                bufs = [pa.py_buffer(valid) if has_valid else None, pa.py_buffer(offs), pa.py_buffer(data[:d.data_bytes])]
+            else:
+                nbytes = vbytes if d.dtype == BOOL else n * 8
+                vals = np.empty(max(nbytes, 1), dtype=np.uint8)
+                self.ctx.check(lib.nqe_table_download_column(
+                    self.ctx.h, self.h, i, vals.ctypes.data, vals.nbytes,
+                    valid.ctypes.data if has_valid else None, valid.nbytes if has_valid else 0, None, 0))
+                bufs = [pa.py_buffer(valid) if has_valid else None, pa.py_buffer(vals[:nbytes])]
+            arrays.append(pa.Array.from_buffers(t, n, bufs, null_count=d.null_count if has_valid else 0))
+        return pa.RecordBatch.from_arrays(arrays, schema=pa.schema(
+            [pa.field(nm, a.type) for nm, a in zip(self.names, arrays)]))
+
+    def slice(self, offset: int, length: int) -> "DeviceTable":
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.nqe_table_slice(self.ctx.h, self.h, offset, length, C.byref(h)))
+        return DeviceTable(self.ctx, h, self.names)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.nqe_table_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

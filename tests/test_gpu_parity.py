@@ -1,0 +1,387 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs, and against the committed golden fixtures.
+
+Bar: bit-exact for integer / boolean / index columns, for f64 arithmetic
+(+,-,*,/ are IEEE-exact) and for min/max; sum/avg within 1e-9 relative
+(north_star); sin/cos within 4 ulp of glibc (CUDA libdevice is not correctly
+rounded -- the reference's sin vector is bit-exact against glibc only)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import gpu_helpers as G
+from tests.helpers import assert_rows, fixtures, golden_table
+
+pytestmark = pytest.mark.gpu
+FX = fixtures()["cases"]
+SUM_REL = 1e-9
+
+
+def lit(v):
+    return ("lit", "i64", v)
+
+
+def numeric_only(b: O.Batch) -> O.Batch:
+    keep = [i for i, c in enumerate(b.cols) if c.dtype != "utf8"]
+    return O.Batch([b.names[i] for i in keep], [b.cols[i] for i in keep])
+
+
+def rand_col(rng, dtype, n, null_frac=0.0, lo=-50, hi=50):
+    if dtype == "i64":
+        v = rng.integers(lo, hi, n).astype(np.int64)
+    elif dtype == "u64":
+        v = rng.integers(0, hi, n).astype(np.uint64)
+    elif dtype == "f64":
+        v = np.round(rng.normal(0, 10, n), 3)
+    else:
+        v = rng.integers(0, 2, n).astype(np.uint8)
+    valid = None
+    if null_frac > 0:
+        valid = (rng.random(n) >= null_frac).astype(np.uint8)
+    return O.Col(dtype, v, valid)
+
+
+def same(a: O.Batch, b: O.Batch, rel=0.0, ordered=True):
+    assert [c.dtype for c in a.cols] == [c.dtype for c in b.cols]
+    assert_rows([list(r) for r in a.rows()], [list(r) for r in b.rows()], rel=rel, ordered=ordered)
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_golden_projection_vector():  # projection.rs:88-121 (numeric columns)
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_projection(t1, [("bin", "Plus", ("col", 0), lit(1))])
+    assert out.cols[0].to_pylist() == FX["test_projection"]["id_plus_1"]
+
+
+def test_golden_selection_vector():  # selection.rs:126-178
+    t1 = numeric_only(golden_table("t1"))
+    pred = ("bin", "Gt", ("bin", "Plus", ("col", 0), lit(1)), lit(5))
+    out = G.gpu_selection(t1, pred)
+    assert out.cols[0].to_pylist() == FX["test_selection"]["id"]
+
+
+def test_golden_sql_where():  # sql/planner.rs:664-680
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_projection(t1, [("col", 0), ("col", 1)], pred=("bin", "Gt", ("col", 0), lit(1)))
+    assert out.cols[0].to_pylist() == FX["sql_where_id_gt_1"]["id"]
+    assert out.cols[1].to_pylist() == FX["sql_where_id_gt_1"]["age"]
+
+
+def test_golden_config1():  # BASELINE.json configs[0]
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_projection(t1, [("col", 0), ("bin", "Plus", ("col", 1), lit(100))],
+                           pred=("bin", "Lt", ("col", 0), lit(9)), names=FX["config1"]["names"])
+    assert [list(r) for r in out.rows()] == FX["config1"]["rows"]
+
+
+def test_golden_abs_sin():  # unary.rs:123-170
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_projection(t1, [("un", "abs", ("col", 2)), ("un", "sin", ("col", 2))])
+    assert out.cols[0].to_pylist() == FX["test_abs_expression"]["score"]
+    for got, want in zip(out.cols[1].to_pylist(), FX["test_sin_expression"]["score"]):
+        assert abs(got - want) <= 4 * math.ulp(want)
+
+
+def test_golden_readme_groupby():  # README.md:105-111
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_aggregate(t1, ("bin", "Modulos", ("col", 0), lit(3)),
+                          [("count", 0), ("sum", 1), ("sum", 2), ("avg", 2), ("max", 2), ("min", 2)])
+    assert out.names == FX["readme_groupby"]["names"]
+    assert_rows([list(r) for r in out.rows()], FX["readme_groupby"]["rows"], rel=SUM_REL, ordered=False)
+
+
+def test_golden_readme_join_numeric_part():  # README.md:77-85 (ids and key columns; strings are a later row)
+    emp, rank, dept = (numeric_only(golden_table(n)) for n in ("employee", "rank", "department"))
+    j1 = G.gpu_join(emp, rank, "rank", "id")
+    want1 = O.hash_join(emp, rank, "rank", "id")
+    same(j1, want1)
+    j2 = G.gpu_join(j1, dept, "department_id", "id")
+    assert j2.cols[0].to_pylist() == [r[0] for r in FX["readme_join"]["rows"]]
+
+
+# ---------------------------------------------------------------- filter / project
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 2047, 2048, 2049, 100_003])
+@pytest.mark.parametrize("null_frac", [0.0, 0.2])
+def test_filter_project_random(n, null_frac):
+    rng = np.random.default_rng(n * 7 + int(null_frac * 10))
+    b = O.Batch(["a", "b", "x", "f"], [rand_col(rng, "i64", n, null_frac), rand_col(rng, "i64", n, null_frac),
+                                      rand_col(rng, "f64", n, null_frac), rand_col(rng, "bool", n, null_frac)])
+    pred = ("bin", "Or", ("bin", "Lt", ("col", 0), lit(10)), ("bin", "And", ("col", 3), ("bin", "GtEq", ("col", 2), ("lit", "f64", 1.5))))
+    exprs = [("col", 0), ("bin", "Plus", ("col", 1), lit(100)), ("bin", "Multiply", ("col", 2), ("lit", "f64", 0.5)),
+             ("col", 3), ("bin", "Minus", ("bin", "Multiply", ("col", 0), ("col", 1)), ("bin", "Plus", ("col", 1), lit(7))),
+             ("bin", "NotEq", ("col", 0), ("col", 1))]
+    want = O.projection(O.selection(b, pred), exprs)
+    got = G.gpu_projection(b, exprs, pred=pred)
+    same(got, want)
+    # bare SelectionPlan (all columns pass through) and bare ProjectionPlan
+    same(G.gpu_selection(b, pred), O.selection(b, pred))
+    same(G.gpu_projection(b, exprs), O.projection(b, exprs))
+
+
+@pytest.mark.parametrize("sel", ["none", "all"])
+def test_filter_all_or_nothing(sel):
+    rng = np.random.default_rng(5)
+    n = 10_000
+    b = O.Batch(["a", "x"], [rand_col(rng, "i64", n), rand_col(rng, "f64", n)])
+    pred = ("bin", "Lt", ("col", 0), lit(-1000 if sel == "none" else 1000))
+    same(G.gpu_selection(b, pred), O.selection(b, pred))
+
+
+OPS_CMP = ["Eq", "NotEq", "Lt", "LtEq", "Gt", "GtEq"]
+OPS_ARITH = ["Plus", "Minus", "Multiply", "Divide", "Modulos"]
+
+
+@pytest.mark.parametrize("dtype", ["i64", "u64", "f64"])
+def test_every_operator(dtype):
+    rng = np.random.default_rng(11)
+    n = 5000
+    a = rand_col(rng, dtype, n, 0.1)
+    bvals = rand_col(rng, dtype, n, 0.1)
+    # non-zero divisors (zero divisors are covered by the error test)
+    if dtype == "f64":
+        bvals.values[bvals.values == 0.0] = 1.25
+        a.values[:5] = [float("nan"), float("inf"), -float("inf"), 0.0, -0.0]
+    else:
+        bvals.values[bvals.values == 0] = 3
+    b = O.Batch(["a", "b"], [a, bvals])
+    exprs = [("bin", op, ("col", 0), ("col", 1)) for op in OPS_CMP + OPS_ARITH]
+    same(G.gpu_projection(b, exprs), O.projection(b, exprs))
+    edge = {"i64": [2**63 - 1, -2**63, -1, 0, 1], "u64": [2**64 - 1, 0, 1, 2**63, 5], "f64": [1e308, -1e308, 5e-324, 0.1, 3.0]}[dtype]
+    e = O.Batch(["a", "b"], [O.col(dtype, edge), O.col(dtype, list(reversed(edge)))])
+    exprs = [("bin", op, ("col", 0), ("col", 1)) for op in OPS_CMP + ["Plus", "Minus", "Multiply"]]
+    same(G.gpu_projection(e, exprs), O.projection(e, exprs))
+
+
+def test_kleene_and_bool_compare():
+    T, F, N = True, False, None
+    b = O.Batch(["a", "b"], [O.col("bool", [T, T, T, F, F, F, N, N, N]), O.col("bool", [T, F, N, T, F, N, T, F, N])])
+    exprs = [("bin", "And", ("col", 0), ("col", 1)), ("bin", "Or", ("col", 0), ("col", 1)),
+             ("bin", "Eq", ("col", 0), ("col", 1)), ("bin", "Lt", ("col", 0), ("col", 1)),
+             ("bin", "And", ("col", 0), ("lit", "bool", None)), ("bin", "Or", ("col", 0), ("lit", "bool", True))]
+    same(G.gpu_projection(b, exprs), O.projection(b, exprs))
+
+
+def test_null_predicate_rows_kept_as_null_rows():  # selection.rs:46
+    b = O.Batch(["a", "b"], [O.col("i64", [1, None, 3, 4]), O.col("f64", [1.5, 2.5, None, 4.5])])
+    pred = ("bin", "Gt", ("col", 0), lit(2))
+    got = G.gpu_selection(b, pred)
+    assert got.rows() == [(None, None), (3, None), (4, 4.5)]
+    exprs = [("bin", "Plus", ("col", 0), lit(1)), ("lit", "i64", 5)]
+    same(G.gpu_projection(b, exprs, pred=pred), O.projection(O.selection(b, pred), exprs))
+
+
+def test_deep_expression_uses_stack():
+    rng = np.random.default_rng(3)
+    n = 3000
+    b = O.Batch(["a", "b", "c"], [rand_col(rng, "i64", n), rand_col(rng, "i64", n, 0.1), rand_col(rng, "i64", n)])
+    e = ("bin", "Minus", lit(5), ("bin", "Multiply", ("bin", "Plus", ("col", 0), ("col", 1)),
+                                   ("bin", "Minus", ("col", 2), ("bin", "Plus", ("col", 0), lit(3)))))
+    same(G.gpu_projection(b, [e]), O.projection(b, [e]))
+
+
+@pytest.mark.parametrize("case", ["interval", "div0_int", "div0_float", "mod0", "overflow", "and_on_int", "arith_on_bool",
+                                  "unary_on_int", "filtered_div0_ok"])
+def test_error_behaviour(case):
+    import nqe_b200 as nq
+    b = O.Batch(["a", "z", "f", "t"], [O.col("i64", [1, 2, -2**63]), O.col("i64", [1, 0, -1]),
+                                      O.col("f64", [1.0, 0.0, 2.0]), O.col("bool", [True, False, True])])
+    cases = {
+        "interval": (("bin", "Lt", ("col", 0), ("lit", "f64", 9.5)), "IntervalError"),
+        "div0_int": (("bin", "Divide", ("col", 0), ("col", 1)), "ArrowError(DivideByZero)"),
+        "div0_float": (("bin", "Divide", ("col", 2), ("col", 2)), "ArrowError(DivideByZero)"),
+        "mod0": (("bin", "Modulos", ("col", 0), ("col", 1)), "ArrowError(DivideByZero)"),
+        "and_on_int": (("bin", "And", ("col", 0), ("col", 1)), "IntervalError"),
+        "arith_on_bool": (("bin", "Plus", ("col", 3), ("col", 3)), "Panic"),
+        "unary_on_int": (("un", "abs", ("col", 0)), "Panic"),
+    }
+    if case == "overflow":
+        b2 = O.Batch(["a", "z"], [O.col("i64", [-2**63]), O.col("i64", [-1])])
+        with pytest.raises(nq.NqeError) as e:
+            G.gpu_projection(b2, [("bin", "Divide", ("col", 0), ("col", 1))])
+        assert e.value.kind == "Panic"
+        with pytest.raises(O.OracleError) as oe:
+            O.projection(b2, [("bin", "Divide", ("col", 0), ("col", 1))])
+        assert oe.value.kind == "Panic"
+        return
+    if case == "filtered_div0_ok":
+        # the zero divisor sits in a row the selection drops: the projection never sees it
+        pred = ("bin", "NotEq", ("col", 1), lit(0))
+        ex = [("bin", "Divide", ("col", 0), ("col", 1))]
+        b3 = O.Batch(["a", "z"], [O.col("i64", [10, 20, 30]), O.col("i64", [2, 0, 5])])
+        same(G.gpu_projection(b3, ex, pred=pred), O.projection(O.selection(b3, pred), ex))
+        return
+    ex, kind = cases[case]
+    with pytest.raises(nq.NqeError) as e:
+        G.gpu_projection(b, [ex])
+    assert e.value.kind == kind
+    with pytest.raises(O.OracleError) as oe:
+        O.projection(b, [ex])
+    assert oe.value.kind == kind
+    if case == "interval":
+        assert e.value.message == oe.value.msg == "Cannot evaluate binary expression Lt with types Int64 and Float64"
+
+
+# ---------------------------------------------------------------- hash join
+@pytest.mark.parametrize("nl,nr,keyspace", [(0, 10, 5), (10, 0, 5), (1, 1, 1), (1000, 5000, 1000), (5000, 1000, 100),
+                                            (3000, 3000, 10**9), (20000, 100_000, 20000)])
+def test_hash_join_random(nl, nr, keyspace):
+    rng = np.random.default_rng(nl + nr)
+    l = O.Batch(["k", "a", "lb"], [O.Col("i64", rng.integers(0, keyspace, nl)), rand_col(rng, "i64", nl, 0.1),
+                                  rand_col(rng, "bool", nl)])
+    r = O.Batch(["fk", "b"], [O.Col("i64", rng.integers(0, keyspace, nr)), rand_col(rng, "f64", nr, 0.1)])
+    want = O.hash_join_c(l, r, 0, 0)
+    got = G.gpu_join(l, r, "k", "fk")
+    same(got, want)  # identical order: probe-row-major, build rows ascending
+
+
+def test_hash_join_unique_build_keys_and_u64():
+    rng = np.random.default_rng(9)
+    nl, nr = 10_000, 50_000
+    l = O.Batch(["k", "a"], [O.Col("u64", rng.permutation(nl).astype(np.uint64)), rand_col(rng, "i64", nl)])
+    r = O.Batch(["fk", "b"], [O.Col("u64", rng.integers(0, 2 * nl, nr).astype(np.uint64)), rand_col(rng, "f64", nr)])
+    same(G.gpu_join(l, r, "k", "fk"), O.hash_join_c(l, r, 0, 0))
+
+
+def test_hash_join_ignores_key_validity():  # hash_join.rs:67,86
+    l = O.Batch(["k", "a"], [O.col("i64", [5, 7, 5, 0], valid=[1, 1, 1, 0]), O.col("i64", [10, 11, 12, 13])])
+    r = O.Batch(["fk", "b"], [O.col("i64", [7, 5, 0, 9]), O.col("f64", [0.5, 1.5, 2.5, 3.5])])
+    got = G.gpu_join(l, r, "k", "fk")
+    assert got.rows() == [(7, 11, 7, 0.5), (5, 10, 5, 1.5), (5, 12, 5, 1.5), (None, 13, 0, 2.5)]
+
+
+def test_hash_join_errors():
+    import nqe_b200 as nq
+    l = O.Batch(["k"], [O.col("f64", [1.0])])
+    r = O.Batch(["fk"], [O.col("f64", [1.0])])
+    with pytest.raises(nq.NqeError) as e:
+        G.gpu_join(l, r, "k", "fk")
+    assert e.value.kind == "NotImplemented"  # hash_join.rs:161
+    li = O.Batch(["k"], [O.col("i64", [1])])
+    with pytest.raises(nq.NqeError) as e:
+        nq.HashJoin.create(G.scan(li), G.scan(li), [], "Inner").execute()
+    assert e.value.kind == "PlanError" and e.value.message == "Inner Join on Conditions can't not be empty"
+
+
+# ---------------------------------------------------------------- aggregates
+ALL_AGGS = [("count", 1), ("sum", 1), ("avg", 1), ("min", 1), ("max", 1)]
+
+
+@pytest.mark.parametrize("n,groups", [(0, 5), (1, 1), (1000, 3), (50_000, 1000), (200_000, 150_000)])
+@pytest.mark.parametrize("vtype", ["f64", "i64"])
+def test_group_by_random(n, groups, vtype):
+    rng = np.random.default_rng(n + groups)
+    k = O.Col("i64", rng.integers(-groups // 2, groups // 2 + 1, n), (rng.random(n) > 0.05).astype(np.uint8))
+    v = rand_col(rng, vtype, n, 0.1, lo=-10**6, hi=10**6)
+    b = O.Batch(["k", "v"], [k, v])
+    want = O.aggregate(b, ("col", 0), ALL_AGGS + [("min", 0)])
+    got = G.gpu_aggregate(b, ("col", 0), ALL_AGGS + [("min", 0)])
+    assert got.names == want.names
+    same(got, want, rel=SUM_REL, ordered=False)
+    # counts, min, max are exact
+    gs, ws = sorted(got.rows(), key=lambda r: r[5]), sorted(want.rows(), key=lambda r: r[5])
+    for a, w in zip(gs, ws):
+        assert a[0] == w[0] and a[3] == w[3] and a[4] == w[4]
+
+
+def test_group_by_expression_key_and_special_values():
+    nan, inf = float("nan"), float("inf")
+    b = O.Batch(["k", "v"], [O.col("i64", [1, 1, None, 2, 3, 3, -2**63, -2**63, 4]),
+                             O.col("f64", [nan, 2.0, 5.0, None, inf, -inf, 1.0, 2.0, -0.0])])
+    for key in [("col", 0), ("bin", "Modulos", ("col", 0), lit(2))]:
+        want = O.aggregate(b, key, ALL_AGGS)
+        got = G.gpu_aggregate(b, key, ALL_AGGS)
+        same(got, want, rel=SUM_REL, ordered=False)
+
+
+def test_global_aggregate():
+    rng = np.random.default_rng(2)
+    for n in [0, 1, 100_000]:
+        b = O.Batch(["k", "v", "u"], [rand_col(rng, "i64", n), rand_col(rng, "f64", n, 0.2), rand_col(rng, "u64", n)])
+        aggs = ALL_AGGS + [("sum", 0), ("max", 2), ("count", 0)]
+        same(G.gpu_aggregate(b, None, aggs), O.aggregate(b, None, aggs), rel=SUM_REL)
+
+
+def test_aggregate_errors():
+    import nqe_b200 as nq
+    b = O.Batch(["k", "t", "f"], [O.col("i64", [1]), O.col("bool", [True]), O.col("f64", [1.0])])
+    with pytest.raises(nq.NqeError) as e:
+        G.gpu_aggregate(b, ("col", 2), [("count", 0)])
+    assert e.value.kind == "NotSupported" and "group by only support" in e.value.message
+    with pytest.raises(nq.NqeError) as e:
+        G.gpu_aggregate(b, None, [("sum", 1)])
+    assert e.value.kind == "NotSupported"
+
+
+@pytest.mark.parametrize("nl,nr,groups", [(1000, 20_000, 10), (20_000, 100_000, 5000)])
+def test_join_aggregate_fused(nl, nr, groups):
+    rng = np.random.default_rng(nl)
+    l = O.Batch(["k", "a"], [O.Col("i64", rng.permutation(nl).astype(np.int64)), O.Col("i64", rng.integers(0, groups, nl))])
+    r = O.Batch(["fk", "b"], [O.Col("i64", rng.integers(0, int(nl * 1.2), nr)), rand_col(rng, "f64", nr, 0.05)])
+    aggs = [("count", 3), ("sum", 3), ("avg", 3), ("min", 3), ("max", 3), ("min", 1)]
+    want = O.aggregate(O.hash_join_c(l, r, 0, 0), ("col", 1), aggs)
+    got = G.gpu_join_aggregate(l, r, "k", "fk", 1, aggs)
+    same(got, want, rel=SUM_REL, ordered=False)
+    # duplicate build keys, group key from the probe side
+    l2 = O.Batch(["k", "a"], [O.Col("i64", rng.integers(0, nl // 4, nl)), rand_col(rng, "i64", nl)])
+    r2 = O.Batch(["fk", "g"], [O.Col("i64", rng.integers(0, nl // 4, nr // 10)), O.Col("i64", rng.integers(0, groups, nr // 10))])
+    aggs2 = [("count", 1), ("sum", 1), ("max", 1), ("min", 3)]
+    want2 = O.aggregate(O.hash_join_c(l2, r2, 0, 0), ("col", 3), aggs2)
+    got2 = G.gpu_join_aggregate(l2, r2, "k", "fk", 3, aggs2)
+    same(got2, want2, rel=SUM_REL, ordered=False)
+
+
+# ---------------------------------------------------------------- limit / offset / partition / synth
+def test_limit_offset():  # limit.rs:67-90, offset.rs:69-92, README.md:70-76
+    import nqe_b200 as nq
+    t1 = numeric_only(golden_table("t1"))
+    off = nq.PhysicalOffsetPlan.create(G.scan(t1), 5)
+    assert G.from_arrow(off.execute()[0]).cols[0].to_pylist() == FX["test_physical_offset"]["id"]
+    lim = nq.PhysicalLimitPlan.create(G.scan(t1), 2)
+    assert G.from_arrow(lim.execute()[0]).cols[0].to_pylist() == [1, 2]
+    rng = np.random.default_rng(4)
+    b = O.Batch(["a", "f", "t"], [rand_col(rng, "i64", 1000, 0.3), rand_col(rng, "f64", 1000), rand_col(rng, "bool", 1000, 0.3)])
+    for o, l in [(0, 1000), (3, 100), (37, 900), (999, 1), (1000, 0), (64, 64)]:
+        plan = nq.PhysicalLimitPlan.create(nq.PhysicalOffsetPlan.create(G.scan(b), o), l)
+        got = G.from_arrow(plan.execute()[0])
+        assert got.rows() == b.rows()[o:][:l]
+
+
+def test_radix_partition_is_a_permutation_grouped_by_destination():
+    import ctypes as C
+    import nqe_b200 as nq
+    rng = np.random.default_rng(8)
+    n = 100_003
+    b = O.Batch(["k", "v"], [O.Col("i64", rng.integers(0, 10**6, n)), rand_col(rng, "f64", n)])
+    src = G.scan(b).execute_device()
+    for parts in [1, 2, 8]:
+        h = C.c_void_p()
+        counts = (C.c_int64 * parts)()
+        src.ctx.check(src.ctx.lib.nqe_radix_partition(src.ctx.h, src.h, 0, parts, C.byref(h), counts))
+        out = G.from_arrow(nq.DeviceTable(src.ctx, h, ["k", "v"]).to_arrow())
+        assert sum(counts) == n
+        assert sorted(out.rows()) == sorted(b.rows())
+        # every region holds one destination only, and the destination is a function of the key
+        dest = {}
+        pos = 0
+        for p in range(parts):
+            for kk in out.cols[0].values[pos:pos + counts[p]]:
+                assert dest.setdefault(int(kk), p) == p
+            pos += counts[p]
+
+
+def test_synth_columns_match_oracle_generator():
+    import torch
+    import nqe_b200 as nq
+    ctx = nq.Context.default()
+    n = 10_000
+    for kind, seed, a, b2, scale, want in [
+            (0, 42, 1000, 0, 0.0, O.gen_mod_i64(42, 7, n, 1000)),
+            (1, 44, 0, 0, 100.0, O.gen_unif_f64(44, 7, n, 100.0)),
+            (2, 0, 7368787, 10**7, 0.0, O.gen_perm_i64(7, n, 7368787, 10**7))]:
+        buf = torch.empty(n, dtype=torch.int64, device="cuda")
+        ctx.check(ctx.lib.nqe_synth_column(ctx.h, kind, seed, 7, n, a, b2, scale, buf.data_ptr()))
+        ctx.sync()
+        got = buf.cpu().numpy()
+        assert np.array_equal(got, want.view(np.int64))
