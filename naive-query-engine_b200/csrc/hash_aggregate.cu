@@ -14,6 +14,7 @@
 // skipped, and the output carries no key column.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "agg_device.cuh"
@@ -243,7 +244,10 @@ int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64
 }
 
 // capacity for `est` expected groups
-uint64_t nqe_agg_capacity(double est) { return nqe_next_pow2((uint64_t)(est * 2.0) + 1024); }
+uint64_t nqe_agg_capacity(double est) {
+    if (const char *e = getenv("NQE_AGG_CAP")) return nqe_next_pow2((uint64_t)atoll(e)); // tuning/debug knob
+    return nqe_next_pow2((uint64_t)(est * 2.0) + 1024);
+}
 
 extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *group_expr,
                                       const nqe_agg *aggs, int32_t n_aggs, nqe_table **out) {

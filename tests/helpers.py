@@ -47,8 +47,12 @@ def _key(v):
     return (1, v)
 
 
-def sort_rows(rows):
-    return sorted(rows, key=lambda r: tuple(_key(v) for v in r))
+def sort_rows(rows, cols=None):
+    """Sort rows for multiset comparison.  `cols`: indices of columns that are
+    exact (ints, counts, min/max, a key) -- float sums must not drive the order."""
+    if cols is None:
+        return sorted(rows, key=lambda r: tuple(_key(v) for v in r))
+    return sorted(rows, key=lambda r: tuple(_key(r[c]) for c in cols))
 
 
 def rows_close(a, b, rel=0.0):
@@ -76,8 +80,8 @@ def rows_close(a, b, rel=0.0):
     return True, ""
 
 
-def assert_rows(a, b, rel=0.0, ordered=True):
+def assert_rows(a, b, rel=0.0, ordered=True, sort_cols=None):
     if not ordered:
-        a, b = sort_rows(a), sort_rows(b)
+        a, b = sort_rows(a, sort_cols), sort_rows(b, sort_cols)
     ok, why = rows_close(a, b, rel)
     assert ok, why

@@ -43,9 +43,9 @@ def rand_col(rng, dtype, n, null_frac=0.0, lo=-50, hi=50):
     return O.Col(dtype, v, valid)
 
 
-def same(a: O.Batch, b: O.Batch, rel=0.0, ordered=True):
+def same(a: O.Batch, b: O.Batch, rel=0.0, ordered=True, sort_cols=None):
     assert [c.dtype for c in a.cols] == [c.dtype for c in b.cols]
-    assert_rows([list(r) for r in a.rows()], [list(r) for r in b.rows()], rel=rel, ordered=ordered)
+    assert_rows([list(r) for r in a.rows()], [list(r) for r in b.rows()], rel=rel, ordered=ordered, sort_cols=sort_cols)
 
 
 # ---------------------------------------------------------------- golden fixtures
@@ -278,7 +278,7 @@ def test_group_by_random(n, groups, vtype):
     want = O.aggregate(b, ("col", 0), ALL_AGGS + [("min", 0)])
     got = G.gpu_aggregate(b, ("col", 0), ALL_AGGS + [("min", 0)])
     assert got.names == want.names
-    same(got, want, rel=SUM_REL, ordered=False)
+    same(got, want, rel=SUM_REL, ordered=False, sort_cols=[5])  # min(k) identifies the group
     # counts, min, max are exact
     gs, ws = sorted(got.rows(), key=lambda r: r[5]), sorted(want.rows(), key=lambda r: r[5])
     for a, w in zip(gs, ws):
@@ -292,7 +292,7 @@ def test_group_by_expression_key_and_special_values():
     for key in [("col", 0), ("bin", "Modulos", ("col", 0), lit(2))]:
         want = O.aggregate(b, key, ALL_AGGS)
         got = G.gpu_aggregate(b, key, ALL_AGGS)
-        same(got, want, rel=SUM_REL, ordered=False)
+        same(got, want, rel=SUM_REL, ordered=False, sort_cols=[0, 3, 4])
 
 
 def test_global_aggregate():
@@ -322,14 +322,14 @@ def test_join_aggregate_fused(nl, nr, groups):
     aggs = [("count", 3), ("sum", 3), ("avg", 3), ("min", 3), ("max", 3), ("min", 1)]
     want = O.aggregate(O.hash_join_c(l, r, 0, 0), ("col", 1), aggs)
     got = G.gpu_join_aggregate(l, r, "k", "fk", 1, aggs)
-    same(got, want, rel=SUM_REL, ordered=False)
+    same(got, want, rel=SUM_REL, ordered=False, sort_cols=[5])
     # duplicate build keys, group key from the probe side
     l2 = O.Batch(["k", "a"], [O.Col("i64", rng.integers(0, nl // 4, nl)), rand_col(rng, "i64", nl)])
     r2 = O.Batch(["fk", "g"], [O.Col("i64", rng.integers(0, nl // 4, nr // 10)), O.Col("i64", rng.integers(0, groups, nr // 10))])
     aggs2 = [("count", 1), ("sum", 1), ("max", 1), ("min", 3)]
     want2 = O.aggregate(O.hash_join_c(l2, r2, 0, 0), ("col", 3), aggs2)
     got2 = G.gpu_join_aggregate(l2, r2, "k", "fk", 3, aggs2)
-    same(got2, want2, rel=SUM_REL, ordered=False)
+    same(got2, want2, rel=SUM_REL, ordered=False, sort_cols=[3])
 
 
 # ---------------------------------------------------------------- limit / offset / partition / synth
