@@ -1,7 +1,12 @@
 // expr_eval.cuh -- per-row evaluation of lowered PhysicalExpr programs.
 //
-// Each thread evaluates K rows (row index e0 + j*stride) with the running value
-// in registers.  Semantics follow the reference / arrow 13 kernels:
+// Each thread evaluates K rows with the running value in registers; every
+// micro-op is decoded once per K rows (the dispatch is warp-uniform) and its
+// element loop is fully unrolled.  Two instantiations exist:
+//   NULLS = false : all K rows are in range and no operand can be NULL (no
+//                   validity bitmap, no NULL literal) -- no validity tracking at all
+//   NULLS = true  : ragged tiles and/or nullable operands
+// Semantics follow the reference / arrow 13 kernels:
 //   compare  : NULL if either side NULL; IEEE partial order for Float64
 //   and/or   : Kleene logic (and_kleene / or_kleene)
 //   + - *    : wrapping for Int64/UInt64, IEEE for Float64
@@ -9,6 +14,8 @@
 //              i64::MIN / -1 and % -1 are overflow panics; % is truncated
 //   abs/sin/cos on Float64 (Tan lowered to cos on the host)
 #pragma once
+
+#include <climits>
 
 #include "nqe_internal.cuh"
 
@@ -22,12 +29,12 @@ __device__ __forceinline__ uint64_t ld_cached_u64(const void *p) { return __ldg(
 template <int K>
 struct RowRegs {
     uint64_t v[K];
-    uint32_t valid; // bit j: v[j] is non-NULL
+    uint32_t valid; // bit j: v[j] is non-NULL (all ones when NULLS == false)
 };
 
-// Row sources.  GlobalRows reads column j-th row straight from HBM (row index
-// e0 + j*stride); SmemRows reads a tile staged in shared memory by TMA bulk copies
-// (values of column slot s at byte offset voff[s], bitmap words at boff[s]).
+// Row sources.  GlobalRows reads row e0 + j*stride straight from HBM; SmemRows
+// reads a tile staged in shared memory by TMA bulk copies (values of column slot
+// s at byte offset voff16[s]*16, its validity bitmap words at boff16[s]*16).
 struct GlobalRows {
     int64_t e0, stride;
     __device__ __forceinline__ uint64_t value(const DevColRef &c, int, int j) const {
@@ -44,10 +51,10 @@ struct GlobalRows {
 };
 
 struct SmemRows {
-    const uint8_t *stage;    // this tile's stage buffer
-    const uint16_t *voff16;  // per column slot: values offset / 16
-    const uint16_t *boff16;  // per column slot: validity bitmap offset / 16
-    int r0, stride;          // row in tile = r0 + j*stride
+    const uint8_t *stage;
+    const uint16_t *voff16;
+    const uint16_t *boff16;
+    int r0, stride; // row in tile = r0 + j*stride
     __device__ __forceinline__ uint64_t value(const DevColRef &, int slot, int j) const {
         return *(const uint64_t *)(stage + (size_t)voff16[slot] * 16 + (size_t)(r0 + j * stride) * 8);
     }
@@ -61,11 +68,23 @@ struct SmemRows {
     }
 };
 
-template <int K, typename Rows>
+template <int K, bool NULLS, typename Rows>
 __device__ __forceinline__ void load_operand(const DevProgramSet &ps, const DevOp &op, const Rows &rows,
                                              uint32_t inrange, uint32_t rownull, RowRegs<K> &b) {
+    constexpr uint32_t ALL = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
     if (op.src == SRC_COL) {
         const DevColRef &c = ps.cols[op.slot];
+        if (!NULLS) {
+            if (c.dtype == NQE_BOOL) {
+#pragma unroll
+                for (int j = 0; j < K; j++) b.v[j] = rows.boolbit(c, op.slot, j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) b.v[j] = rows.value(c, op.slot, j);
+            }
+            b.valid = ALL;
+            return;
+        }
         uint32_t valid = inrange;
         if (c.dtype == NQE_BOOL) {
 #pragma unroll
@@ -84,7 +103,7 @@ __device__ __forceinline__ void load_operand(const DevProgramSet &ps, const DevO
     } else if (op.src == SRC_LIT) {
 #pragma unroll
         for (int j = 0; j < K; j++) b.v[j] = op.imm;
-        b.valid = inrange;
+        b.valid = NULLS ? inrange : ALL;
     } else { // SRC_NULL
 #pragma unroll
         for (int j = 0; j < K; j++) b.v[j] = 0;
@@ -92,114 +111,118 @@ __device__ __forceinline__ void load_operand(const DevProgramSet &ps, const DevO
     }
 }
 
-template <typename T>
-__device__ __forceinline__ bool cmp_op(uint8_t code, T x, T y) {
-    switch (code) {
-    case NQE_OP_EQ: return x == y;
-    case NQE_OP_NOT_EQ: return x != y;
-    case NQE_OP_LT: return x < y;
-    case NQE_OP_LT_EQ: return x <= y;
-    case NQE_OP_GT: return x > y;
-    default: return x >= y;
-    }
-}
+#define NQE_FOR_J _Pragma("unroll") for (int j = 0; j < K; j++)
+#define NQE_AS_F64(x) __longlong_as_double((long long)(x))
+#define NQE_F64_BITS(x) ((uint64_t)__double_as_longlong(x))
 
-// a (op) b -> a.  `active` = rows whose errors count (kept, in range).
+// right-hand operand accessors: a per-row vector, or one broadcast immediate
 template <int K>
-__device__ __forceinline__ void apply_binary(uint8_t code, uint8_t type, RowRegs<K> &a, const RowRegs<K> &b,
+struct VecOperand {
+    const RowRegs<K> &r;
+    __device__ __forceinline__ uint64_t operator[](int j) const { return r.v[j]; }
+    __device__ __forceinline__ uint32_t valid() const { return r.valid; }
+};
+struct ImmOperand {
+    uint64_t imm;
+    uint32_t vmask;
+    __device__ __forceinline__ uint64_t operator[](int) const { return imm; }
+    __device__ __forceinline__ uint32_t valid() const { return vmask; }
+};
+
+// a (op) b -> a.  `live` = rows whose errors count (kept, in range, both operands valid).
+template <int K, bool NULLS, typename B>
+__device__ __forceinline__ void apply_binary(uint8_t code, uint8_t type, RowRegs<K> &a, const B &b,
                                              uint32_t active, uint32_t *status) {
-    const uint32_t both = a.valid & b.valid;
+    const uint32_t both = a.valid & b.valid();
     if (code <= NQE_OP_GT_EQ) {
-        if (type == T_I64) {
-#pragma unroll
-            for (int j = 0; j < K; j++) a.v[j] = cmp_op<long long>(code, (long long)a.v[j], (long long)b.v[j]);
-        } else if (type == T_F64) {
-#pragma unroll
-            for (int j = 0; j < K; j++)
-                a.v[j] = cmp_op<double>(code, __longlong_as_double((long long)a.v[j]), __longlong_as_double((long long)b.v[j]));
-        } else { // U64, BOOL (0/1)
-#pragma unroll
-            for (int j = 0; j < K; j++) a.v[j] = cmp_op<unsigned long long>(code, a.v[j], b.v[j]);
-        }
+#define NQE_CMP_ALL(T, CONV)                                                                      \
+    switch (code) {                                                                               \
+    case NQE_OP_EQ: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) == (T)CONV(b[j]); break;                 \
+    case NQE_OP_NOT_EQ: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) != (T)CONV(b[j]); break;             \
+    case NQE_OP_LT: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) < (T)CONV(b[j]); break;                  \
+    case NQE_OP_LT_EQ: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) <= (T)CONV(b[j]); break;              \
+    case NQE_OP_GT: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) > (T)CONV(b[j]); break;                  \
+    default: NQE_FOR_J a.v[j] = (T)CONV(a.v[j]) >= (T)CONV(b[j]); break;                        \
+    }
+        if (type == T_I64) { NQE_CMP_ALL(long long, ) }
+        else if (type == T_F64) { NQE_CMP_ALL(double, NQE_AS_F64) }
+        else { NQE_CMP_ALL(unsigned long long, ) } // U64, BOOL (0/1)
+#undef NQE_CMP_ALL
         a.valid = both;
         return;
     }
     if (code == NQE_OP_AND || code == NQE_OP_OR) {
         uint32_t at = 0, bt = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
+        NQE_FOR_J {
             at |= (uint32_t)(a.v[j] & 1) << j;
-            bt |= (uint32_t)(b.v[j] & 1) << j;
+            bt |= (uint32_t)(b[j] & 1) << j;
         }
-        at &= a.valid; bt &= b.valid;
-        const uint32_t af = a.valid & ~at, bf = b.valid & ~bt;
+        at &= a.valid; bt &= b.valid();
+        const uint32_t af = a.valid & ~at, bf = b.valid() & ~bt;
         uint32_t val, ok;
         if (code == NQE_OP_AND) { val = at & bt; ok = both | af | bf; }
         else { val = at | bt; ok = both | at | bt; }
-#pragma unroll
-        for (int j = 0; j < K; j++) a.v[j] = (val >> j) & 1u;
+        NQE_FOR_J a.v[j] = (val >> j) & 1u;
         a.valid = ok;
         return;
     }
-    // arithmetic
+    const uint32_t live = both & active;
     if (type == T_F64) {
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            double x = __longlong_as_double((long long)a.v[j]), y = __longlong_as_double((long long)b.v[j]), r;
-            switch (code) {
-            case NQE_OP_PLUS: r = __dadd_rn(x, y); break;
-            case NQE_OP_MINUS: r = __dsub_rn(x, y); break;
-            case NQE_OP_MULTIPLY: r = __dmul_rn(x, y); break;
-            case NQE_OP_DIVIDE:
-                if (y == 0.0 && ((both & active) >> j & 1u)) atomicOr(status, DEV_ERR_DIV0);
-                r = x / y; break;
-            default:
-                if (y == 0.0 && ((both & active) >> j & 1u)) atomicOr(status, DEV_ERR_DIV0);
-                r = fmod(x, y); break;
+        switch (code) {
+        case NQE_OP_PLUS: NQE_FOR_J a.v[j] = NQE_F64_BITS(__dadd_rn(NQE_AS_F64(a.v[j]), NQE_AS_F64(b[j]))); break;
+        case NQE_OP_MINUS: NQE_FOR_J a.v[j] = NQE_F64_BITS(__dsub_rn(NQE_AS_F64(a.v[j]), NQE_AS_F64(b[j]))); break;
+        case NQE_OP_MULTIPLY: NQE_FOR_J a.v[j] = NQE_F64_BITS(__dmul_rn(NQE_AS_F64(a.v[j]), NQE_AS_F64(b[j]))); break;
+        case NQE_OP_DIVIDE:
+            NQE_FOR_J {
+                const double y = NQE_AS_F64(b[j]);
+                if (y == 0.0 && ((live >> j) & 1u)) atomicOr(status, DEV_ERR_DIV0);
+                a.v[j] = NQE_F64_BITS(NQE_AS_F64(a.v[j]) / y);
             }
-            a.v[j] = (uint64_t)__double_as_longlong(r);
+            break;
+        default:
+            NQE_FOR_J {
+                const double y = NQE_AS_F64(b[j]);
+                if (y == 0.0 && ((live >> j) & 1u)) atomicOr(status, DEV_ERR_DIV0);
+                a.v[j] = NQE_F64_BITS(fmod(NQE_AS_F64(a.v[j]), y));
+            }
+            break;
         }
-    } else if (type == T_I64) {
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            long long x = (long long)a.v[j], y = (long long)b.v[j];
-            unsigned long long r;
-            switch (code) {
-            case NQE_OP_PLUS: r = (unsigned long long)x + (unsigned long long)y; break;
-            case NQE_OP_MINUS: r = (unsigned long long)x - (unsigned long long)y; break;
-            case NQE_OP_MULTIPLY: r = (unsigned long long)x * (unsigned long long)y; break;
-            default: {
-                const bool live = (both & active) >> j & 1u;
-                if (y == 0) { if (live) atomicOr(status, DEV_ERR_DIV0); r = 0; }
-                else if (y == -1) {
-                    if (x == LLONG_MIN) { if (live) atomicOr(status, DEV_ERR_OVERFLOW); r = 0; }
-                    else r = code == NQE_OP_DIVIDE ? (unsigned long long)(-x) : 0ull;
-                } else r = (unsigned long long)(code == NQE_OP_DIVIDE ? x / y : x % y);
+    } else {
+        switch (code) {
+        case NQE_OP_PLUS: NQE_FOR_J a.v[j] = a.v[j] + b[j]; break; // two's complement: same bits for i64/u64
+        case NQE_OP_MINUS: NQE_FOR_J a.v[j] = a.v[j] - b[j]; break;
+        case NQE_OP_MULTIPLY: NQE_FOR_J a.v[j] = a.v[j] * b[j]; break;
+        default:
+            if (type == T_I64) {
+                NQE_FOR_J {
+                    const long long x = (long long)a.v[j], y = (long long)b[j];
+                    const bool lv = (live >> j) & 1u;
+                    unsigned long long r = 0;
+                    if (y == 0) { if (lv) atomicOr(status, DEV_ERR_DIV0); }
+                    else if (y == -1) {
+                        if (x == LLONG_MIN) { if (lv) atomicOr(status, DEV_ERR_OVERFLOW); }
+                        else r = code == NQE_OP_DIVIDE ? (unsigned long long)(-x) : 0ull;
+                    } else r = (unsigned long long)(code == NQE_OP_DIVIDE ? x / y : x % y);
+                    a.v[j] = r;
+                }
+            } else {
+                NQE_FOR_J {
+                    const unsigned long long x = a.v[j], y = b[j];
+                    unsigned long long r = 0;
+                    if (y == 0) { if ((live >> j) & 1u) atomicOr(status, DEV_ERR_DIV0); }
+                    else r = code == NQE_OP_DIVIDE ? x / y : x % y;
+                    a.v[j] = r;
+                }
             }
-            }
-            a.v[j] = r;
-        }
-    } else { // U64
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            unsigned long long x = a.v[j], y = b.v[j], r;
-            switch (code) {
-            case NQE_OP_PLUS: r = x + y; break;
-            case NQE_OP_MINUS: r = x - y; break;
-            case NQE_OP_MULTIPLY: r = x * y; break;
-            default:
-                if (y == 0) { if ((both & active) >> j & 1u) atomicOr(status, DEV_ERR_DIV0); r = 0; }
-                else r = code == NQE_OP_DIVIDE ? x / y : x % y;
-            }
-            a.v[j] = r;
+            break;
         }
     }
     a.valid = both;
 }
 
-// Run program p for K rows; result in acc.  rownull = rows whose inputs are
-// forced NULL (predicate was NULL, selection.rs:46).
-template <int K, typename Rows>
+// Run program p for K rows; result in acc.  rownull = rows whose column inputs are
+// forced NULL (the selection predicate was NULL, selection.rs:46).
+template <int K, bool NULLS, typename Rows>
 __device__ __forceinline__ void run_program_on(const DevProgramSet &ps, int p, const Rows &rows, uint32_t inrange,
                                                uint32_t active, uint32_t rownull, RowRegs<K> &acc, uint32_t *status) {
     RowRegs<K> stack[NQE_STACK];
@@ -207,31 +230,32 @@ __device__ __forceinline__ void run_program_on(const DevProgramSet &ps, int p, c
     for (int i = ps.prog_begin[p]; i < end; i++) {
         const DevOp op = ps.ops[i];
         if (op.code == UOP_LOAD) {
-            load_operand<K>(ps, op, rows, inrange, rownull, acc);
+            load_operand<K, NULLS>(ps, op, rows, inrange, rownull, acc);
         } else if (op.code == UOP_PUSH) {
             stack[op.slot] = acc;
         } else if (op.code >= UOP_ABS) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                double x = __longlong_as_double((long long)acc.v[j]);
-                double r = op.code == UOP_ABS ? fabs(x) : (op.code == UOP_SIN ? sin(x) : cos(x));
-                acc.v[j] = (uint64_t)__double_as_longlong(r);
-            }
+            if (op.code == UOP_ABS) { NQE_FOR_J acc.v[j] &= 0x7FFFFFFFFFFFFFFFull; }
+            else if (op.code == UOP_SIN) { NQE_FOR_J acc.v[j] = NQE_F64_BITS(sin(NQE_AS_F64(acc.v[j]))); }
+            else { NQE_FOR_J acc.v[j] = NQE_F64_BITS(cos(NQE_AS_F64(acc.v[j]))); }
         } else if (op.src == SRC_STACK) {
             RowRegs<K> l = stack[op.slot];
-            apply_binary<K>(op.code, op.type, l, acc, active, status);
+            apply_binary<K, NULLS>(op.code, op.type, l, VecOperand<K>{acc}, active, status);
             acc = l;
+        } else if (op.src == SRC_LIT) {
+            constexpr uint32_t ALL = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+            apply_binary<K, NULLS>(op.code, op.type, acc, ImmOperand{op.imm, NULLS ? inrange : ALL}, active, status);
         } else {
             RowRegs<K> b;
-            load_operand<K>(ps, op, rows, inrange, rownull, b);
-            apply_binary<K>(op.code, op.type, acc, b, active, status);
+            load_operand<K, NULLS>(ps, op, rows, inrange, rownull, b);
+            apply_binary<K, NULLS>(op.code, op.type, acc, VecOperand<K>{b}, active, status);
         }
     }
 }
 
+// general entry (row source = HBM, nullable / ragged allowed)
 template <int K>
 __device__ __forceinline__ void run_program(const DevProgramSet &ps, int p, int64_t e0, int64_t stride,
                                             uint32_t inrange, uint32_t active, uint32_t rownull,
                                             RowRegs<K> &acc, uint32_t *status) {
-    run_program_on<K>(ps, p, GlobalRows{e0, stride}, inrange, active, rownull, acc, status);
+    run_program_on<K, true>(ps, p, GlobalRows{e0, stride}, inrange, active, rownull, acc, status);
 }

@@ -31,7 +31,9 @@ struct FilterParams {
     unsigned int *ticket;
     unsigned long long *out_count;
     uint32_t *status;
-    int32_t num_tiles;
+    int32_t num_tiles;  // tiles of the whole input (the last one writes out_count)
+    int32_t tile_base;  // direct kernel: first tile handled by this launch
+    int32_t tile_end;   // TMA kernel: tiles [0, tile_end) are handled by this launch (all full)
 };
 
 constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
@@ -86,7 +88,7 @@ filter_project_kernel(const __grid_constant__ DevProgramSet ps, const __grid_con
     while (true) {
         int tile;
         if (HAS_PRED) {
-            if (tid == 0) s_tile = (int)atomicAdd(fp.ticket, 1u);
+            if (tid == 0) s_tile = fp.tile_base + (int)atomicAdd(fp.ticket, 1u);
             __syncthreads();
             tile = s_tile;
         } else {
@@ -191,7 +193,7 @@ filter_project_kernel(const __grid_constant__ DevProgramSet ps, const __grid_con
 // memory, so HBM latency is decoupled from the interpreter and a column used by
 // several programs (`id` in the predicate and in the projection) is fetched once.
 // ---------------------------------------------------------------------------
-constexpr int TMA_STAGES_MAX = 4;
+constexpr int TMA_STAGES_MAX = 3;
 
 struct TmaParams {
     uint16_t voff16[NQE_MAX_COLS]; // stage-relative offset of the column's values / 16
@@ -256,102 +258,102 @@ __device__ __forceinline__ unsigned long long lb_walk(unsigned long long *state,
     return excl;
 }
 
-// Software-pipelined persistent kernel: the COUNT phase of tile i+1 (predicate,
-// ballots, publish the tile aggregate) runs before the WRITE phase of tile i
-// (look-back, projection, stores), so aggregates reach the look-back chain as soon
-// as a tile's data has landed and the look-back of tile i normally finds its
-// predecessors already resolved.
-template <int K>
-__global__ void __launch_bounds__(FP_THREADS)
-filter_project_tma_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ FilterParams fp,
-                          const __grid_constant__ TmaParams tp) {
+// ---------------------------------------------------------------------------
+// Warp-specialised, software-pipelined persistent kernel (the hot path).
+//
+//   warps 0..7  WORKERS  count phase of tile i   : predicate -> keep ballots -> smem
+//                        write phase of tile i-1 : ranks + tile prefix -> projection -> stores
+//   warp  8     CONTROL  claims tiles (atomic ticket) and issues their cp.async.bulk copies,
+//                        scans the 8*K ballot counts of tile i, publishes the tile aggregate,
+//                        runs the decoupled look-back and hands the offsets to the workers.
+//
+// All hand-offs are mbarriers (no __syncthreads in the steady state), so the look-back
+// latency of tile i overlaps the workers' write of tile i-1 and count of tile i+1.
+// ---------------------------------------------------------------------------
+constexpr int WS_WORKERS = 8;                       // worker warps
+constexpr int WS_THREADS = (WS_WORKERS + 1) * 32;   // + control warp
+
+template <int K, int STAGES>
+struct WsSmem {
+    uint64_t full[STAGES];       // TMA bytes landed (tx) / "no tile" arrive
+    uint64_t stage_free[STAGES]; // 8 worker arrives: stage buffer may be refilled
+    uint64_t cnt_ready[2];       // 8 worker arrives: ballots of the tile are in smem
+    uint64_t off_ready[2];       // 1 control arrive: offsets + tile prefix are in smem
+    unsigned long long tile_excl[2];
+    int tile_id[STAGES];
+    unsigned int keep[2][K][WS_WORKERS];    // keep ballots
+    unsigned int rownull[2][K][WS_WORKERS]; // predicate-was-NULL ballots (NULLS only)
+    unsigned int offs[2][K][WS_WORKERS];    // exclusive offsets inside the tile
+    uint16_t voff[NQE_MAX_COLS], boff[NQE_MAX_COLS];
+};
+
+template <int K, int STAGES, bool NULLS>
+__global__ void __launch_bounds__(WS_THREADS)
+filter_project_ws_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ FilterParams fp,
+                         const __grid_constant__ TmaParams tp) {
     constexpr int TILE = K * FP_THREADS;
+    constexpr uint32_t ALL = (1u << K) - 1u;
     extern __shared__ __align__(128) uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t s_bar[TMA_STAGES_MAX];
-    __shared__ int s_tile_id[TMA_STAGES_MAX];
-    __shared__ unsigned int s_cnt[2][K * FP_WARPS];
-    __shared__ unsigned int s_total[2];
-    __shared__ unsigned int s_flags[2][FP_THREADS]; // per thread: keep | rownull << 16
-    __shared__ unsigned long long s_tile_excl;
-    __shared__ uint16_t s_voff[NQE_MAX_COLS], s_boff[NQE_MAX_COLS];
+    __shared__ __align__(16) WsSmem<K, STAGES> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int stages = tp.stages;
 
-    // producer side (thread 0): claim the next tile and start its bulk copies into `stage`
-    auto issue = [&](int stage) {
-        const int tile = (int)atomicAdd(fp.ticket, 1u);
-        s_tile_id[stage] = tile;
-        uint64_t *bar = &s_bar[stage];
-        if (tile < fp.num_tiles && (int64_t)(tile + 1) * TILE <= fp.n_rows) {
-            mbar_arrive_expect_tx(bar, tp.tx_bytes);
-            uint8_t *dst = smem_dyn + (size_t)stage * tp.stage_bytes;
-            for (int c = 0; c < ps.n_cols; c++) {
-                const DevColRef &col = ps.cols[c];
-                if (col.dtype == NQE_BOOL)
-                    bulk_g2s(dst + (size_t)tp.voff16[c] * 16, (const uint8_t *)col.values + (size_t)tile * (TILE / 8), TILE / 8, bar);
-                else
-                    bulk_g2s(dst + (size_t)tp.voff16[c] * 16, (const uint8_t *)col.values + (size_t)tile * TILE * 8, TILE * 8, bar);
-                if (col.validity)
-                    bulk_g2s(dst + (size_t)tp.boff16[c] * 16, (const uint8_t *)col.validity + (size_t)tile * (TILE / 8), TILE / 8, bar);
-            }
-        } else {
-            mbar_arrive(bar); // past the end, or the ragged last tile (filled cooperatively below)
+    if (tid < NQE_MAX_COLS) {
+        sm.voff[tid] = tp.voff16[tid];
+        sm.boff[tid] = tp.boff16[tid];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.stage_free[s], WS_WORKERS);
         }
-    };
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&sm.cnt_ready[b], WS_WORKERS);
+            mbar_init(&sm.off_ready[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
 
-    // COUNT phase of pipeline slot `it`; returns the tile id (>= num_tiles: nothing left)
-    auto count_phase = [&](int it) -> int {
-        const int stage = it % stages, buf = it & 1;
-        mbar_wait(&s_bar[stage], (uint32_t)((it / stages) & 1));
-        const int tile = s_tile_id[stage];
-        if (tile >= fp.num_tiles) return tile;
-        uint8_t *stg = smem_dyn + (size_t)stage * tp.stage_bytes;
-        const int64_t e0 = (int64_t)tile * TILE + tid;
-        uint32_t inrange = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            if (e0 + (int64_t)j * FP_THREADS < fp.n_rows) inrange |= 1u << j;
-        if ((int64_t)(tile + 1) * TILE > fp.n_rows) {
-            // ragged last tile: every thread stages its own rows (and its warp's bitmap words)
-            for (int c = 0; c < ps.n_cols; c++) {
-                const DevColRef &col = ps.cols[c];
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    if (!((inrange >> j) & 1u)) continue;
-                    const int r = j * FP_THREADS + tid;
-                    const int64_t e = e0 + (int64_t)j * FP_THREADS;
+    if (warp == WS_WORKERS) {
+        // ============================ CONTROL WARP ============================
+        auto issue = [&](int stage) { // lane 0 only
+            const int tile = (int)atomicAdd(fp.ticket, 1u);
+            sm.tile_id[stage] = tile;
+            uint64_t *bar = &sm.full[stage];
+            if (tile < fp.tile_end) {
+                mbar_arrive_expect_tx(bar, tp.tx_bytes);
+                uint8_t *dst = smem_dyn + (size_t)stage * tp.stage_bytes;
+                for (int c = 0; c < ps.n_cols; c++) {
+                    const DevColRef &col = ps.cols[c];
                     if (col.dtype == NQE_BOOL)
-                        *(uint32_t *)(stg + (size_t)s_voff[c] * 16 + (r >> 5) * 4) = ((const uint32_t *)col.values)[e >> 5];
+                        bulk_g2s(dst + (size_t)tp.voff16[c] * 16, (const uint8_t *)col.values + (size_t)tile * (TILE / 8), TILE / 8, bar);
                     else
-                        *(uint64_t *)(stg + (size_t)s_voff[c] * 16 + (size_t)r * 8) = ((const uint64_t *)col.values)[e];
-                    if (col.validity)
-                        *(uint32_t *)(stg + (size_t)s_boff[c] * 16 + (r >> 5) * 4) = col.validity[e >> 5];
+                        bulk_g2s(dst + (size_t)tp.voff16[c] * 16, (const uint8_t *)col.values + (size_t)tile * TILE * 8, TILE * 8, bar);
+                    if (NULLS && col.validity)
+                        bulk_g2s(dst + (size_t)tp.boff16[c] * 16, (const uint8_t *)col.validity + (size_t)tile * (TILE / 8), TILE / 8, bar);
                 }
+            } else {
+                mbar_arrive(bar); // nothing left for this stage
             }
-            __syncwarp();
-        }
-        const SmemRows rows{stg, s_voff, s_boff, tid, FP_THREADS};
-        RowRegs<K> m;
-        run_program_on<K>(ps, 0, rows, inrange, inrange, 0u, m, fp.status);
-        uint32_t mt = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) mt |= (uint32_t)(m.v[j] & 1) << j;
-        const uint32_t rownull = inrange & ~m.valid;            // predicate NULL: keep as an all-NULL row
-        const uint32_t keep = inrange & ((mt & m.valid) | rownull);
-        s_flags[buf][tid] = keep | (rownull << 16);
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const unsigned b = __ballot_sync(0xffffffffu, (keep >> j) & 1u);
-            if (lane == 0) s_cnt[buf][j * FP_WARPS + warp] = __popc(b);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            constexpr int N = K * FP_WARPS, PER = (N + 31) / 32;
+        };
+        if (lane == 0)
+            for (int s = 0; s < STAGES; s++) issue(s);
+        __syncwarp();
+        int stage = 0;
+        for (int it = 0;; it++) {
+            const int buf = it & 1;
+            const int tile = *(volatile int *)&sm.tile_id[stage];
+            if (tile >= fp.tile_end) break;
+            mbar_wait(&sm.cnt_ready[buf], (uint32_t)((it >> 1) & 1));
+            // exclusive scan of the K*8 ballot popcounts (row order: j major, worker warp minor)
+            constexpr int N = K * WS_WORKERS, PER = (N + 31) / 32;
             unsigned int c[PER], sum = 0;
+            const unsigned int *kb = &sm.keep[buf][0][0];
 #pragma unroll
             for (int q = 0; q < PER; q++) {
                 const int i = lane * PER + q;
-                c[q] = i < N ? s_cnt[buf][i] : 0;
+                c[q] = i < N ? __popc(kb[i]) : 0;
                 sum += c[q];
             }
             unsigned int incl = sum;
@@ -361,91 +363,113 @@ filter_project_tma_kernel(const __grid_constant__ DevProgramSet ps, const __grid
                 if (lane >= o) incl += t;
             }
             unsigned int run = incl - sum;
+            unsigned int *ob = &sm.offs[buf][0][0];
 #pragma unroll
             for (int q = 0; q < PER; q++) {
                 const int i = lane * PER + q;
-                if (i < N) s_cnt[buf][i] = run;
+                if (i < N) ob[i] = run;
                 run += c[q];
             }
-            if (lane == 31) {
-                s_total[buf] = incl;
-                lb_publish(fp.tile_state, tile, incl);
-            }
-        }
-        return tile;
-    };
-
-    // WRITE phase of pipeline slot `it` (its COUNT phase already ran)
-    auto write_phase = [&](int it, int tile) {
-        const int stage = it % stages, buf = it & 1;
-        if (warp == 0) {
-            const unsigned int total = s_total[buf];
+            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) lb_publish(fp.tile_state, tile, total);
             const unsigned long long excl = lb_walk(fp.tile_state, tile, total, lane);
             if (lane == 0) {
-                s_tile_excl = excl;
+                sm.tile_excl[buf] = excl;
                 if (tile == fp.num_tiles - 1) *fp.out_count = excl + total;
             }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&sm.off_ready[buf]);
+                // refill the stage the workers are writing out right now (tile it-1) as soon as they are done
+                if (it >= 1) {
+                    const int ps_ = (stage + STAGES - 1) % STAGES;
+                    mbar_wait(&sm.stage_free[ps_], (uint32_t)(((it - 1) / STAGES) & 1));
+                    issue(ps_);
+                }
+            }
+            __syncwarp();
+            stage = stage + 1 == STAGES ? 0 : stage + 1;
         }
-        __syncthreads();
-        const unsigned long long tile_excl = s_tile_excl;
-        const uint32_t fl = s_flags[buf][tid];
-        const uint32_t keep = fl & 0xffffu, rownull = fl >> 16;
-        const int64_t e0 = (int64_t)tile * TILE + tid;
-        uint32_t inrange = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            if (e0 + (int64_t)j * FP_THREADS < fp.n_rows) inrange |= 1u << j;
-        int64_t pos[K];
+        return;
+    }
+
+    // ================================ WORKERS ================================
+    const unsigned int ltmask = (1u << lane) - 1u;
+
+    auto write_tile = [&](int it, int stage, int tile) {
+        const int buf = it & 1;
+        mbar_wait(&sm.off_ready[buf], (uint32_t)((it >> 1) & 1));
+        const unsigned long long tile_excl = sm.tile_excl[buf];
+        uint32_t keep = 0, rownull = 0;
+        unsigned int idx[K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            const unsigned b = __ballot_sync(0xffffffffu, (keep >> j) & 1u);
-            pos[j] = (int64_t)(tile_excl + s_cnt[buf][j * FP_WARPS + warp] + __popc(b & ((1u << lane) - 1u)));
+            const unsigned int b = sm.keep[buf][j][warp];
+            keep |= ((b >> lane) & 1u) << j;
+            idx[j] = sm.offs[buf][j][warp] + __popc(b & ltmask);
+            if (NULLS) rownull |= ((sm.rownull[buf][j][warp] >> lane) & 1u) << j;
         }
-        const SmemRows rows{smem_dyn + (size_t)stage * tp.stage_bytes, s_voff, s_boff, tid, FP_THREADS};
+        const SmemRows rows{smem_dyn + (size_t)stage * tp.stage_bytes, sm.voff, sm.boff, tid, FP_THREADS};
         const uint32_t active = keep & ~rownull;
         for (int o = 0; o < fp.n_out; o++) {
             RowRegs<K> r;
-            run_program_on<K>(ps, 1 + o, rows, inrange, active, rownull, r, fp.status);
+            run_program_on<K, NULLS>(ps, 1 + o, rows, ALL, active, rownull, r, fp.status);
             if (ps.prog_type[1 + o] == T_BOOL) {
-                uint8_t *out = (uint8_t *)fp.out_values[o];
+                uint8_t *out = (uint8_t *)fp.out_values[o] + tile_excl;
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((keep >> j) & 1u) out[pos[j]] = (uint8_t)(r.v[j] & 1);
+                    if ((keep >> j) & 1u) out[idx[j]] = (uint8_t)(r.v[j] & 1);
             } else {
-                uint64_t *out = (uint64_t *)fp.out_values[o];
+                uint64_t *out = (uint64_t *)fp.out_values[o] + tile_excl;
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((keep >> j) & 1u) out[pos[j]] = ((r.valid >> j) & 1u) ? r.v[j] : 0ull;
+                    if ((keep >> j) & 1u) out[idx[j]] = (!NULLS || ((r.valid >> j) & 1u)) ? r.v[j] : 0ull;
             }
-            if (fp.out_valid[o]) {
-                uint8_t *ov = fp.out_valid[o];
+            if (NULLS && fp.out_valid[o]) {
+                uint8_t *ov = fp.out_valid[o] + tile_excl;
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((keep >> j) & 1u) ov[pos[j]] = (uint8_t)((r.valid >> j) & 1u);
+                    if ((keep >> j) & 1u) ov[idx[j]] = (uint8_t)((r.valid >> j) & 1u);
             }
         }
-        __syncthreads(); // stage buffer, s_flags[buf], s_cnt[buf], s_tile_excl are free again
-        if (tid == 0) issue(stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.stage_free[stage]);
     };
 
-    if (tid < NQE_MAX_COLS) {
-        s_voff[tid] = tp.voff16[tid];
-        s_boff[tid] = tp.boff16[tid];
+    int stage = 0, prev_stage = 0, prev_tile = -1, it = 0;
+    uint32_t full_phase = 0;
+    for (;; it++) {
+        const int buf = it & 1;
+        mbar_wait(&sm.full[stage], full_phase);
+        const int tile = sm.tile_id[stage];
+        if (tile >= fp.tile_end) break;
+        {
+            // ---- count phase of tile `it`
+            const SmemRows rows{smem_dyn + (size_t)stage * tp.stage_bytes, sm.voff, sm.boff, tid, FP_THREADS};
+            RowRegs<K> m;
+            run_program_on<K, NULLS>(ps, 0, rows, ALL, ALL, 0u, m, fp.status);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const bool isnull = NULLS && !((m.valid >> j) & 1u); // predicate NULL: keep as an all-NULL row
+                const unsigned kb = __ballot_sync(0xffffffffu, isnull || (m.v[j] & 1));
+                if (lane == 0) sm.keep[buf][j][warp] = kb;
+                if (NULLS) {
+                    const unsigned nb = __ballot_sync(0xffffffffu, isnull);
+                    if (lane == 0) sm.rownull[buf][j][warp] = nb;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.cnt_ready[buf]);
+        }
+        if (prev_tile >= 0) write_tile(it - 1, prev_stage, prev_tile);
+        prev_tile = tile;
+        prev_stage = stage;
+        if (++stage == STAGES) {
+            stage = 0;
+            full_phase ^= 1u;
+        }
     }
-    if (tid == 0) {
-        for (int s = 0; s < stages; s++) mbar_init(&s_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < stages; s++) issue(s);
-    }
-    __syncthreads();
-
-    int tile = count_phase(0);
-    for (int it = 0; tile < fp.num_tiles; it++) {
-        const int next = count_phase(it + 1); // publishes tile it+1's aggregate before tile it is written
-        write_phase(it, tile);
-        tile = next;
-    }
+    if (prev_tile >= 0) write_tile(it - 1, prev_stage, prev_tile);
 }
 
 // bytes (0/1 per row) -> LSB-first bitmap; counts zero bytes (nulls) into *zeros
@@ -516,7 +540,9 @@ int32_t launch_fp(nqe_ctx *ctx, bool has_pred, const DevProgramSet &ps, FilterPa
     }
     tp.stage_bytes = (off + 127) & ~127u;
     tp.tx_bytes = tx;
-    if (ok && tp.stage_bytes * 2 > 200 * 1024) ok = false;
+    const int32_t n_full = (int32_t)(fp.n_rows / TILE);
+    if (ok && (tp.stage_bytes * 2 > 200 * 1024 || n_full == 0)) ok = false;
+    int32_t done = 0; // tiles [0, done) handled by the TMA kernel
     if (ok) {
         static int want_stages = 0;
         if (!want_stages) {
@@ -526,29 +552,38 @@ int32_t launch_fp(nqe_ctx *ctx, bool has_pred, const DevProgramSet &ps, FilterPa
         }
         int stages = want_stages;
         while (stages > 2 && (size_t)stages * tp.stage_bytes > 100 * 1024) stages--; // leave room for >= 2 CTAs per SM
+        stages = stages >= 3 ? 3 : 2;
         tp.stages = stages;
-        const size_t dyn = (size_t)stages * tp.stage_bytes;
-        auto kern = filter_project_tma_kernel<K>;
-        NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        const size_t dyn2 = (size_t)stages * tp.stage_bytes;
+        void (*kern)(DevProgramSet, FilterParams, TmaParams) =
+            stages == 3 ? (ps.any_nulls ? filter_project_ws_kernel<K, 3, true> : filter_project_ws_kernel<K, 3, false>)
+                        : (ps.any_nulls ? filter_project_ws_kernel<K, 2, true> : filter_project_ws_kernel<K, 2, false>);
+        NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
         int occ = 0;
-        NQE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FP_THREADS, dyn));
-        if (occ < 1) ok = false;
-        if (ok) {
+        NQE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WS_THREADS, dyn2));
+        if (occ >= 1) {
             int grid = ctx->sm_count * occ;
-            if (grid > fp.num_tiles) grid = fp.num_tiles;
-            kern<<<grid, FP_THREADS, dyn, ctx->stream>>>(ps, fp, tp);
+            if (grid > n_full) grid = n_full;
+            fp.tile_end = n_full;
+            kern<<<grid, WS_THREADS, dyn2, ctx->stream>>>(ps, fp, tp);
             ctx->launches++;
             NQE_CUDA(ctx, cudaGetLastError());
-            return NQE_OK;
+            done = n_full;
         }
     }
-    int occ = 0;
-    NQE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_project_kernel<K, true>, FP_THREADS, 0));
-    int grid = ctx->sm_count * (occ > 0 ? occ : 1);
-    if (grid > fp.num_tiles) grid = fp.num_tiles;
-    filter_project_kernel<K, true><<<grid, FP_THREADS, 0, ctx->stream>>>(ps, fp);
-    ctx->launches++;
-    NQE_CUDA(ctx, cudaGetLastError());
+    if (done < fp.num_tiles) {
+        // the ragged last tile (or everything, when the TMA path is not applicable): direct-load kernel,
+        // continuing the same look-back chain; it draws tickets from its own counter word
+        fp.tile_base = done;
+        fp.ticket += 1;
+        int occ = 0;
+        NQE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_project_kernel<K, true>, FP_THREADS, 0));
+        int grid = ctx->sm_count * (occ > 0 ? occ : 1);
+        if (grid > fp.num_tiles - done) grid = fp.num_tiles - done;
+        filter_project_kernel<K, true><<<grid, FP_THREADS, 0, ctx->stream>>>(ps, fp);
+        ctx->launches++;
+        NQE_CUDA(ctx, cudaGetLastError());
+    }
     return NQE_OK;
 }
 
