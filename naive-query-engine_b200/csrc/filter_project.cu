@@ -36,44 +36,13 @@ struct FilterParams {
     int32_t tile_end;   // TMA kernel: tiles [0, tile_end) are handled by this launch (all full)
 };
 
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+#include "lookback_body.inc"
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
-}
-
-// exclusive prefix of kept rows over all tiles before `tile` (called by warp 0)
+// publish + walk (warp 0 of a tile)
 __device__ __forceinline__ unsigned long long lookback(unsigned long long *state, int tile, unsigned long long my_total,
                                                        int lane) {
-    if (lane == 0) st_volatile_u64(state + tile, (tile == 0 ? LB_PREFIX : LB_AGG) | my_total);
-    if (tile == 0) return 0;
-    unsigned long long excl = 0;
-    int idx = tile - 1;
-    while (true) {
-        const int my = idx - lane;
-        unsigned long long s;
-        do {
-            s = my >= 0 ? ld_volatile_u64(state + my) : LB_PREFIX;
-        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-        const unsigned m = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        unsigned long long v = s & LB_MASK;
-        if (m) {
-            const int first = __ffs(m) - 1;
-            if (lane > first) v = 0;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (m) break;
-        idx -= 32;
-    }
-    if (lane == 0) st_volatile_u64(state + tile, LB_PREFIX | (excl + my_total));
-    return excl;
+    if (lane == 0) nqe_lb_publish(state, tile, my_total);
+    return nqe_lb_walk(state, tile, my_total, lane);
 }
 
 template <int K, bool HAS_PRED>
@@ -228,36 +197,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-__device__ __forceinline__ void lb_publish(unsigned long long *state, int tile, unsigned long long total) {
-    st_volatile_u64(state + tile, (tile == 0 ? LB_PREFIX : LB_AGG) | total);
-}
-// walk back over predecessors' aggregates until an inclusive prefix is found (warp 0)
-__device__ __forceinline__ unsigned long long lb_walk(unsigned long long *state, int tile, unsigned long long my_total, int lane) {
-    if (tile == 0) return 0;
-    unsigned long long excl = 0;
-    int idx = tile - 1;
-    while (true) {
-        const int my = idx - lane;
-        unsigned long long s;
-        do {
-            s = my >= 0 ? ld_volatile_u64(state + my) : LB_PREFIX;
-        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-        const unsigned m = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        unsigned long long v = s & LB_MASK;
-        if (m) {
-            const int first = __ffs(m) - 1;
-            if (lane > first) v = 0;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (m) break;
-        idx -= 32;
-    }
-    if (lane == 0) st_volatile_u64(state + tile, LB_PREFIX | (excl + my_total));
-    return excl;
-}
-
 // ---------------------------------------------------------------------------
 // Warp-specialised, software-pipelined persistent kernel (the hot path).
 //
@@ -371,8 +310,8 @@ filter_project_ws_kernel(const __grid_constant__ DevProgramSet ps, const __grid_
                 run += c[q];
             }
             const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) lb_publish(fp.tile_state, tile, total);
-            const unsigned long long excl = lb_walk(fp.tile_state, tile, total, lane);
+            if (lane == 0) nqe_lb_publish(fp.tile_state, tile, total);
+            const unsigned long long excl = nqe_lb_walk(fp.tile_state, tile, total, lane);
             if (lane == 0) {
                 sm.tile_excl[buf] = excl;
                 if (tile == fp.num_tiles - 1) *fp.out_count = excl + total;
@@ -598,6 +537,11 @@ int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *
     return NQE_OK;
 }
 
+int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
+                               std::string *source_out);
+
 static int32_t status_to_error(nqe_ctx *ctx, uint32_t st) {
     if (st & DEV_ERR_DIV0) return nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error");
     if (st & DEV_ERR_OVERFLOW) return nqe_fail(ctx, NQE_ERR_PANIC, "attempt to divide with overflow");
@@ -683,14 +627,18 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
         K = e ? atoi(e) : 8;
         if (K != 2 && K != 4 && K != 8) K = 8;
     }
-    const int64_t num_tiles = (n + K * FP_THREADS - 1) / (K * FP_THREADS);
+    const int64_t num_tiles = (n + 255) / 256; // look-back words for the smallest tile any kernel variant uses
     if (rc == NQE_OK && predicate) {
         rc = nqe_dev_alloc(ctx, &lb, (size_t)(num_tiles + 1) * 8);
         if (rc == NQE_OK && cudaMemsetAsync(lb, 0, (size_t)(num_tiles + 1) * 8, ctx->stream) != cudaSuccess) rc = NQE_ERR_CUDA;
         fp.tile_state = (unsigned long long *)lb;
     }
     OpTimer timer(ctx);
-    if (rc == NQE_OK)
+    bool jit_used = false;
+    if (rc == NQE_OK && !ps.any_nulls) // query-shape specialised kernel (jit.cu); falls through when not applicable
+        rc = nqe_jit_filter_project(ctx, in, predicate, projs, n_projs, fp.out_values, fp.tile_state, fp.ticket,
+                                    fp.out_count, fp.status, &jit_used, nullptr);
+    if (rc == NQE_OK && !jit_used)
         rc = K == 2 ? launch_fp<2>(ctx, predicate != nullptr, ps, fp)
            : K == 4 ? launch_fp<4>(ctx, predicate != nullptr, ps, fp)
                     : launch_fp<8>(ctx, predicate != nullptr, ps, fp);

@@ -139,42 +139,11 @@ struct ProbeParams {
     int32_t num_tiles;
 };
 
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
-}
+#include "lookback_body.inc"
 
 __device__ __forceinline__ unsigned long long lookback(unsigned long long *state, int tile, unsigned long long my_total, int lane) {
-    if (lane == 0) st_volatile_u64(state + tile, (tile == 0 ? LB_PREFIX : LB_AGG) | my_total);
-    if (tile == 0) return 0;
-    unsigned long long excl = 0;
-    int idx = tile - 1;
-    while (true) {
-        const int my = idx - lane;
-        unsigned long long s;
-        do {
-            s = my >= 0 ? ld_volatile_u64(state + my) : LB_PREFIX;
-        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-        const unsigned m = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        unsigned long long v = s & LB_MASK;
-        if (m) {
-            const int first = __ffs(m) - 1;
-            if (lane > first) v = 0;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (m) break;
-        idx -= 32;
-    }
-    if (lane == 0) st_volatile_u64(state + tile, LB_PREFIX | (excl + my_total));
-    return excl;
+    if (lane == 0) nqe_lb_publish(state, tile, my_total);
+    return nqe_lb_walk(state, tile, my_total, lane);
 }
 
 __device__ __forceinline__ void emit_value(const ColSrc &c, int64_t src_row, void *out_values, uint8_t *out_valid, int64_t pos) {

@@ -1,0 +1,576 @@
+// jit.cu -- query-shape specialisation of the filter/project kernel.
+//
+// The expression trees of one SelectionPlan + ProjectionPlan pair are turned into
+// straight-line CUDA C++ (one typed expression per output, literals and column
+// pointers stay kernel parameters, so the compiled kernel depends only on the
+// SHAPE of the query), compiled for sm_100a with NVRTC and cached per context
+// process.  The hand-written skeleton below is the same algorithm as the
+// interpreter kernels in filter_project.cu (tile ticket, ballot ranks, decoupled
+// look-back, contiguous warp stores); only the per-row arithmetic is generated.
+//
+// Applies when no referenced column has a validity bitmap and no literal is NULL;
+// everything else runs on the pre-compiled interpreter kernels.  If libnvrtc is
+// not present the interpreter kernels are used as well (NQE_JIT=0 forces that).
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "nqe_internal.cuh"
+
+namespace {
+
+const char *kLookbackSrc =
+#include "build/lookback_body.inc.h"
+    ;
+
+const char *kSkeletonHead = R"SRC(
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+struct JP {
+    const u64 *col[16];
+    void *out[16];
+    u64 lit[32];
+    i64 n_rows;
+    u64 *tile_state;
+    u32 *ticket;
+    u64 *out_count;
+    u32 *status;
+    int num_tiles;
+    int pad;
+};
+#define THREADS 256
+#define WARPS 8
+#define LB_AGG (1ull << 62)
+#define LB_PREFIX (2ull << 62)
+#define LB_MASK ((1ull << 62) - 1)
+#define I64_MIN (-9223372036854775807ll - 1)
+
+__device__ __forceinline__ u64 ldg_stream(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u64 ld_vol(const u64 *p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_vol(u64 *p, u64 v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v)); }
+
+// arrow 13 divide / modulus semantics (see expr_eval.cuh)
+__device__ __forceinline__ i64 nqe_div_i64(i64 x, i64 y, bool live, u32 *st) {
+    if (y == 0) { if (live) atomicOr(st, 1u); return 0; }
+    if (y == -1) { if (x == I64_MIN) { if (live) atomicOr(st, 2u); return 0; } return -x; }
+    return x / y;
+}
+__device__ __forceinline__ i64 nqe_mod_i64(i64 x, i64 y, bool live, u32 *st) {
+    if (y == 0) { if (live) atomicOr(st, 1u); return 0; }
+    if (y == -1) { if (x == I64_MIN && live) atomicOr(st, 2u); return 0; }
+    return x % y;
+}
+__device__ __forceinline__ u64 nqe_div_u64(u64 x, u64 y, bool live, u32 *st) {
+    if (y == 0) { if (live) atomicOr(st, 1u); return 0; }
+    return x / y;
+}
+__device__ __forceinline__ u64 nqe_mod_u64(u64 x, u64 y, bool live, u32 *st) {
+    if (y == 0) { if (live) atomicOr(st, 1u); return 0; }
+    return x % y;
+}
+__device__ __forceinline__ double nqe_div_f64(double x, double y, bool live, u32 *st) {
+    if (y == 0.0 && live) atomicOr(st, 1u);
+    return x / y;
+}
+__device__ __forceinline__ double nqe_mod_f64(double x, double y, bool live, u32 *st) {
+    if (y == 0.0 && live) atomicOr(st, 1u);
+    return fmod(x, y);
+}
+
+)SRC";
+
+// Count-ahead skeleton.  Every CTA keeps D claimed tiles "counted but not yet written":
+//   count(t) : load the predicate's columns, evaluate it, publish the tile aggregate
+//   write(t) : D iterations later -- re-load the columns (the predicate's now come from
+//              L2), re-evaluate, rank, resolve the exclusive prefix by look-back (all
+//              predecessors were counted long ago, so the walk does not wait), project, store
+// The HBM loads of count(next) are issued before write(t) and consumed after it, so
+// their latency overlaps the write phase.
+const char *kSkeletonKernel = R"SRC(
+#if HAS_PRED
+extern "C" __global__ void __launch_bounds__(THREADS) nqe_fp_jit(const __grid_constant__ JP p) {
+    __shared__ u32 s_cnt[K * WARPS];
+    __shared__ u32 s_wsum[WARPS];
+    __shared__ u64 s_tile_excl;
+    __shared__ int s_ring_tile[D];
+    __shared__ u32 s_ring_total[D];
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 ltmask = (1u << lane) - 1u;
+    const int TILE = K * THREADS;
+
+    // ---- prologue: claim and count D tiles
+    for (int d = 0; d < D; d++) {
+        if (tid == 0) s_ring_tile[d] = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int tile = s_ring_tile[d];
+        if (tile < p.num_tiles) {
+            const i64 e0 = (i64)tile * TILE + tid;
+            const bool full = (i64)(tile + 1) * TILE <= p.n_rows;
+            LOAD_PRED_COLUMNS
+            u32 wsum = 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const bool inr = full || (e0 + (i64)j * THREADS < p.n_rows);
+                const bool keep = inr && (PRED_EXPR);
+                wsum += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            if (lane == 0) s_wsum[warp] = wsum;
+            __syncthreads();
+            if (tid == 0) {
+                u32 total = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; w++) total += s_wsum[w];
+                s_ring_total[d] = total;
+                nqe_lb_publish(p.tile_state, tile, total);
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int head = 0;; head = head + 1 == D ? 0 : head + 1) {
+        const int tile = s_ring_tile[head];
+        if (tile >= p.num_tiles) break;
+        const u32 my_total = s_ring_total[head];
+        if (tid == 0) s_next = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int next = s_next;
+        // ---- start the HBM loads of count(next)
+        const bool has_next = next < p.num_tiles;
+        const i64 n0 = (i64)next * TILE + tid;
+        const bool nfull = (i64)(next + 1) * TILE <= p.n_rows;
+        DECL_NEXT_COLUMNS
+        if (has_next) {
+            LOAD_NEXT_COLUMNS
+        }
+        // ---- write(tile)
+        {
+            const i64 e0 = (i64)tile * TILE + tid;
+            const bool full = (i64)(tile + 1) * TILE <= p.n_rows;
+            LOAD_COLUMNS
+            bool keep[K];
+            u32 bal[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const bool inr = full || (e0 + (i64)j * THREADS < p.n_rows);
+                keep[j] = inr && (PRED_EXPR);
+                bal[j] = __ballot_sync(0xffffffffu, keep[j]);
+                if (lane == 0) s_cnt[j * WARPS + warp] = __popc(bal[j]);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const int N = K * WARPS, PER = (N + 31) / 32;
+                u32 c[PER], sum = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    const int i = lane * PER + q;
+                    c[q] = i < N ? s_cnt[i] : 0;
+                    sum += c[q];
+                }
+                u32 incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                u32 run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    const int i = lane * PER + q;
+                    if (i < N) s_cnt[i] = run;
+                    run += c[q];
+                }
+                const u64 excl = nqe_lb_walk(p.tile_state, tile, my_total, lane);
+                if (lane == 0) {
+                    s_tile_excl = excl;
+                    if (tile == p.num_tiles - 1) *p.out_count = excl + my_total;
+                }
+            }
+            __syncthreads();
+            const u64 tile_excl = s_tile_excl;
+            u32 idx[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) idx[j] = s_cnt[j * WARPS + warp] + __popc(bal[j] & ltmask);
+            STORE_OUTPUTS
+        }
+        // ---- finish count(next): its loads have been in flight during the write phase
+        if (has_next) {
+            u32 wsum = 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const bool inr = nfull || (n0 + (i64)j * THREADS < p.n_rows);
+                const bool keep = inr && (NEXT_PRED_EXPR);
+                wsum += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            if (lane == 0) s_wsum[warp] = wsum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_ring_tile[head] = next;
+            if (has_next) {
+                u32 total = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; w++) total += s_wsum[w];
+                s_ring_total[head] = total;
+                nqe_lb_publish(p.tile_state, next, total);
+            }
+        }
+        __syncthreads();
+    }
+}
+#else
+extern "C" __global__ void __launch_bounds__(THREADS) nqe_fp_jit(const __grid_constant__ JP p) {
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const i64 e0 = (i64)tile * (K * THREADS) + tid;
+    const bool full = (i64)(tile + 1) * (K * THREADS) <= p.n_rows;
+    LOAD_COLUMNS
+    bool keep[K];
+    u32 idx[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        keep[j] = full || (e0 + (i64)j * THREADS < p.n_rows);
+        idx[j] = j * THREADS + tid;
+    }
+    const u64 tile_excl = (u64)tile * (K * THREADS);
+    STORE_OUTPUTS
+}
+#endif
+)SRC";
+
+struct TNode {
+    int kind, op, dtype, col, lit; // col: column slot; lit: literal slot
+    int left = -1, right = -1;
+};
+
+struct Gen {
+    const nqe_table *in;
+    std::vector<int> col_of_slot; // table column per slot
+    std::vector<uint64_t> lits;
+    std::vector<TNode> nodes;
+
+    int slot_of(int col) {
+        for (size_t s = 0; s < col_of_slot.size(); s++)
+            if (col_of_slot[s] == col) return (int)s;
+        col_of_slot.push_back(col);
+        return (int)col_of_slot.size() - 1;
+    }
+
+    // parse one postfix program; returns root index or -1 when the JIT does not apply
+    int parse(const nqe_expr *ex) {
+        std::vector<int> st;
+        for (int i = 0; i < ex->n_nodes; i++) {
+            const nqe_expr_node &s = ex->nodes[i];
+            TNode n{};
+            n.kind = s.kind; n.op = s.op;
+            if (s.kind == NQE_NODE_COLUMN) {
+                const DevColumn &c = in->cols[s.column];
+                if (c.validity || c.dtype == NQE_UTF8) return -1;
+                n.dtype = c.dtype;
+                n.col = slot_of(s.column);
+                if (col_of_slot.size() > 16) return -1;
+            } else if (s.kind == NQE_NODE_LITERAL) {
+                if (s.is_null) return -1;
+                n.dtype = s.dtype;
+                n.lit = (int)lits.size();
+                lits.push_back(s.dtype == NQE_BOOL ? (s.value.u64 ? 1 : 0) : s.value.u64);
+                if (lits.size() > 32) return -1;
+            } else if (s.kind == NQE_NODE_BINARY) {
+                n.right = st.back(); st.pop_back();
+                n.left = st.back(); st.pop_back();
+                const int lt = nodes[n.left].dtype;
+                n.dtype = (s.op <= NQE_OP_GT_EQ || s.op == NQE_OP_AND || s.op == NQE_OP_OR) ? NQE_BOOL : lt;
+            } else {
+                n.left = st.back(); st.pop_back();
+                n.dtype = NQE_FLOAT64;
+            }
+            nodes.push_back(n);
+            st.push_back((int)nodes.size() - 1);
+        }
+        return st.back();
+    }
+
+    static const char *ctype(int dt) {
+        return dt == NQE_INT64 ? "i64" : dt == NQE_UINT64 ? "u64" : dt == NQE_FLOAT64 ? "double" : "bool";
+    }
+
+    // typed C expression for row j of this thread
+    std::string emit(int n, const char *live, const char *v = "c") {
+        const TNode &t = nodes[n];
+        std::ostringstream o;
+        if (t.kind == NQE_NODE_COLUMN) {
+            if (t.dtype == NQE_INT64) o << "((i64)" << v << t.col << "_[j])";
+            else if (t.dtype == NQE_UINT64) o << "(" << v << t.col << "_[j])";
+            else if (t.dtype == NQE_FLOAT64) o << "__longlong_as_double((i64)" << v << t.col << "_[j])";
+            else o << "(" << v << t.col << "_[j] != 0)";
+            return o.str();
+        }
+        if (t.kind == NQE_NODE_LITERAL) {
+            if (t.dtype == NQE_INT64) o << "((i64)p.lit[" << t.lit << "])";
+            else if (t.dtype == NQE_UINT64) o << "(p.lit[" << t.lit << "])";
+            else if (t.dtype == NQE_FLOAT64) o << "__longlong_as_double((i64)p.lit[" << t.lit << "])";
+            else o << "(p.lit[" << t.lit << "] != 0)";
+            return o.str();
+        }
+        if (t.kind == NQE_NODE_UNARY) {
+            const std::string a = emit(t.left, live, v);
+            if (t.op == NQE_FN_ABS) return "fabs(" + a + ")";
+            if (t.op == NQE_FN_SIN) return "sin(" + a + ")";
+            return "cos(" + a + ")"; // Cos and Tan (unary.rs:96)
+        }
+        const std::string a = emit(t.left, live, v), b = emit(t.right, live, v);
+        const int lt = nodes[t.left].dtype;
+        static const char *cmp[] = {"==", "!=", "<", "<=", ">", ">="};
+        if (t.op <= NQE_OP_GT_EQ) return "(" + a + " " + cmp[t.op] + " " + b + ")";
+        if (t.op == NQE_OP_AND) return "(" + a + " & " + b + ")"; // both sides always evaluated
+        if (t.op == NQE_OP_OR) return "(" + a + " | " + b + ")";
+        const char *sfx = lt == NQE_INT64 ? "i64" : lt == NQE_UINT64 ? "u64" : "f64";
+        if (t.op == NQE_OP_DIVIDE) return std::string("nqe_div_") + sfx + "(" + a + ", " + b + ", " + live + ", p.status)";
+        if (t.op == NQE_OP_MODULOS) return std::string("nqe_mod_") + sfx + "(" + a + ", " + b + ", " + live + ", p.status)";
+        if (lt == NQE_FLOAT64) {
+            const char *fn = t.op == NQE_OP_PLUS ? "__dadd_rn" : t.op == NQE_OP_MINUS ? "__dsub_rn" : "__dmul_rn";
+            return std::string(fn) + "(" + a + ", " + b + ")";
+        }
+        const char *sym = t.op == NQE_OP_PLUS ? "+" : t.op == NQE_OP_MINUS ? "-" : "*";
+        const std::string r = "((u64)" + a + " " + sym + " (u64)" + b + ")"; // wrapping
+        return lt == NQE_INT64 ? "((i64)" + r + ")" : r;
+    }
+};
+
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+    bool ok = false;
+};
+
+Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *e = getenv("NQE_JIT");
+        if (e && !strcmp(e, "0")) return;
+        const char *names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+        for (const char *nm : names)
+            if ((n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!n.h) return;
+#define NQE_SYM(f) *(void **)(&n.f) = dlsym(n.h, "nvrtc" #f); if (!n.f) return;
+        NQE_SYM(CreateProgram) NQE_SYM(CompileProgram) NQE_SYM(GetCUBINSize) NQE_SYM(GetCUBIN)
+        NQE_SYM(GetProgramLogSize) NQE_SYM(GetProgramLog) NQE_SYM(DestroyProgram)
+#undef NQE_SYM
+        n.ok = true;
+    });
+    return n;
+}
+
+struct JitParams {
+    const void *col[16];
+    void *out[16];
+    uint64_t lit[32];
+    int64_t n_rows;
+    unsigned long long *tile_state;
+    unsigned int *ticket;
+    unsigned long long *out_count;
+    uint32_t *status;
+    int32_t num_tiles;
+    int32_t pad;
+};
+
+struct CachedKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    bool failed = false;
+};
+
+std::map<std::string, CachedKernel> &cache() {
+    static std::map<std::string, CachedKernel> c;
+    return c;
+}
+std::mutex &cache_mutex() {
+    static std::mutex m;
+    return m;
+}
+
+} // namespace
+
+// Returns NQE_OK and sets *used = true when the specialised kernel was launched;
+// *used = false means "not applicable, use the interpreter kernels".
+int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
+                               std::string *source_out) {
+    *used = false;
+    Nvrtc &rt = nvrtc();
+    if (!rt.ok && !source_out) return NQE_OK;
+    static int K = 0;
+    if (!K) {
+        const char *e = getenv("NQE_JIT_K");
+        K = e ? atoi(e) : 4;
+        if (K != 1 && K != 2 && K != 4 && K != 8) K = 4;
+    }
+    Gen g;
+    g.in = in;
+    int pred_root = -1;
+    if (predicate) {
+        pred_root = g.parse(predicate);
+        if (pred_root < 0) return NQE_OK;
+    }
+    const size_t n_pred_cols = g.col_of_slot.size();
+    std::vector<int> roots;
+    for (int i = 0; i < n_projs; i++) {
+        const int r = g.parse(&projs[i]);
+        if (r < 0) return NQE_OK;
+        roots.push_back(r);
+    }
+    // ---- generate the source (depends on the query shape only)
+    std::ostringstream src;
+    static int D = 0;
+    if (!D) {
+        const char *e = getenv("NQE_JIT_D");
+        D = e ? atoi(e) : 2;
+        if (D < 1 || D > 8) D = 2;
+    }
+    src << "#define K " << K << "\n#define D " << D << "\n#define HAS_PRED " << (predicate ? 1 : 0) << "\n";
+    // column slots used by the predicate are parsed first, so they are slots [0, n_pred_cols)
+    auto emit_loads = [&](std::ostringstream &o, size_t first, size_t last, const char *v, const char *e0, const char *full, bool decl) {
+        for (size_t s = first; s < last; s++) {
+            const int dt = in->cols[g.col_of_slot[s]].dtype;
+            if (decl) o << "u64 " << v << s << "_[K];\n";
+            o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; ";
+            if (dt == NQE_BOOL)
+                o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull; }\n";
+            else
+                o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
+        }
+    };
+    std::ostringstream loads, pred_loads, next_decl, next_loads;
+    emit_loads(loads, 0, g.col_of_slot.size(), "c", "e0", "full", true);
+    emit_loads(pred_loads, 0, n_pred_cols, "c", "e0", "full", true);
+    for (size_t s = 0; s < n_pred_cols; s++) next_decl << "u64 n" << s << "_[K];\n";
+    emit_loads(next_loads, 0, n_pred_cols, "n", "n0", "nfull", false);
+    std::ostringstream stores;
+    for (int o = 0; o < n_projs; o++) {
+        const TNode &r = g.nodes[roots[o]];
+        stores << "{ ";
+        if (r.dtype == NQE_BOOL) stores << "u8 *out = (u8 *)p.out[" << o << "] + tile_excl;\n";
+        else stores << "u64 *out = (u64 *)p.out[" << o << "] + tile_excl;\n";
+        stores << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const " << Gen::ctype(r.dtype) << " v = "
+               << g.emit(roots[o], "keep[j]") << "; if (keep[j]) out[idx[j]] = ";
+        if (r.dtype == NQE_FLOAT64) stores << "(u64)__double_as_longlong(v)";
+        else if (r.dtype == NQE_BOOL) stores << "(u8)v";
+        else stores << "(u64)v";
+        stores << "; } }\n";
+    }
+    std::string pred_expr = predicate ? g.emit(pred_root, "inr") : "true";
+    std::string next_pred_expr = predicate ? g.emit(pred_root, "inr", "n") : "true";
+    auto replace_all = [](std::string s, const std::string &a, const std::string &b) {
+        size_t pos = 0;
+        while ((pos = s.find(a, pos)) != std::string::npos) {
+            s.replace(pos, a.size(), b);
+            pos += b.size();
+        }
+        return s;
+    };
+    std::string kernel = kSkeletonKernel;
+    kernel = replace_all(kernel, "LOAD_PRED_COLUMNS", pred_loads.str());
+    kernel = replace_all(kernel, "DECL_NEXT_COLUMNS", next_decl.str());
+    kernel = replace_all(kernel, "LOAD_NEXT_COLUMNS", next_loads.str());
+    kernel = replace_all(kernel, "LOAD_COLUMNS", loads.str());
+    kernel = replace_all(kernel, "NEXT_PRED_EXPR", next_pred_expr);
+    kernel = replace_all(kernel, "PRED_EXPR", pred_expr);
+    kernel = replace_all(kernel, "STORE_OUTPUTS", stores.str());
+    const std::string source = src.str() + kSkeletonHead + kLookbackSrc + kernel;
+    if (source_out) {
+        *source_out = source;
+        if (!rt.ok) return NQE_OK;
+    }
+
+    // ---- compile (cached per source text)
+    CachedKernel ck;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex());
+        auto it = cache().find(source);
+        if (it != cache().end()) ck = it->second;
+        else {
+            nvrtcProgram prog;
+            if (rt.CreateProgram(&prog, source.c_str(), "nqe_fp_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) ck.failed = true;
+            if (!ck.failed) {
+                const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=false"};
+                const nvrtcResult r = rt.CompileProgram(prog, 4, opts);
+                if (r != NVRTC_SUCCESS) {
+                    size_t n = 0;
+                    rt.GetProgramLogSize(prog, &n);
+                    std::string log(n, 0);
+                    rt.GetProgramLog(prog, &log[0]);
+                    nqe_fail(ctx, NQE_ERR_CUDA, "NVRTC compile failed: %s", log.c_str());
+                    if (getenv("NQE_JIT_DEBUG")) fprintf(stderr, "NVRTC: %s\n%s\n", log.c_str(), source.c_str());
+                    ck.failed = true;
+                } else {
+                    size_t n = 0;
+                    rt.GetCUBINSize(prog, &n);
+                    std::vector<char> cubin(n);
+                    rt.GetCUBIN(prog, cubin.data());
+                    if (cudaLibraryLoadData(&ck.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+                        cudaLibraryGetKernel(&ck.kernel, ck.lib, "nqe_fp_jit") != cudaSuccess) {
+                        cudaGetLastError();
+                        ck.failed = true;
+                    }
+                }
+                rt.DestroyProgram(&prog);
+            }
+            cache()[source] = ck;
+        }
+    }
+    if (ck.failed) return NQE_OK; // interpreter kernels take over
+
+    JitParams jp;
+    memset(&jp, 0, sizeof jp);
+    for (size_t s = 0; s < g.col_of_slot.size(); s++) jp.col[s] = in->cols[g.col_of_slot[s]].values;
+    for (int o = 0; o < n_projs; o++) jp.out[o] = out_values[o];
+    for (size_t i = 0; i < g.lits.size(); i++) jp.lit[i] = g.lits[i];
+    jp.n_rows = in->nrows;
+    jp.tile_state = tile_state;
+    jp.ticket = ticket;
+    jp.out_count = out_count;
+    jp.status = status;
+    const int64_t tile = (int64_t)K * 256;
+    jp.num_tiles = (int32_t)((in->nrows + tile - 1) / tile);
+    if (jp.num_tiles == 0) { *used = true; return NQE_OK; }
+    int grid = jp.num_tiles;
+    if (predicate) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)ck.kernel, 256, 0) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            occ = 4;
+        }
+        grid = ctx->sm_count * occ;
+        if (grid > jp.num_tiles) grid = jp.num_tiles;
+    }
+    void *args[] = {&jp};
+    NQE_CUDA(ctx, cudaLaunchKernel((const void *)ck.kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+    ctx->launches++;
+    *used = true;
+    return NQE_OK;
+}
