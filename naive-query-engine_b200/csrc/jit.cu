@@ -59,6 +59,11 @@ __device__ __forceinline__ u64 ldg_stream(const u64 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ u64 ldg_keep(const u64 *p, u64 pol) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ u64 ld_vol(const u64 *p) {
     u64 v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -115,6 +120,9 @@ extern "C" __global__ void __launch_bounds__(THREADS) nqe_fp_jit(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 ltmask = (1u << lane) - 1u;
     const int TILE = K * THREADS;
+    u64 pol_keep, pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
     // ---- prologue: claim and count D tiles
     for (int d = 0; d < D; d++) {
@@ -449,12 +457,18 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
     static int D = 0;
     if (!D) {
         const char *e = getenv("NQE_JIT_D");
-        D = e ? atoi(e) : 2;
-        if (D < 1 || D > 8) D = 2;
+        D = e ? atoi(e) : 4;
+        if (D < 1 || D > 8) D = 4;
     }
     src << "#define K " << K << "\n#define D " << D << "\n#define HAS_PRED " << (predicate ? 1 : 0) << "\n";
     // column slots used by the predicate are parsed first, so they are slots [0, n_pred_cols)
-    auto emit_loads = [&](std::ostringstream &o, size_t first, size_t last, const char *v, const char *e0, const char *full, bool decl) {
+    static int HINTS = -1;
+    if (HINTS < 0) {
+        const char *e = getenv("NQE_JIT_L2_HINTS");
+        HINTS = e ? atoi(e) : 0; // measured: no gain on B200 (profiles/README_r01.md)
+    }
+    auto emit_loads = [&](std::ostringstream &o, size_t first, size_t last, const char *v, const char *e0, const char *full, bool decl,
+                          const char *pol = nullptr) {
         for (size_t s = first; s < last; s++) {
             const int dt = in->cols[g.col_of_slot[s]].dtype;
             if (decl) o << "u64 " << v << s << "_[K];\n";
@@ -462,14 +476,17 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
             if (dt == NQE_BOOL)
                 o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull; }\n";
             else
-                o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
+                if (pol && HINTS && predicate)
+                    o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_keep(p.col[" << s << "] + e, " << pol << ") : 0ull; }\n";
+                else
+                    o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
         }
     };
     std::ostringstream loads, pred_loads, next_decl, next_loads;
-    emit_loads(loads, 0, g.col_of_slot.size(), "c", "e0", "full", true);
-    emit_loads(pred_loads, 0, n_pred_cols, "c", "e0", "full", true);
+    emit_loads(loads, 0, g.col_of_slot.size(), "c", "e0", "full", true, "pol_stream");
+    emit_loads(pred_loads, 0, n_pred_cols, "c", "e0", "full", true, "pol_keep");
     for (size_t s = 0; s < n_pred_cols; s++) next_decl << "u64 n" << s << "_[K];\n";
-    emit_loads(next_loads, 0, n_pred_cols, "n", "n0", "nfull", false);
+    emit_loads(next_loads, 0, n_pred_cols, "n", "n0", "nfull", false, "pol_keep");
     std::ostringstream stores;
     for (int o = 0; o < n_projs; o++) {
         const TNode &r = g.nodes[roots[o]];
