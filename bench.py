@@ -440,11 +440,11 @@ def run_secondary(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hb
 
 
 def shuffled_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, world):
-    """Each rank owns 1/world of L (1e7 rows total) and MULTI_PROBE_PER_GPU rows of R.  Both sides are
-    radix-partitioned on the join key (nqe_radix_partition), exchanged with NCCL all-to-all, joined and
-    pre-aggregated locally (nqe_join_aggregate with min(a) carrying the group key), and the partial
-    states are all-gathered and merged with one more nqe_hash_aggregate."""
-    import ctypes as C
+    """BASELINE configs[4] shape, weak-scaled: each rank owns 1/world of L (1e7 rows in total) and
+    MULTI_PROBE_PER_GPU rows of R; the plan is naive-query-engine_b200/distributed.py (radix partition
+    -> NCCL all-to-all -> fused join + partial aggregate -> all-gather + merge)."""
+    from importlib import import_module
+    D = import_module("naive-query-engine_b200.distributed")
     I64, F64 = 2, 4
     col = nq.ColumnExpr.try_create
     nb_total = args.build_rows
@@ -452,86 +452,30 @@ def shuffled_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, 
     npr = args.multi_probe_rows
     with torch.cuda.stream(stream):
         lt0, lb0 = device_table(nq, torch, ctx, synth.join_build_table(nb_total), rank * nb, nb, [I64])
-        lt = pp._filter_project(lt0, None, [col(None, 0), nq.PhysicalBinaryExpr.create(
-            col(None, 0), "Modulos", nq.PhysicalLiteralExpr.create(nq.ScalarValue.Int64(N_GROUPS)))], ["k", "a"])
+        la = torch.remainder(lb0[0], N_GROUPS)
         rt, rb = device_table(nq, torch, ctx, synth.join_probe_table(nb_total), rank * npr, npr, [I64, F64])
-
-    def exchange(t, ncols):
-        h = C.c_void_p()
-        counts = (C.c_int64 * world)()
-        ctx.check(ctx.lib.nqe_radix_partition(ctx.h, t.h, 0, world, C.byref(h), counts))
-        part = nq.DeviceTable(ctx, h, t.names)
-        send = torch.tensor(list(counts), dtype=torch.int64, device="cuda")
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)
-        send_l, recv_l = [int(x) for x in counts], [int(x) for x in recv.tolist()]
-        total = sum(recv_l)
-        outs = []
-        for c in range(ncols):
-            d = part.column_desc(c)
-            src = torch.as_tensor(CAI(d.values, t.num_rows), device="cuda")
-            dst = torch.empty(total, dtype=torch.int64, device="cuda")
-            dist.all_to_all_single(dst, src, output_split_sizes=recv_l, input_split_sizes=send_l)
-            outs.append(dst)
-        torch.cuda.current_stream().synchronize()
-        part.free()
-        return outs, total, sum(send_l) - send_l[rank]
-
-    sent = {"rows": 0}
+    torch.cuda.synchronize()
+    engine = D.CudaEngine(nq, ctx, torch)
+    lcols, rcols = [lb0[0], la], [rb[0], rb[1]]
+    info = {}
 
     def step():
         with torch.cuda.stream(stream):
-            lcols, ln, s1 = exchange(lt, 2)
-            rcols, rn, s2 = exchange(rt, 2)
-            sent["rows"] = s1 + s2
-            L = nq.DeviceTable.from_device_pointers(ctx, ["k", "a"], [I64, I64], [x.data_ptr() for x in lcols], ln, lcols)
-            R = nq.DeviceTable.from_device_pointers(ctx, ["fk", "b"], [I64, F64], [x.data_ptr() for x in rcols], rn, rcols)
-            aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 3), (1, 3), (3, 3), (4, 3), (3, 1)]])
-            h = C.c_void_p()
-            ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, L.h, R.h, 0, 0, 1, aggs, 5, C.byref(h)))
-            part = nq.DeviceTable(ctx, h, ["count", "sum", "min", "max", "key"])
-            g = part.num_rows
-            # all-gather the partial states (count,sum,min,max,key) and merge them
-            sizes = torch.tensor([g], dtype=torch.int64, device="cuda")
-            all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-            dist.all_gather(all_sizes, sizes)
-            gl = [int(x.item()) for x in all_sizes]
-            gmax = max(gl)
-            gathered = []
-            for c in range(5):
-                d = part.column_desc(c)
-                src = torch.zeros(gmax, dtype=torch.int64, device="cuda")
-                src[:g] = torch.as_tensor(CAI(d.values, g), device="cuda")
-                buf = torch.empty(gmax * world, dtype=torch.int64, device="cuda")
-                dist.all_gather_into_tensor(buf, src)
-                gathered.append(torch.cat([buf[r * gmax: r * gmax + gl[r]] for r in range(world)]))
-            torch.cuda.current_stream().synchronize()
-            tot = sum(gl)
-            # count (u64) -> f64 so that the merge can sum it; key is f64 (min(a)) -> i64 group key
-            cnt_f = gathered[0].to(torch.float64).view(torch.int64)
-            key_i = gathered[4].view(torch.float64).to(torch.int64)
-            M = nq.DeviceTable.from_device_pointers(ctx, ["key", "cnt", "sum", "min", "max"], [I64, F64, F64, F64, F64],
-                                                    [key_i.data_ptr(), cnt_f.data_ptr(), gathered[1].data_ptr(),
-                                                     gathered[2].data_ptr(), gathered[3].data_ptr()], tot,
-                                                    [key_i, cnt_f, gathered])
-            torch.cuda.current_stream().synchronize()
-            m_aggs = (nq._ffi.Agg * 4)(*[nq._ffi.Agg(op, c) for op, c in [(1, 1), (1, 2), (3, 3), (4, 4)]])
-            ke, keep = col(None, 0).to_expr(M.names)
-            mh = C.c_void_p()
-            ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, M.h, C.pointer(ke), m_aggs, 4, C.byref(mh)))
-            merged = nq.DeviceTable(ctx, mh, ["count", "sum", "min", "max"])
-            step.groups = merged.num_rows
-            merged.free(); M.free(); part.free(); L.free(); R.free()
+            merged, sent = D.shuffled_join_group_by(dist, torch, engine, lcols, rcols, world)
+            info["groups"] = int(merged[0].numel())
+            info["sent"] = sent
+            info["count_total"] = int(merged[1].sum().item())
 
     for _ in range(2):
         step()
     steps = 3
     ms = timed(torch, dist, world, stream, steps, step)
-    lt0.free(); lt.free(); rt.free()
+    lt0.free(); rt.free()
     return {"workload": f"radix-partitioned hash-join + group-by, {npr} probe rows/GPU, {nb_total} build rows total, "
                         "NCCL all-to-all (BASELINE configs[4] shape, weak-scaled)",
-            "rows_per_s": world * npr * steps / (ms / 1e3), "ms_per_step": ms / steps, "groups": step.groups,
-            "rows_sent_per_gpu": sent["rows"], "nvlink_bytes_sent_per_gpu": sent["rows"] * 16}
+            "rows_per_s": world * npr * steps / (ms / 1e3), "ms_per_step": ms / steps, "groups": info["groups"],
+            "joined_rows_total": info["count_total"], "rows_sent_per_gpu": info["sent"],
+            "nvlink_bytes_sent_per_gpu": info["sent"] * 16}
 
 
 def main():

@@ -13,16 +13,25 @@ constexpr int AG_MAX = 16;
 constexpr uint64_t EMPTY_KEY = 0x8000000000000000ULL; // i64::MIN; its group lives in the extra last record
 constexpr int MAX_PROBE = 256;
 
+constexpr int AG_MAXS = 2 * AG_MAX; // state words (an AVG needs a SUM and a CNT state)
+enum : int32_t { ST_CNT = 0, ST_SUM = 1, ST_MIN = 2, ST_MAX = 3 };
+
+// Aggregates over the same argument share state words: count(v), sum(v), avg(v), min(v),
+// max(v) need {CNT(v), SUM(v), MIN(v), MAX(v)} -- two reductions and two compare-loads per row.
 struct AggParams {
     int64_t n_rows;
-    int32_t n_aggs;
-    int32_t rec_words;
-    int32_t op[AG_MAX];
-    int32_t col_slot[AG_MAX];  // index into DevProgramSet::cols
-    int32_t state_off[AG_MAX]; // word offset of the op's state inside a record
-    unsigned long long *table; // (capacity + 1) records
-    uint64_t mask;             // capacity - 1
+    int32_t n_aggs, n_states, rec_words, pad;
+    int32_t agg_op[AG_MAX];
+    int32_t agg_state[AG_MAX];  // primary state of the aggregate
+    int32_t agg_state2[AG_MAX]; // AVG: its CNT state
+    int32_t st_kind[AG_MAXS];
+    int32_t st_src[AG_MAXS];    // caller-defined source id of the argument column (sorted)
+    int32_t st_off[AG_MAXS];    // word offset of the state inside a record
+    unsigned long long *table;  // (capacity + 1) records: [key | states...]
+    uint64_t mask;              // capacity - 1
     uint32_t *status;
+    int32_t rec_shift;          // log2(rec_words): records are power-of-two sized
+    int32_t hash_shift;         // 64 - log2(capacity)
 };
 
 __device__ __forceinline__ double value_as_f64(int dtype, uint64_t bits) {
@@ -49,58 +58,94 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
-// find-or-claim the record of `key`; returns nullptr when the table is full
-__device__ __forceinline__ unsigned long long *find_slot(const AggParams &ap, uint64_t key) {
-    if (key == EMPTY_KEY) { // i64::MIN has its own record; word 0 != EMPTY marks it occupied
-        unsigned long long *rec = ap.table + (ap.mask + 1) * ap.rec_words;
-        *(volatile unsigned long long *)rec = 0ull;
-        return rec;
+// slot of a key: Fibonacci (multiply-shift) hashing, one 64-bit multiply
+__device__ __forceinline__ uint64_t agg_slot_of(const AggParams &ap, uint64_t key) {
+    return (key * 0x9E3779B97F4A7C15ULL) >> ap.hash_shift;
+}
+__device__ __forceinline__ unsigned long long *agg_rec(const AggParams &ap, uint64_t slot) {
+    return ap.table + (slot << ap.rec_shift);
+}
+
+// one probe step at `slot`: 1 = found/claimed, 0 = occupied by another key
+__device__ __forceinline__ int agg_probe_step(unsigned long long *r, unsigned long long seen, uint64_t key) {
+    if (seen == EMPTY_KEY) seen = atomicCAS(r, (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+    return seen == key || seen == EMPTY_KEY;
+}
+
+// find-or-claim the records of K keys.  The first probe of all K keys is issued together
+// (K independent loads in flight: most keys resolve there at load factor <= 0.5); the rare
+// collisions are then walked one key at a time with a tight loop.  rec[j] == nullptr afterwards:
+// key j was not looked up (want bit clear) or the table is full (status flagged).
+template <int K>
+__device__ __forceinline__ void find_slots(const AggParams &ap, const uint64_t (&key)[K], uint32_t want,
+                                           unsigned long long *(&rec)[K]) {
+    uint64_t slot[K];
+    unsigned long long seen[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        slot[j] = agg_slot_of(ap, key[j]);
+        if ((want >> j) & 1u) seen[j] = ld_relaxed_u64(agg_rec(ap, slot[j]));
     }
-    uint64_t slot = nqe_mix64(key) & ap.mask;
-    for (int probe = 0; probe < MAX_PROBE; probe++) {
-        unsigned long long *rec = ap.table + slot * ap.rec_words;
-        unsigned long long k = ld_relaxed_u64(rec);
-        if (k == key) return rec;
-        if (k == EMPTY_KEY) {
-            k = atomicCAS(rec, (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-            if (k == EMPTY_KEY || k == key) return rec;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        rec[j] = nullptr;
+        if (!((want >> j) & 1u)) continue;
+        if (key[j] == EMPTY_KEY) { // i64::MIN has its own record; word 0 != EMPTY marks it occupied
+            rec[j] = agg_rec(ap, ap.mask + 1);
+            *(volatile unsigned long long *)rec[j] = 0ull;
+            continue;
         }
-        slot = (slot + 1) & ap.mask;
-    }
-    return nullptr;
-}
-
-// one value (already known non-NULL) folded into state word(s) of aggregate a
-__device__ __forceinline__ void update_state(const AggParams &ap, int a, unsigned long long *rec, int dtype,
-                                             uint64_t bits) {
-    unsigned long long *s = rec + ap.state_off[a];
-    const int op = ap.op[a];
-    if (op == NQE_AGG_COUNT) { red_add_u64(s, 1ull); return; }
-    const double v = value_as_f64(dtype, bits);
-    if (op == NQE_AGG_SUM) red_add_f64(s, v);
-    else if (op == NQE_AGG_AVG) { red_add_f64(s, v); red_add_u64(s + 1, 1ull); }
-    else if (op == NQE_AGG_MAX) {
-        const unsigned long long k = nqe_f64_to_ord(v);
-        if (k > ld_relaxed_u64(s)) red_max_u64(s, k);
-    } else if (v == v) { // MIN: `val < self.val` is never true for NaN (min.rs:49)
-        const unsigned long long k = nqe_f64_to_ord(v);
-        if (k < ld_relaxed_u64(s)) red_min_u64(s, k);
+        unsigned long long *r = agg_rec(ap, slot[j]);
+        if (agg_probe_step(r, seen[j], key[j])) { rec[j] = r; continue; }
+        uint64_t s = slot[j];
+        for (int probe = 1; probe < MAX_PROBE; probe++) {
+            s = (s + 1) & ap.mask;
+            r = agg_rec(ap, s);
+            if (agg_probe_step(r, ld_relaxed_u64(r), key[j])) { rec[j] = r; break; }
+        }
+        if (!rec[j]) atomicOr(ap.status, DEV_ERR_TABLE_FULL);
     }
 }
 
-__device__ __forceinline__ void update_record(const AggParams &ap, const DevProgramSet &ps, unsigned long long *rec,
-                                              int64_t e) {
-    for (int a = 0; a < ap.n_aggs; a++) {
-        const DevColRef &c = ps.cols[ap.col_slot[a]];
-        if (c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) continue;
-        const uint64_t bits = ap.op[a] == NQE_AGG_COUNT ? 0ull : ld_cached_u64((const uint64_t *)c.values + e);
-        update_state(ap, a, rec, c.dtype, bits);
+__device__ __forceinline__ unsigned long long *find_slot(const AggParams &ap, uint64_t key) {
+    const uint64_t k1[1] = {key};
+    unsigned long long *r1[1];
+    find_slots<1>(ap, k1, 1u, r1);
+    return r1[0];
+}
+
+// Fold one input row into its group's record.  src(id, &dtype, &bits) -> the argument value
+// of source id for this row is non-NULL.  States are sorted by source id, so a column that
+// feeds several states is fetched once.
+template <typename Src>
+__device__ __forceinline__ void update_states(const AggParams &ap, unsigned long long *rec, const Src &src) {
+    int last = -1, dtype = 0;
+    bool valid = false;
+    uint64_t bits = 0;
+    for (int s = 0; s < ap.n_states; s++) {
+        if (ap.st_src[s] != last) {
+            last = ap.st_src[s];
+            valid = src(last, &dtype, &bits);
+        }
+        if (!valid) continue; // NULL argument: the row does not touch this state
+        unsigned long long *w = rec + ap.st_off[s];
+        const int kind = ap.st_kind[s];
+        if (kind == ST_CNT) { red_add_u64(w, 1ull); continue; }
+        const double v = value_as_f64(dtype, bits);
+        if (kind == ST_SUM) red_add_f64(w, v);
+        else if (kind == ST_MAX) {
+            const unsigned long long k = nqe_f64_to_ord(v);
+            if (k > ld_relaxed_u64(w)) red_max_u64(w, k);
+        } else if (v == v) { // MIN: `val < self.val` is never true for NaN (min.rs:49)
+            const unsigned long long k = nqe_f64_to_ord(v);
+            if (k < ld_relaxed_u64(w)) red_min_u64(w, k);
+        }
     }
 }
 
 // host helpers implemented in hash_aggregate.cu
-int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const int32_t *col_dtypes, bool grouped,
-                       AggParams *ap);
+int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const int32_t *col_dtypes,
+                       const int32_t *src_ids, bool grouped, AggParams *ap);
 int32_t nqe_agg_table_create(nqe_ctx *ctx, AggParams *ap, uint64_t capacity);
 int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64_t max_groups, nqe_table *t);
 uint64_t nqe_agg_capacity(double est);

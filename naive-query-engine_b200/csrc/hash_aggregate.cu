@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "agg_device.cuh"
@@ -24,19 +25,31 @@ namespace {
 __global__ void agg_init_kernel(AggParams ap, uint64_t n_records) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_records) return;
-    unsigned long long *rec = ap.table + r * ap.rec_words;
+    unsigned long long *rec = ap.table + (r << ap.rec_shift);
     rec[0] = EMPTY_KEY;
-    for (int a = 0; a < ap.n_aggs; a++) {
-        unsigned long long *s = rec + ap.state_off[a];
-        switch (ap.op[a]) {
-        case NQE_AGG_COUNT: s[0] = 0; break;
-        case NQE_AGG_SUM: s[0] = 0; break; // +0.0
-        case NQE_AGG_AVG: s[0] = 0; s[1] = 0; break;
-        case NQE_AGG_MIN: s[0] = nqe_f64_to_ord(DBL_MAX); break;  // f64::MAX, min.rs:38
-        case NQE_AGG_MAX: s[0] = nqe_f64_to_ord(-DBL_MAX); break; // f64::MIN, max.rs:38
+    for (int s = 0; s < ap.n_states; s++) {
+        unsigned long long *w = rec + ap.st_off[s];
+        switch (ap.st_kind[s]) {
+        case ST_CNT: *w = 0; break;
+        case ST_SUM: *w = 0; break; // +0.0
+        case ST_MIN: *w = nqe_f64_to_ord(DBL_MAX); break;  // f64::MAX, min.rs:38
+        default: *w = nqe_f64_to_ord(-DBL_MAX); break;     // f64::MIN, max.rs:38
         }
     }
 }
+
+// argument values of one input row, read from the columns registered in DevProgramSet
+struct RowSource {
+    const DevProgramSet &ps;
+    int64_t e;
+    __device__ __forceinline__ bool operator()(int slot, int *dtype, uint64_t *bits) const {
+        const DevColRef &c = ps.cols[slot];
+        if (c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) return false;
+        *dtype = c.dtype;
+        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : ld_cached_u64((const uint64_t *)c.values + e);
+        return true;
+    }
+};
 
 // program 0 of ps = group key expression
 __global__ void __launch_bounds__(AG_THREADS)
@@ -52,17 +65,10 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
         RowRegs<AG_K> key;
         run_program<AG_K>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
         unsigned long long *rec[AG_K];
-#pragma unroll
-        for (int j = 0; j < AG_K; j++) {
-            rec[j] = nullptr;
-            if ((key.valid >> j) & 1u) { // NULL keys are dropped
-                rec[j] = find_slot(ap, key.v[j]);
-                if (!rec[j]) atomicOr(ap.status, DEV_ERR_TABLE_FULL);
-            }
-        }
+        find_slots<AG_K>(ap, key.v, key.valid, rec); // NULL keys are dropped (valid bit clear)
 #pragma unroll
         for (int j = 0; j < AG_K; j++)
-            if (rec[j]) update_record(ap, ps, rec[j], e0 + (int64_t)j * AG_THREADS);
+            if (rec[j]) update_states(ap, rec[j], RowSource{ps, e0 + (int64_t)j * AG_THREADS});
     }
 }
 
@@ -71,19 +77,19 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
 __global__ void __launch_bounds__(AG_THREADS)
 global_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap) {
     const int lane = threadIdx.x & 31;
-    for (int a = 0; a < ap.n_aggs; a++) {
-        const DevColRef &c = ps.cols[ap.col_slot[a]];
-        const int op = ap.op[a];
+    for (int s = 0; s < ap.n_states; s++) {
+        const DevColRef &c = ps.cols[ap.st_src[s]];
+        const int kind = ap.st_kind[s];
         double sum = 0.0;
         unsigned long long cnt = 0;
-        unsigned long long ext = op == NQE_AGG_MIN ? nqe_f64_to_ord(DBL_MAX) : nqe_f64_to_ord(-DBL_MAX);
+        unsigned long long ext = kind == ST_MIN ? nqe_f64_to_ord(DBL_MAX) : nqe_f64_to_ord(-DBL_MAX);
         for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ap.n_rows; e += (int64_t)gridDim.x * blockDim.x) {
             if (c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) continue;
             cnt++;
-            if (op == NQE_AGG_COUNT) continue;
+            if (kind == ST_CNT) continue;
             const double v = value_as_f64(c.dtype, ld_cached_u64((const uint64_t *)c.values + e));
-            if (op == NQE_AGG_SUM || op == NQE_AGG_AVG) sum += v;
-            else if (op == NQE_AGG_MAX) { const unsigned long long k = nqe_f64_to_ord(v); if (k > ext) ext = k; }
+            if (kind == ST_SUM) sum += v;
+            else if (kind == ST_MAX) { const unsigned long long k = nqe_f64_to_ord(v); if (k > ext) ext = k; }
             else if (v == v) { const unsigned long long k = nqe_f64_to_ord(v); if (k < ext) ext = k; }
         }
 #pragma unroll
@@ -91,15 +97,14 @@ global_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_c
             sum += __shfl_xor_sync(0xffffffffu, sum, o);
             cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, ext, o);
-            if (op == NQE_AGG_MIN ? other < ext : other > ext) ext = other;
+            if (kind == ST_MIN ? other < ext : other > ext) ext = other;
         }
         if (lane == 0) {
-            unsigned long long *s = ap.table + ap.state_off[a];
-            if (op == NQE_AGG_COUNT) red_add_u64(s, cnt);
-            else if (op == NQE_AGG_SUM) red_add_f64(s, sum);
-            else if (op == NQE_AGG_AVG) { red_add_f64(s, sum); red_add_u64(s + 1, cnt); }
-            else if (op == NQE_AGG_MAX) red_max_u64(s, ext);
-            else red_min_u64(s, ext);
+            unsigned long long *w = ap.table + ap.st_off[s];
+            if (kind == ST_CNT) red_add_u64(w, cnt);
+            else if (kind == ST_SUM) red_add_f64(w, sum);
+            else if (kind == ST_MAX) red_max_u64(w, ext);
+            else red_min_u64(w, ext);
         }
     }
 }
@@ -117,7 +122,7 @@ __global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_re
     bool occ = false;
     const unsigned long long *rec = nullptr;
     if (r < n_records) {
-        rec = ap.table + r * ap.rec_words;
+        rec = ap.table + (r << ap.rec_shift);
         if (xp.is_global) occ = true;
         else if (r == n_records - 1) {
             // the record of key == i64::MIN is occupied iff any state moved off its identity;
@@ -132,14 +137,16 @@ __global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_re
     if (!occ) return;
     const unsigned long long row = base + __popc(m & ((1u << lane) - 1u));
     for (int a = 0; a < ap.n_aggs; a++) {
-        const unsigned long long *s = rec + ap.state_off[a];
-        switch (ap.op[a]) {
-        case NQE_AGG_COUNT: ((unsigned long long *)xp.out[a])[row] = s[0]; break;
-        case NQE_AGG_SUM: ((unsigned long long *)xp.out[a])[row] = s[0]; break;
-        case NQE_AGG_AVG: // avg.rs:118: sum / cnt as f64, cnt is u32 (wraps in release builds)
-            ((double *)xp.out[a])[row] = __longlong_as_double((long long)s[0]) / (double)(uint32_t)s[1];
+        const unsigned long long w = rec[ap.st_off[ap.agg_state[a]]];
+        switch (ap.agg_op[a]) {
+        case NQE_AGG_COUNT: ((unsigned long long *)xp.out[a])[row] = w; break;
+        case NQE_AGG_SUM: ((unsigned long long *)xp.out[a])[row] = w; break;
+        case NQE_AGG_AVG: { // avg.rs:118: sum / cnt as f64, cnt is u32 (wraps in release builds)
+            const unsigned long long c = rec[ap.st_off[ap.agg_state2[a]]];
+            ((double *)xp.out[a])[row] = __longlong_as_double((long long)w) / (double)(uint32_t)c;
             break;
-        default: ((double *)xp.out[a])[row] = nqe_ord_to_f64(s[0]); break;
+        }
+        default: ((double *)xp.out[a])[row] = nqe_ord_to_f64(w); break;
         }
     }
 }
@@ -178,12 +185,19 @@ static const char *dtype_name2(int d) {
     }
 }
 
-// validate one aggregate against its argument column dtype and lay out its state
-int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const int32_t *col_dtypes, bool grouped,
-                       AggParams *ap) {
+// validate the aggregates against their argument dtypes and lay out the (shared) state words
+int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const int32_t *col_dtypes,
+                       const int32_t *src_ids, bool grouped, AggParams *ap) {
     if (n_aggs < 0 || n_aggs > AG_MAX) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "at most %d aggregates per plan", AG_MAX);
     ap->n_aggs = n_aggs;
-    int words = 1;
+    ap->n_states = 0;
+    auto state_of = [&](int kind, int src) {
+        for (int s = 0; s < ap->n_states; s++)
+            if (ap->st_kind[s] == kind && ap->st_src[s] == src) return s;
+        ap->st_kind[ap->n_states] = kind;
+        ap->st_src[ap->n_states] = src;
+        return ap->n_states++;
+    };
     for (int a = 0; a < n_aggs; a++) {
         const int op = aggs[a].op;
         if (op < NQE_AGG_COUNT || op > NQE_AGG_MAX) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad aggregate op %d", op);
@@ -193,11 +207,44 @@ int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const 
             return nqe_fail(ctx, grouped ? NQE_ERR_PANIC : NQE_ERR_NOT_SUPPORTED, "%s func for %s is not supported",
                             agg_fn_name(op), dtype_name2(dt));
         }
-        ap->op[a] = op;
-        ap->state_off[a] = words;
-        words += op == NQE_AGG_AVG ? 2 : 1;
+        ap->agg_op[a] = op;
+        ap->agg_state2[a] = 0;
+        switch (op) {
+        case NQE_AGG_COUNT: ap->agg_state[a] = state_of(ST_CNT, src_ids[a]); break;
+        case NQE_AGG_SUM: ap->agg_state[a] = state_of(ST_SUM, src_ids[a]); break;
+        case NQE_AGG_AVG:
+            ap->agg_state[a] = state_of(ST_SUM, src_ids[a]);
+            ap->agg_state2[a] = state_of(ST_CNT, src_ids[a]);
+            break;
+        case NQE_AGG_MIN: ap->agg_state[a] = state_of(ST_MIN, src_ids[a]); break;
+        default: ap->agg_state[a] = state_of(ST_MAX, src_ids[a]); break;
+        }
     }
-    ap->rec_words = (words + 3) & ~3; // 32-byte multiple
+    // sort states by source id (stable) so that update_states fetches each column once
+    int order[AG_MAXS], inv[AG_MAXS];
+    for (int s = 0; s < ap->n_states; s++) order[s] = s;
+    std::stable_sort(order, order + ap->n_states, [&](int x, int y) { return ap->st_src[x] < ap->st_src[y]; });
+    int kind2[AG_MAXS], src2[AG_MAXS];
+    for (int i = 0; i < ap->n_states; i++) {
+        kind2[i] = ap->st_kind[order[i]];
+        src2[i] = ap->st_src[order[i]];
+        inv[order[i]] = i;
+    }
+    for (int i = 0; i < ap->n_states; i++) {
+        ap->st_kind[i] = kind2[i];
+        ap->st_src[i] = src2[i];
+        ap->st_off[i] = 1 + i;
+    }
+    for (int a = 0; a < n_aggs; a++) {
+        ap->agg_state[a] = inv[ap->agg_state[a]];
+        ap->agg_state2[a] = inv[ap->agg_state2[a]];
+    }
+    ap->rec_words = 4; // power of two >= 32 bytes: a record never straddles more sectors than needed
+    ap->rec_shift = 2;
+    while (ap->rec_words < 1 + ap->n_states) {
+        ap->rec_words <<= 1;
+        ap->rec_shift++;
+    }
     return NQE_OK;
 }
 
@@ -207,6 +254,9 @@ int32_t nqe_agg_table_create(nqe_ctx *ctx, AggParams *ap, uint64_t capacity) {
     NQE_TRY(nqe_dev_alloc(ctx, &table, (size_t)n_records * ap->rec_words * 8));
     ap->table = (unsigned long long *)table;
     ap->mask = capacity - 1;
+    ap->hash_shift = 64;
+    for (uint64_t c = capacity; c > 1; c >>= 1) ap->hash_shift--;
+    if (capacity < 2) ap->hash_shift = 63; // single-record (global) table: slot 0/1 never used
     agg_init_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->stream>>>(*ap, n_records);
     ctx->launches++;
     NQE_CUDA(ctx, cudaGetLastError());
@@ -229,7 +279,7 @@ int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64
     if (out_cap < 1) out_cap = 1;
     t->cols.resize(ap.n_aggs);
     for (int a = 0; a < ap.n_aggs; a++) {
-        NQE_TRY(nqe_column_alloc(ctx, ap.op[a] == NQE_AGG_COUNT ? NQE_UINT64 : NQE_FLOAT64, out_cap, false, &t->cols[a]));
+        NQE_TRY(nqe_column_alloc(ctx, ap.agg_op[a] == NQE_AGG_COUNT ? NQE_UINT64 : NQE_FLOAT64, out_cap, false, &t->cols[a]));
         xp.out[a] = t->cols[a].values;
     }
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint64_t), ctx->stream));
@@ -278,12 +328,12 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         if (col < 0 || col >= (int)in->cols.size()) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", col);
         dts[a] = in->cols[col].dtype;
     }
-    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, group_expr != nullptr, &ap));
+    int32_t slots[AG_MAX];
     for (int a = 0; a < n_aggs; a++) { // register the argument columns as column slots
         const DevColumn &c = in->cols[aggs[a].column];
         int slot = -1;
-        for (int s = 0; s < ps.n_cols; s++)
-            if (ps.cols[s].values == c.values && ps.cols[s].dtype == c.dtype) slot = s;
+        for (int q = 0; q < ps.n_cols; q++)
+            if (ps.cols[q].values == c.values && ps.cols[q].dtype == c.dtype) slot = q;
         if (slot < 0) {
             if (ps.n_cols >= NQE_MAX_COLS) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "too many distinct columns");
             slot = ps.n_cols++;
@@ -291,8 +341,9 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             ps.cols[slot].validity = (const uint32_t *)c.validity;
             ps.cols[slot].dtype = c.dtype;
         }
-        ap.col_slot[a] = slot;
+        slots[a] = slot;
     }
+    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, slots, group_expr != nullptr, &ap));
     ap.status = (uint32_t *)(ctx->d_scratch + 1);
 
     nqe_table *t;

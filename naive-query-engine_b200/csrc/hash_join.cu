@@ -124,6 +124,31 @@ __device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, un
     return best;
 }
 
+// First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
+// K rows is issued together (K independent loads in flight; at load factor <= 0.6 most rows
+// resolve there), collisions are then walked one row at a time.
+template <int K>
+__device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
+                                            unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
+    Slot first[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        slot[j] = nqe_mix64(key[j]) & jt.mask;
+        if ((want >> j) & 1u) first[j] = ld_slot(jt.slots + slot[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        brow[j] = EMPTY_ROW;
+        if (!((want >> j) & 1u)) continue;
+        Slot sl = first[j];
+        while (sl.row != EMPTY_ROW) {
+            if (sl.key == key[j]) { brow[j] = sl.row; break; }
+            slot[j] = (slot[j] + 1) & jt.mask;
+            sl = ld_slot(jt.slots + slot[j]);
+        }
+    }
+}
+
 struct ProbeParams {
     JoinTable jt;
     const unsigned long long *probe_keys;
@@ -178,10 +203,21 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
             key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
         }
+        if (!pp.jt.has_dups) {
+            uint64_t slot[K];
+            uint32_t inrange = 0;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            cnt[j] = e < pp.n_probe ? probe_count(pp.jt, key[j], &first[j]) : 0u;
+            for (int j = 0; j < K; j++)
+                if (e0 + (int64_t)j * HJ_THREADS < pp.n_probe) inrange |= 1u << j;
+            probe_first<K>(pp.jt, key, inrange, first, slot);
+#pragma unroll
+            for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+                cnt[j] = e < pp.n_probe ? probe_count(pp.jt, key[j], &first[j]) : 0u;
+            }
         }
         // ranks: warp inclusive scan of counts per j, then scan of the K*WARPS warp totals
         unsigned long long excl_in_warp[K];
@@ -255,20 +291,18 @@ __device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
     return !c.validity || ((__ldg(c.validity + (r >> 5)) >> (r & 31)) & 1u);
 }
 
-__device__ __forceinline__ void join_agg_match(const JoinAggParams &jp, const AggParams &ap, int64_t brow, int64_t prow) {
-    const int64_t grow = jp.group_left ? brow : prow;
-    if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
-    const unsigned long long gkey = __ldg((const unsigned long long *)jp.group.values + grow);
-    unsigned long long *rec = find_slot(ap, gkey);
-    if (!rec) { atomicOr(ap.status, DEV_ERR_TABLE_FULL); return; }
-    for (int a = 0; a < ap.n_aggs; a++) {
-        const ColSrc &c = jp.val[a];
-        const int64_t r = jp.val_left[a] ? brow : prow;
-        if (!col_valid(c, r)) continue;
-        const uint64_t bits = ap.op[a] == NQE_AGG_COUNT ? 0ull : __ldg((const unsigned long long *)c.values + r);
-        update_state(ap, a, rec, c.dtype, bits);
+struct JoinRowSource {
+    const JoinAggParams &jp;
+    int64_t brow, prow;
+    __device__ __forceinline__ bool operator()(int id, int *dtype, uint64_t *bits) const {
+        const ColSrc &c = jp.val[id];
+        const int64_t r = jp.val_left[id] ? brow : prow;
+        if (!col_valid(c, r)) return false;
+        *dtype = c.dtype;
+        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : __ldg((const unsigned long long *)c.values + r);
+        return true;
     }
-}
+};
 
 __global__ void __launch_bounds__(HJ_THREADS)
 join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_constant__ AggParams ap) {
@@ -276,25 +310,52 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
     const int64_t num_tiles = (jp.n_probe + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * TILE + threadIdx.x;
-        unsigned long long key[K];
+        unsigned long long key[K], brow[K];
+        uint64_t slot[K];
+        uint32_t inrange = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
             key[j] = e < jp.n_probe ? ld_stream_u64(jp.probe_keys + e) : 0ull;
+            if (e < jp.n_probe) inrange |= 1u << j;
         }
+        probe_first<K>(jp.jt, key, inrange, brow, slot);
+        // group keys of the (first) matches, K independent gathers
+        uint64_t gkey[K];
+        uint32_t have = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            if (e >= jp.n_probe) continue;
-            uint64_t s = nqe_mix64(key[j]) & jp.jt.mask;
-            while (true) {
-                const Slot sl = ld_slot(jp.jt.slots + s);
-                if (sl.row == EMPTY_ROW) break;
-                if (sl.key == key[j]) {
-                    join_agg_match(jp, ap, (int64_t)sl.row, e);
-                    if (!jp.jt.has_dups) break;
+            gkey[j] = 0;
+            if (brow[j] == EMPTY_ROW) continue;
+            const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
+            if (!col_valid(jp.group, grow)) continue; // NULL group keys are dropped (aggregate/mod.rs:63-71)
+            gkey[j] = __ldg((const unsigned long long *)jp.group.values + grow);
+            have |= 1u << j;
+        }
+        unsigned long long *rec[K];
+        find_slots<K>(ap, gkey, have, rec);
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if (rec[j]) update_states(ap, rec[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS});
+        if (jp.jt.has_dups) {
+            // duplicate build keys: walk on from the first match for the remaining ones
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                if (brow[j] == EMPTY_ROW) continue;
+                const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+                uint64_t s = (slot[j] + 1) & jp.jt.mask;
+                while (true) {
+                    const Slot sl = ld_slot(jp.jt.slots + s);
+                    if (sl.row == EMPTY_ROW) break;
+                    if (sl.key == key[j]) {
+                        const int64_t grow = jp.group_left ? (int64_t)sl.row : e;
+                        if (col_valid(jp.group, grow)) {
+                            unsigned long long *r = find_slot(ap, __ldg((const unsigned long long *)jp.group.values + grow));
+                            if (r) update_states(ap, r, JoinRowSource{jp, (int64_t)sl.row, e});
+                        }
+                    }
+                    s = (s + 1) & jp.jt.mask;
                 }
-                s = (s + 1) & jp.jt.mask;
             }
         }
     }
@@ -503,7 +564,12 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         fill_src(&jp.val[a], *c);
         jp.val_left[a] = aggs[a].column < nl;
     }
-    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, true, &ap));
+    int32_t src_ids[AG_MAX];
+    for (int a = 0; a < n_aggs; a++) src_ids[a] = a; // jp.val[a]; identical (side, column) pairs share an id
+    for (int a = 0; a < n_aggs; a++)
+        for (int b2 = 0; b2 < a; b2++)
+            if (aggs[b2].column == aggs[a].column) { src_ids[a] = src_ids[b2]; break; }
+    NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, src_ids, true, &ap));
     fill_src(&jp.group, *g);
     jp.group_left = group_column < nl;
     ap.n_rows = right->nrows;

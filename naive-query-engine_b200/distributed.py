@@ -1,0 +1,152 @@
+"""Multi-GPU plan for hash-join + group-by: one process per GPU,
+`torch.distributed` for the plumbing.
+
+    rank r owns a row range of L (build) and R (probe)
+    1. radix-partition both sides on the join key          (nqe_radix_partition, dest = mix64(key) % P)
+    2. all-to-all the partitions over NCCL / NVLink        (dist.all_to_all_single, uneven splits)
+    3. local fused join -> group-by on the received rows   (nqe_join_aggregate; min(group) carries the key,
+                                                            because the reference's aggregate emits no key column)
+    4. all-gather the partial states and merge them        (count -> sum of counts, sum -> sum, min, max;
+                                                            avg = sum / count)
+
+Filter / projection need no exchange: every rank runs them on its own rows.
+
+The orchestration is written against a small `engine` interface so that the CPU
+tests can drive it over gloo with a stand-in engine, while bench.py drives it over
+NCCL with the CUDA engine below.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+
+class Engine:
+    """What the exchange plan needs from the execution layer.  Columns are 1-D
+    torch tensors (int64 storage; float64 columns are bit-cast) on the engine's device."""
+
+    def partition(self, cols: Sequence, key: int, parts: int) -> Tuple[List, List[int]]:
+        """-> (columns permuted so that rows of destination p are contiguous, counts[parts])"""
+        raise NotImplementedError
+
+    def join_partial_aggregate(self, lcols: Sequence, rcols: Sequence):
+        """inner join L(k, a) x R(fk, b) on k = fk, group by a ->
+        columns [key(a) i64, count i64, sum f64-bits, min f64-bits, max f64-bits]"""
+        raise NotImplementedError
+
+    def merge_partials(self, cols: Sequence):
+        """group by key over partial states -> [key, count, sum, min, max] (one row per key)"""
+        raise NotImplementedError
+
+
+def exchange(dist, torch, engine: Engine, cols: Sequence, key: int, world: int):
+    """Steps 1-2 for one table.  Returns (received columns, rows sent to other ranks)."""
+    part, counts = engine.partition(cols, key, world)
+    rank = dist.get_rank()
+    send = torch.tensor(counts, dtype=torch.int64, device=part[0].device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    send_l = [int(x) for x in counts]
+    recv_l = [int(x) for x in recv.tolist()]
+    total = sum(recv_l)
+    outs = []
+    for c in part:
+        dst = torch.empty(total, dtype=c.dtype, device=c.device)
+        dist.all_to_all_single(dst, c, output_split_sizes=recv_l, input_split_sizes=send_l)
+        outs.append(dst)
+    return outs, sum(send_l) - send_l[rank]
+
+
+def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int):
+    """Steps 1-4.  Every rank returns the full merged result
+    [key, count, sum, min, max] (tensors) and the number of rows it sent over the wire."""
+    l_recv, s1 = exchange(dist, torch, engine, lcols, 0, world)
+    r_recv, s2 = exchange(dist, torch, engine, rcols, 0, world)
+    partial = engine.join_partial_aggregate(l_recv, r_recv)
+    g = int(partial[0].numel())
+    sizes = torch.tensor([g], dtype=torch.int64, device=partial[0].device)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    gl = [int(x.item()) for x in all_sizes]
+    gmax = max(max(gl), 1)
+    gathered = []
+    for c in partial:
+        src = torch.zeros(gmax, dtype=c.dtype, device=c.device)
+        src[:g] = c
+        bufs = [torch.empty_like(src) for _ in range(world)]
+        dist.all_gather(bufs, src)
+        gathered.append(torch.cat([bufs[r][:gl[r]] for r in range(world)]))
+    merged = engine.merge_partials(gathered)
+    return merged, s1 + s2
+
+
+class CudaEngine(Engine):
+    """The CUDA execution layer behind the Engine interface (through the C ABI)."""
+
+    I64, F64 = 2, 4
+
+    def __init__(self, nq, ctx, torch):
+        self.nq, self.ctx, self.torch = nq, ctx, torch
+
+    def _table(self, names, dtypes, cols):
+        return self.nq.DeviceTable.from_device_pointers(self.ctx, names, dtypes, [c.data_ptr() for c in cols],
+                                                        int(cols[0].numel()), keepalive=list(cols))
+
+    def _column(self, table, i, n, copy=True):
+        if n == 0:
+            return self.torch.empty(0, dtype=self.torch.int64, device="cuda")
+        d = table.column_desc(i)
+
+        class _View:  # __cuda_array_interface__ over the table's device buffer
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (d.values, False), "version": 2}
+        v = self.torch.as_tensor(_View(), device="cuda")
+        return v.clone() if copy else v
+
+    def partition(self, cols, key, parts):
+        ctx = self.ctx
+        t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
+        h = C.c_void_p()
+        counts = (C.c_int64 * parts)()
+        ctx.check(ctx.lib.nqe_radix_partition(ctx.h, t.h, key, parts, C.byref(h), counts))
+        out = self.nq.DeviceTable(ctx, h, t.names)
+        n = int(cols[0].numel())
+        res = [self._column(out, i, n, copy=False) for i in range(len(cols))]
+        for r in res:
+            r._nqe_keepalive = out  # the views borrow the partitioned table's buffers
+        t.free()
+        return res, [int(x) for x in counts]
+
+    def join_partial_aggregate(self, lcols, rcols):
+        ctx, nq = self.ctx, self.nq
+        L = self._table(["k", "a"], [self.I64, self.I64], lcols)
+        R = self._table(["fk", "b"], [self.I64, self.F64], rcols)
+        # join output schema: k, a, fk, b -> count(b), sum(b), min(b), max(b), min(a) group by a
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 3), (1, 3), (3, 3), (4, 3), (3, 1)]])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, L.h, R.h, 0, 0, 1, aggs, 5, C.byref(h)))
+        part = nq.DeviceTable(ctx, h, ["count", "sum", "min", "max", "key"])
+        g = part.num_rows
+        cols = [self._column(part, i, g) for i in range(5)]
+        self.torch.cuda.current_stream().synchronize()
+        part.free(); L.free(); R.free()
+        key = cols[4].view(self.torch.float64).to(self.torch.int64)  # min(a) is a Float64 (aggregates are f64)
+        return [key, cols[0], cols[1], cols[2], cols[3]]
+
+    def merge_partials(self, cols):
+        ctx, nq, torch = self.ctx, self.nq, self.torch
+        key, cnt, s, mn, mx = cols
+        cnt_f = cnt.to(torch.float64).view(torch.int64)  # counts are summed as f64 (exact below 2^53)
+        M = self._table(["key", "cnt", "sum", "min", "max"], [self.I64, self.F64, self.F64, self.F64, self.F64],
+                        [key, cnt_f, s, mn, mx])
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(3, 0), (1, 1), (1, 2), (3, 3), (4, 4)]])
+        ke, keep = nq.ColumnExpr.try_create(None, 0).to_expr(M.names)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, M.h, C.pointer(ke), aggs, 5, C.byref(h)))
+        out = nq.DeviceTable(ctx, h, ["key", "count", "sum", "min", "max"])
+        g = out.num_rows
+        res = [self._column(out, i, g) for i in range(5)]
+        torch.cuda.current_stream().synchronize()
+        out.free(); M.free()
+        res[0] = res[0].view(torch.float64).to(torch.int64)
+        res[1] = res[1].view(torch.float64).to(torch.int64)
+        return res

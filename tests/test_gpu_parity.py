@@ -385,3 +385,43 @@ def test_synth_columns_match_oracle_generator():
         ctx.sync()
         got = buf.cpu().numpy()
         assert np.array_equal(got, want.view(np.int64))
+
+
+def test_distributed_plan_on_one_gpu_matches_oracle():
+    """distributed.py's CudaEngine through a 1-rank NCCL group (the >1-rank orchestration is
+    covered on CPU over gloo in test_distributed_gloo.py)."""
+    import os
+    from importlib import import_module
+    import torch
+    import torch.distributed as dist
+    import nqe_b200 as nq
+    D = import_module("naive-query-engine_b200.distributed")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29611")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        n_build, n_probe, groups = 5000, 60000, 101
+        lk = O.gen_perm_i64(0, n_build, 7368787 % n_build, n_build)
+        la = lk % groups
+        fk = O.gen_mod_i64(47, 0, n_probe, int(n_build * 1.3))
+        rb = O.gen_unif_f64(48, 0, n_probe, 100.0)
+        dev = lambda a: torch.from_numpy(a.view(np.int64).copy()).cuda()
+        eng = D.CudaEngine(nq, nq.Context.default(), torch)
+        merged, sent = D.shuffled_join_group_by(dist, torch, eng, [dev(lk), dev(la)], [dev(fk), dev(rb)], 1)
+        got = [m.cpu().numpy() for m in merged]
+        L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", la)])
+        R = O.Batch(["fk", "b"], [O.Col("i64", fk), O.Col("f64", rb)])
+        want = O.aggregate(O.hash_join_c(L, R, 0, 0), ("col", 1), [("min", 1), ("count", 3), ("sum", 3), ("min", 3), ("max", 3)])
+        wk = want.cols[0].values.astype(np.int64)
+        wo, go = np.argsort(wk), np.argsort(got[0])
+        assert np.array_equal(wk[wo], got[0][go])
+        assert np.array_equal(want.cols[1].values[wo].astype(np.int64), got[1][go])
+        assert np.allclose(want.cols[2].values[wo], got[2][go].view(np.float64), rtol=SUM_REL, atol=0)
+        assert np.array_equal(want.cols[3].values[wo], got[3][go].view(np.float64))
+        assert np.array_equal(want.cols[4].values[wo], got[4][go].view(np.float64))
+        assert sent == 0
+    finally:
+        if created:
+            dist.destroy_process_group()
