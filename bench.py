@@ -281,7 +281,7 @@ def run_gpu(args, rank, local_rank, world):
     tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("filter_project_kernel")
+            traffic = json.load(f).get("nqe_fp_jit")
 
     # ------------------------------------------------ e2e: pinned host Arrow buffers -> H2D -> kernel -> D2H
     host = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(3)]
@@ -349,7 +349,7 @@ def run_gpu(args, rank, local_rank, world):
                        "timing": "CUDA events on the operator's stream, barrier+synchronize both sides, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
-                         "kernel": "filter_project_kernel", "kernel_ms": kernel_ms,
+                         "kernel": "nqe_fp_jit (filter_project, NVRTC shape-specialised; csrc/jit.cu)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
