@@ -2,17 +2,23 @@
 // join -> PhysicalAggregatePlan path.
 //
 // Build (hash_join.rs:58-78): the build side's raw key words (validity is ignored,
-// :67) go into one open-addressing multimap of 16-byte slots {key, build row}; a
-// slot is claimed with a CAS on the row word.  A verification pass marks whether
-// any key repeats, so that unique-key (PK-FK) probes stop at the first match.
+// :67) go into one open-addressing multimap; a slot is claimed with a CAS on its row
+// word.  Two slot formats:
+//   thin  16 B  {key, build row}                      any build table
+//   fat   32 B  {key, build row, payload0, payload1}  build tables whose non-key columns
+//               are at most two NULL-free 8-byte columns (the PK-FK dimension-table
+//               shape): one 32-byte sector then holds everything the probe needs, so the
+//               dependent payload gather -- a second random HBM access -- disappears
+// A verification pass marks whether any key repeats, so unique-key probes stop at the
+// first match.
 //
-// Probe (hash_join.rs:80-103, 236-246): one pass over the probe side.  Every tile
-// counts the matches of its rows, ranks them with warp shuffles + a decoupled
-// look-back across tiles (so the output is probe-row-major like the reference),
-// and writes the joined row -- all build columns gathered at the matching build
-// row, all probe columns from the probe row -- straight to its final position.
-// No (outer_pos, inner_pos) index arrays and no separate `take` pass exist.
-// Within one probe row, matches are emitted in ascending build-row order.
+// Probe (hash_join.rs:80-103, 236-246): one pass over the probe side.  Every tile looks
+// its rows up (the first table probe of a thread's K rows is issued together, collisions
+// walk sequentially), ranks the matches with warp shuffles + a decoupled look-back across
+// tiles (so the output is probe-row-major like the reference's), and writes the joined row
+// straight to its final position: no (outer_pos, inner_pos) index arrays and no separate
+// `take` pass.  Within one probe row, matches are emitted in ascending build-row order.
+#include <cstdlib>
 #include <cstring>
 
 #include "agg_device.cuh"
@@ -35,9 +41,14 @@ struct Slot {
 };
 
 struct JoinTable {
-    Slot *slots;
+    unsigned long long *words; // slot s starts at words + (s << shift)
     uint64_t mask;
+    int32_t shift;    // 1: thin (2 words), 2: fat (4 words)
     int32_t has_dups;
+    int32_t key_col;  // build-side key column
+    int32_t n_pay;    // fat: number of payload columns (<= 2)
+    int32_t pay_col[2];
+    const unsigned long long *pay_src[2];
 };
 
 struct ColSrc {
@@ -47,11 +58,21 @@ struct ColSrc {
     int32_t pad;
 };
 
-__global__ void join_clear_kernel(Slot *slots, uint64_t n) {
+__device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uint64_t s) { return jt.words + (s << jt.shift); }
+__device__ __forceinline__ Slot ld_slot(const JoinTable &jt, uint64_t s) {
+    const ulonglong2 v = __ldg((const ulonglong2 *)slot_ptr(jt, s));
+    return Slot{v.x, v.y};
+}
+__device__ __forceinline__ ulonglong2 ld_payload(const JoinTable &jt, uint64_t s) {
+    return __ldg((const ulonglong2 *)(slot_ptr(jt, s) + 2));
+}
+
+__global__ void join_clear_kernel(JoinTable jt, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        slots[i].key = 0;
-        slots[i].row = EMPTY_ROW;
+        unsigned long long *p = slot_ptr(jt, i);
+        p[0] = 0;
+        p[1] = EMPTY_ROW;
     }
 }
 
@@ -61,9 +82,14 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
     const unsigned long long key = keys[i];
     uint64_t s = nqe_mix64(key) & jt.mask;
     for (uint64_t probe = 0; probe <= jt.mask; probe++) {
-        const unsigned long long old = atomicCAS(&jt.slots[s].row, EMPTY_ROW, (unsigned long long)i);
+        unsigned long long *p = slot_ptr(jt, s);
+        const unsigned long long old = atomicCAS(p + 1, EMPTY_ROW, (unsigned long long)i);
         if (old == EMPTY_ROW) {
-            jt.slots[s].key = key;
+            p[0] = key;
+            if (jt.shift == 2) {
+                p[2] = jt.n_pay > 0 ? jt.pay_src[0][i] : 0ull;
+                p[3] = jt.n_pay > 1 ? jt.pay_src[1][i] : 0ull;
+            }
             return;
         }
         s = (s + 1) & jt.mask;
@@ -79,49 +105,12 @@ __global__ void join_dups_kernel(JoinTable jt, const unsigned long long *__restr
     uint64_t s = nqe_mix64(key) & jt.mask;
     int matches = 0;
     while (true) {
-        const Slot sl = jt.slots[s];
+        const Slot sl = ld_slot(jt, s);
         if (sl.row == EMPTY_ROW) break;
         if (sl.key == key) matches++;
         s = (s + 1) & jt.mask;
     }
     if (matches > 1) *flag = 1u;
-}
-
-__device__ __forceinline__ Slot ld_slot(const Slot *p) {
-    const ulonglong2 v = __ldg((const ulonglong2 *)p);
-    return Slot{v.x, v.y};
-}
-
-// number of matches of `key`, and the smallest matching build row
-__device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigned long long key, unsigned long long *first) {
-    uint64_t s = nqe_mix64(key) & jt.mask;
-    unsigned int c = 0;
-    unsigned long long best = EMPTY_ROW;
-    while (true) {
-        const Slot sl = ld_slot(jt.slots + s);
-        if (sl.row == EMPTY_ROW) break;
-        if (sl.key == key) {
-            c++;
-            if (sl.row < best) best = sl.row;
-            if (!jt.has_dups) break;
-        }
-        s = (s + 1) & jt.mask;
-    }
-    *first = best;
-    return c;
-}
-
-// smallest matching build row strictly greater than `after`
-__device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, unsigned long long key, unsigned long long after) {
-    uint64_t s = nqe_mix64(key) & jt.mask;
-    unsigned long long best = EMPTY_ROW;
-    while (true) {
-        const Slot sl = ld_slot(jt.slots + s);
-        if (sl.row == EMPTY_ROW) break;
-        if (sl.key == key && sl.row > after && sl.row < best) best = sl.row;
-        s = (s + 1) & jt.mask;
-    }
-    return best;
 }
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
@@ -134,7 +123,7 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
 #pragma unroll
     for (int j = 0; j < K; j++) {
         slot[j] = nqe_mix64(key[j]) & jt.mask;
-        if ((want >> j) & 1u) first[j] = ld_slot(jt.slots + slot[j]);
+        if ((want >> j) & 1u) first[j] = ld_slot(jt, slot[j]);
     }
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -144,9 +133,42 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
         while (sl.row != EMPTY_ROW) {
             if (sl.key == key[j]) { brow[j] = sl.row; break; }
             slot[j] = (slot[j] + 1) & jt.mask;
-            sl = ld_slot(jt.slots + slot[j]);
+            sl = ld_slot(jt, slot[j]);
         }
     }
+}
+
+// number of matches of `key`; the smallest matching build row and its slot
+__device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigned long long key, unsigned long long *first,
+                                                    uint64_t *first_slot) {
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    unsigned int c = 0;
+    unsigned long long best = EMPTY_ROW;
+    while (true) {
+        const Slot sl = ld_slot(jt, s);
+        if (sl.row == EMPTY_ROW) break;
+        if (sl.key == key) {
+            c++;
+            if (sl.row < best) { best = sl.row; *first_slot = s; }
+        }
+        s = (s + 1) & jt.mask;
+    }
+    *first = best;
+    return c;
+}
+
+// smallest matching build row strictly greater than `after` (and its slot)
+__device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, unsigned long long key, unsigned long long after,
+                                                         uint64_t *slot_out) {
+    uint64_t s = nqe_mix64(key) & jt.mask;
+    unsigned long long best = EMPTY_ROW;
+    while (true) {
+        const Slot sl = ld_slot(jt, s);
+        if (sl.row == EMPTY_ROW) break;
+        if (sl.key == key && sl.row > after && sl.row < best) { best = sl.row; *slot_out = s; }
+        s = (s + 1) & jt.mask;
+    }
+    return best;
 }
 
 struct ProbeParams {
@@ -154,6 +176,8 @@ struct ProbeParams {
     const unsigned long long *probe_keys;
     int64_t n_probe;
     int32_t n_left, n_right;
+    int32_t key_from_probe; // the build key column carries no validity: its output value is the probe key
+    int32_t pad;
     ColSrc left[HJ_MAX_COLS], right[HJ_MAX_COLS];
     void *out_values[2 * HJ_MAX_COLS];   // 8-byte values or one byte per row (Boolean)
     uint8_t *out_valid[2 * HJ_MAX_COLS]; // one byte per row or nullptr
@@ -166,11 +190,7 @@ struct ProbeParams {
 
 #include "lookback_body.inc"
 
-__device__ __forceinline__ unsigned long long lookback(unsigned long long *state, int tile, unsigned long long my_total, int lane) {
-    if (lane == 0) nqe_lb_publish(state, tile, my_total);
-    return nqe_lb_walk(state, tile, my_total, lane);
-}
-
+// one output cell: column c of the joined row (build row | probe row) -> position pos
 __device__ __forceinline__ void emit_value(const ColSrc &c, int64_t src_row, void *out_values, uint8_t *out_valid, int64_t pos) {
     bool valid = true;
     if (c.validity) valid = (__ldg(c.validity + (src_row >> 5)) >> (src_row & 31)) & 1u;
@@ -183,6 +203,15 @@ __device__ __forceinline__ void emit_value(const ColSrc &c, int64_t src_row, voi
     if (out_valid) out_valid[pos] = (uint8_t)valid;
 }
 
+__device__ __forceinline__ void emit_row(const ProbeParams &pp, int64_t brow, int64_t prow, int64_t pos) {
+    const int ncols = pp.n_left + pp.n_right;
+    for (int c = 0; c < ncols; c++) {
+        const bool is_left = c < pp.n_left;
+        emit_value(is_left ? pp.left[c] : pp.right[c - pp.n_left], is_left ? brow : prow, pp.out_values[c], pp.out_valid[c], pos);
+    }
+}
+
+template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
@@ -197,26 +226,34 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
         if (tile >= pp.num_tiles) break;
         const int64_t e0 = (int64_t)tile * TILE + tid;
         unsigned long long key[K], first[K];
+        uint64_t slot[K];
         unsigned int cnt[K];
+        uint32_t inrange = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
             key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
+            if (e < pp.n_probe) inrange |= 1u << j;
         }
         if (!pp.jt.has_dups) {
-            uint64_t slot[K];
-            uint32_t inrange = 0;
-#pragma unroll
-            for (int j = 0; j < K; j++)
-                if (e0 + (int64_t)j * HJ_THREADS < pp.n_probe) inrange |= 1u << j;
             probe_first<K>(pp.jt, key, inrange, first, slot);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
         } else {
 #pragma unroll
             for (int j = 0; j < K; j++) {
-                const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-                cnt[j] = e < pp.n_probe ? probe_count(pp.jt, key[j], &first[j]) : 0u;
+                slot[j] = 0;
+                first[j] = EMPTY_ROW;
+                cnt[j] = ((inrange >> j) & 1u) ? probe_count(pp.jt, key[j], &first[j], &slot[j]) : 0u;
+            }
+        }
+        // fat slots: the payload of the first match sits next to the key that was just read
+        ulonglong2 pay[K];
+        if (FAT) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                pay[j] = make_ulonglong2(0, 0);
+                if (cnt[j]) pay[j] = ld_payload(pp.jt, slot[j]);
             }
         }
         // ranks: warp inclusive scan of counts per j, then scan of the K*WARPS warp totals
@@ -234,8 +271,7 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
         }
         __syncthreads();
         if (warp == 0) {
-            constexpr int N = K * HJ_WARPS; // 32
-            static_assert(N == 32, "one entry per lane");
+            static_assert(K * HJ_WARPS == 32, "one entry per lane");
             const unsigned long long mine = s_cnt[lane];
             unsigned long long incl = mine;
 #pragma unroll
@@ -245,7 +281,8 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             }
             s_cnt[lane] = incl - mine;
             const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
-            const unsigned long long excl = lookback(pp.tile_state, tile, total, lane);
+            if (lane == 0) nqe_lb_publish(pp.tile_state, tile, total);
+            const unsigned long long excl = nqe_lb_walk(pp.tile_state, tile, total, lane);
             if (lane == 0) {
                 s_tile_excl = excl;
                 if (tile == pp.num_tiles - 1) *pp.out_count = excl + total;
@@ -253,23 +290,62 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
         }
         __syncthreads();
         const unsigned long long tile_excl = s_tile_excl;
-        const int ncols = pp.n_left + pp.n_right;
+        unsigned long long pos[K];
+        uint32_t emit = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            if (!cnt[j]) continue;
-            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            unsigned long long pos = tile_excl + s_cnt[j * HJ_WARPS + warp] + excl_in_warp[j];
-            unsigned long long brow = first[j];
-            for (unsigned int m = 0; m < cnt[j]; m++) {
-                if ((int64_t)pos < pp.out_cap) {
-                    for (int c = 0; c < ncols; c++) {
-                        const bool is_left = c < pp.n_left;
-                        const ColSrc &src = is_left ? pp.left[c] : pp.right[c - pp.n_left];
-                        emit_value(src, is_left ? (int64_t)brow : e, pp.out_values[c], pp.out_valid[c], (int64_t)pos);
-                    }
+            pos[j] = tile_excl + s_cnt[j * HJ_WARPS + warp] + excl_in_warp[j];
+            if (cnt[j] && (int64_t)pos[j] < pp.out_cap) emit |= 1u << j;
+        }
+        // ---- first match of every row, column by column (the loads of the K rows are independent)
+        for (int c = 0; c < pp.n_left; c++) {
+            unsigned long long *out = (unsigned long long *)pp.out_values[c];
+            if (c == pp.jt.key_col && pp.key_from_probe) {
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u) out[pos[j]] = key[j];
+            } else if (FAT) {
+                const bool second = pp.jt.n_pay > 1 && c == pp.jt.pay_col[1];
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u) out[pos[j]] = second ? pay[j].y : pay[j].x;
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u) emit_value(pp.left[c], (int64_t)first[j], pp.out_values[c], pp.out_valid[c], (int64_t)pos[j]);
+            }
+        }
+        for (int c = 0; c < pp.n_right; c++) {
+            const ColSrc &src = pp.right[c];
+            if (src.dtype != NQE_BOOL && !src.validity) {
+                unsigned long long v[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    v[j] = 0;
+                    if ((emit >> j) & 1u) v[j] = ld_stream_u64((const unsigned long long *)src.values + e0 + (int64_t)j * HJ_THREADS);
                 }
-                pos++;
-                if (m + 1 < cnt[j]) brow = probe_next(pp.jt, key[j], brow);
+                unsigned long long *out = (unsigned long long *)pp.out_values[pp.n_left + c];
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u) out[pos[j]] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u)
+                        emit_value(src, e0 + (int64_t)j * HJ_THREADS, pp.out_values[pp.n_left + c], pp.out_valid[pp.n_left + c], (int64_t)pos[j]);
+            }
+        }
+        // ---- duplicate build keys: the remaining matches of a row, ascending build row
+        if (pp.jt.has_dups) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                unsigned long long brow = first[j];
+                uint64_t s = slot[j];
+                for (unsigned int m = 1; m < cnt[j]; m++) {
+                    brow = probe_next(pp.jt, key[j], brow, &s);
+                    const int64_t p = (int64_t)pos[j] + m;
+                    if (p < pp.out_cap) emit_row(pp, (int64_t)brow, e0 + (int64_t)j * HJ_THREADS, p);
+                }
             }
         }
         __syncthreads();
@@ -283,8 +359,10 @@ struct JoinAggParams {
     int64_t n_probe;
     ColSrc group;          // group key column
     int32_t group_left;    // 1: taken from the build row, 0: from the probe row
+    int32_t group_pay;     // fat table: 0/1 = group key is payload word 0/1, -1 = not in the slot
     ColSrc val[AG_MAX];
     int32_t val_left[AG_MAX];
+    int32_t val_pay[AG_MAX]; // fat table: payload word holding this build-side argument, or -1
 };
 
 __device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
@@ -294,20 +372,41 @@ __device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
 struct JoinRowSource {
     const JoinAggParams &jp;
     int64_t brow, prow;
+    ulonglong2 pay;
     __device__ __forceinline__ bool operator()(int id, int *dtype, uint64_t *bits) const {
         const ColSrc &c = jp.val[id];
+        *dtype = c.dtype;
+        if (jp.val_left[id] && jp.val_pay[id] >= 0) { // build-side argument stored in the fat slot
+            *bits = jp.val_pay[id] ? pay.y : pay.x;
+            return true;
+        }
         const int64_t r = jp.val_left[id] ? brow : prow;
         if (!col_valid(c, r)) return false;
-        *dtype = c.dtype;
         *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : __ldg((const unsigned long long *)c.values + r);
         return true;
     }
 };
 
+__device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggParams &ap, int64_t brow, int64_t prow,
+                                             uint64_t slot) {
+    ulonglong2 pay = make_ulonglong2(0, 0);
+    if (jp.jt.shift == 2) pay = ld_payload(jp.jt, slot);
+    uint64_t gkey;
+    if (jp.group_left && jp.group_pay >= 0) gkey = jp.group_pay ? pay.y : pay.x;
+    else {
+        const int64_t grow = jp.group_left ? brow : prow;
+        if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
+        gkey = __ldg((const unsigned long long *)jp.group.values + grow);
+    }
+    unsigned long long *r = find_slot(ap, gkey);
+    if (r) update_states(ap, r, JoinRowSource{jp, brow, prow, pay});
+}
+
 __global__ void __launch_bounds__(HJ_THREADS)
 join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_constant__ AggParams ap) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
     const int64_t num_tiles = (jp.n_probe + TILE - 1) / TILE;
+    const bool fat = jp.jt.shift == 2;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * TILE + threadIdx.x;
         unsigned long long key[K], brow[K];
@@ -320,40 +419,40 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
             if (e < jp.n_probe) inrange |= 1u << j;
         }
         probe_first<K>(jp.jt, key, inrange, brow, slot);
-        // group keys of the (first) matches, K independent gathers
+        // group keys of the (first) matches: K independent loads
+        ulonglong2 pay[K];
         uint64_t gkey[K];
         uint32_t have = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             gkey[j] = 0;
+            pay[j] = make_ulonglong2(0, 0);
             if (brow[j] == EMPTY_ROW) continue;
-            const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
-            if (!col_valid(jp.group, grow)) continue; // NULL group keys are dropped (aggregate/mod.rs:63-71)
-            gkey[j] = __ldg((const unsigned long long *)jp.group.values + grow);
+            if (fat) pay[j] = ld_payload(jp.jt, slot[j]);
+            if (jp.group_left && jp.group_pay >= 0) {
+                gkey[j] = jp.group_pay ? pay[j].y : pay[j].x;
+            } else {
+                const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
+                if (!col_valid(jp.group, grow)) continue; // NULL group keys are dropped
+                gkey[j] = __ldg((const unsigned long long *)jp.group.values + grow);
+            }
             have |= 1u << j;
         }
         unsigned long long *rec[K];
         find_slots<K>(ap, gkey, have, rec);
 #pragma unroll
         for (int j = 0; j < K; j++)
-            if (rec[j]) update_states(ap, rec[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS});
+            if (rec[j]) update_states(ap, rec[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS, pay[j]});
         if (jp.jt.has_dups) {
             // duplicate build keys: walk on from the first match for the remaining ones
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 if (brow[j] == EMPTY_ROW) continue;
-                const int64_t e = e0 + (int64_t)j * HJ_THREADS;
                 uint64_t s = (slot[j] + 1) & jp.jt.mask;
                 while (true) {
-                    const Slot sl = ld_slot(jp.jt.slots + s);
+                    const Slot sl = ld_slot(jp.jt, s);
                     if (sl.row == EMPTY_ROW) break;
-                    if (sl.key == key[j]) {
-                        const int64_t grow = jp.group_left ? (int64_t)sl.row : e;
-                        if (col_valid(jp.group, grow)) {
-                            unsigned long long *r = find_slot(ap, __ldg((const unsigned long long *)jp.group.values + grow));
-                            if (r) update_states(ap, r, JoinRowSource{jp, (int64_t)sl.row, e});
-                        }
-                    }
+                    if (sl.key == key[j]) join_agg_one(jp, ap, (int64_t)sl.row, e0 + (int64_t)j * HJ_THREADS, s);
                     s = (s + 1) & jp.jt.mask;
                 }
             }
@@ -377,15 +476,34 @@ int32_t check_join_keys(nqe_ctx *ctx, const nqe_table *left, const nqe_table *ri
 // build the multimap over left->cols[lk]
 int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt) {
     const int64_t nl = left->nrows;
+    memset(jt, 0, sizeof *jt);
+    jt->key_col = lk;
+    // fat slots when every non-key build column is a NULL-free 8-byte column and there are at most two
+    static int allow_fat = -1;
+    if (allow_fat < 0) {
+        const char *e = getenv("NQE_JOIN_FAT");
+        allow_fat = e ? atoi(e) : 0; // measured slower on B200: the 2x larger table loses more L2 hits than the gather costs
+    }
+    bool fat = allow_fat && left->cols.size() <= 3;
+    int n_pay = 0;
+    for (size_t c = 0; c < left->cols.size() && fat; c++) {
+        if ((int)c == lk) continue;
+        const DevColumn &col = left->cols[c];
+        if (col.validity || col.dtype == NQE_BOOL || col.dtype == NQE_UTF8) { fat = false; break; }
+        jt->pay_col[n_pay] = (int)c;
+        jt->pay_src[n_pay] = (const unsigned long long *)col.values;
+        n_pay++;
+    }
+    jt->n_pay = fat ? n_pay : 0;
+    jt->shift = fat ? 2 : 1;
     const uint64_t cap = nqe_next_pow2((uint64_t)((double)nl / 0.6) + 16);
     void *slots = nullptr;
-    NQE_TRY(nqe_dev_alloc(ctx, &slots, cap * sizeof(Slot)));
-    jt->slots = (Slot *)slots;
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, (cap << jt->shift) * 8));
+    jt->words = (unsigned long long *)slots;
     jt->mask = cap - 1;
-    jt->has_dups = 0;
     uint32_t *status = (uint32_t *)(ctx->d_scratch + 1);
     uint32_t *dupflag = (uint32_t *)(ctx->d_scratch + 3);
-    join_clear_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(jt->slots, cap);
+    join_clear_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(*jt, cap);
     ctx->launches++;
     if (nl > 0) {
         const unsigned long long *keys = (const unsigned long long *)left->cols[lk].values;
@@ -431,6 +549,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     pp.n_probe = right->nrows;
     pp.n_left = nl;
     pp.n_right = nr;
+    pp.key_from_probe = left->cols[left_key].validity == nullptr;
     for (int c = 0; c < nl; c++) fill_src(&pp.left[c], left->cols[c]);
     for (int c = 0; c < nr; c++) fill_src(&pp.right[c], right->cols[c]);
     constexpr int TILE = HJ_K * HJ_THREADS;
@@ -440,6 +559,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     pp.tile_state = (unsigned long long *)lb;
     pp.out_count = (unsigned long long *)ctx->d_scratch;
     pp.ticket = (unsigned int *)(ctx->d_scratch + 2);
+    const bool fat = pp.jt.shift == 2 && pp.key_from_probe;
 
     nqe_table *t = nullptr;
     int64_t cap = pp.n_probe > 0 ? pp.n_probe : 1;
@@ -471,11 +591,12 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
             if (pp.num_tiles > 0) {
+                auto kern = fat ? join_probe_kernel<true> : join_probe_kernel<false>;
                 int occ = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_probe_kernel, HJ_THREADS, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);
                 if (grid > pp.num_tiles) grid = pp.num_tiles;
-                join_probe_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pp);
+                kern<<<grid, HJ_THREADS, 0, ctx->stream>>>(pp);
                 ctx->launches++;
             }
             cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
@@ -512,7 +633,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     for (auto p : bool_bytes) nqe_dev_free(ctx, p);
     for (auto p : valid_bytes) nqe_dev_free(ctx, p);
     nqe_dev_free(ctx, lb);
-    nqe_dev_free(ctx, pp.jt.slots);
+    nqe_dev_free(ctx, pp.jt.words);
     if (rc != NQE_OK) {
         if (t) nqe_table_free(t);
         return rc;
@@ -556,19 +677,17 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     memset(&jp, 0, sizeof jp);
     AggParams ap;
     memset(&ap, 0, sizeof ap);
-    int32_t dts[AG_MAX];
+    int32_t dts[AG_MAX], src_ids[AG_MAX];
     for (int a = 0; a < n_aggs; a++) {
         const DevColumn *c = col_at(aggs[a].column);
         if (!c) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", aggs[a].column);
         dts[a] = c->dtype;
         fill_src(&jp.val[a], *c);
         jp.val_left[a] = aggs[a].column < nl;
-    }
-    int32_t src_ids[AG_MAX];
-    for (int a = 0; a < n_aggs; a++) src_ids[a] = a; // jp.val[a]; identical (side, column) pairs share an id
-    for (int a = 0; a < n_aggs; a++)
+        src_ids[a] = a; // jp.val[a]; identical columns share an id
         for (int b2 = 0; b2 < a; b2++)
             if (aggs[b2].column == aggs[a].column) { src_ids[a] = src_ids[b2]; break; }
+    }
     NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, src_ids, true, &ap));
     fill_src(&jp.group, *g);
     jp.group_left = group_column < nl;
@@ -578,13 +697,23 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     OpTimer timer(ctx);
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
     int32_t rc = build_table(ctx, left, left_key, &jp.jt);
+    // which build-side columns can be served from the fat slot's payload words
+    jp.group_pay = -1;
+    for (int a = 0; a < n_aggs; a++) jp.val_pay[a] = -1;
+    if (jp.jt.shift == 2) {
+        for (int q = 0; q < jp.jt.n_pay; q++) {
+            if (jp.group_left && group_column == jp.jt.pay_col[q]) jp.group_pay = q;
+            for (int a = 0; a < n_aggs; a++)
+                if (jp.val_left[a] && aggs[a].column == jp.jt.pay_col[q]) jp.val_pay[a] = q;
+        }
+    }
     jp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
     jp.n_probe = right->nrows;
     nqe_table *t;
     nqe_table_new(ctx, 0, &t);
     // groups come from one column of one side: at most that side's row count
     const int64_t side_rows = jp.group_left ? left->nrows : right->nrows;
-    uint64_t capacity = nqe_agg_capacity((double)(side_rows < (1 << 20) ? side_rows : (1 << 20)));
+    uint64_t capacity = nqe_agg_capacity((double)(side_rows < (1 << 18) ? side_rows : (1 << 18)));
     for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
         cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
         rc = nqe_agg_table_create(ctx, &ap, capacity);
@@ -610,7 +739,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, false, side_rows + 1, t);
     timer.stop();
     nqe_dev_free(ctx, ap.table);
-    nqe_dev_free(ctx, jp.jt.slots);
+    nqe_dev_free(ctx, jp.jt.words);
     if (rc != NQE_OK) {
         nqe_table_free(t);
         return rc;
