@@ -542,6 +542,9 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
                                unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
                                std::string *source_out);
 
+int32_t nqe_filter_project_strings(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                                   int32_t n_projs, const int *utf8_src, nqe_table **out);
+
 static int32_t status_to_error(nqe_ctx *ctx, uint32_t st) {
     if (st & DEV_ERR_DIV0) return nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error");
     if (st & DEV_ERR_OVERFLOW) return nqe_fail(ctx, NQE_ERR_PANIC, "attempt to divide with overflow");
@@ -570,6 +573,22 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
             pass_exprs[i] = nqe_expr{&pass_nodes[i], 1, 0};
         }
         projs = pass_exprs.data();
+    }
+
+    // bare references to Utf8 columns ride along through a hidden row-id column (utf8.cu)
+    {
+        int utf8_src[16];
+        bool any_utf8 = false;
+        for (int i = 0; i < n_projs; i++) {
+            utf8_src[i] = -1;
+            const nqe_expr &e = projs[i];
+            if (e.n_nodes == 1 && e.nodes && e.nodes[0].kind == NQE_NODE_COLUMN && e.nodes[0].column >= 0 &&
+                e.nodes[0].column < (int)in->cols.size() && in->cols[e.nodes[0].column].dtype == NQE_UTF8) {
+                utf8_src[i] = e.nodes[0].column;
+                any_utf8 = true;
+            }
+        }
+        if (any_utf8) return nqe_filter_project_strings(ctx, in, predicate, projs, n_projs, utf8_src, out);
     }
 
     DevProgramSet ps;

@@ -27,6 +27,9 @@
 
 int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *words, unsigned long long *zeros);
 
+int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t left_key,
+                              int32_t right_key, nqe_table **out);
+
 namespace {
 
 constexpr int HJ_THREADS = 256;
@@ -538,7 +541,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     if (nl > HJ_MAX_COLS || nr > HJ_MAX_COLS) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "more than %d columns on one join side", HJ_MAX_COLS);
     for (auto *t : {left, right})
         for (auto &c : t->cols)
-            if (c.dtype == NQE_UTF8) return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 payload columns are not implemented on the CUDA join path yet");
+            if (c.dtype == NQE_UTF8) return nqe_hash_join_strings(ctx, left, right, left_key, right_key, out); // utf8.cu
 
     OpTimer timer(ctx);
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));

@@ -1,0 +1,297 @@
+// utf8.cu -- Utf8 (StringArray) columns riding along through selection and join.
+//
+// The reference compacts every input column in SelectionPlan, strings included
+// (selection.rs:82-97), and `take`s string payload columns in HashJoin (hash_join.rs:236-246).
+// Here the numeric kernels additionally emit the surviving input row numbers (a hidden Int64
+// row-id column travels through the same compaction / join), and the string columns are then
+// gathered with those row ids:
+//   lengths[i] = offsets[id+1] - offsets[id]   (0 for NULL)  ->  exclusive scan  ->  byte copy
+#include <cstring>
+#include <vector>
+
+#include "nqe_internal.cuh"
+
+int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *words, unsigned long long *zeros);
+
+namespace {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8; // 2048 elements per block
+
+__global__ void iota_kernel(unsigned long long *out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (unsigned long long)i;
+}
+
+// lengths of the gathered strings; valid[i] = the source row exists and is non-NULL
+__global__ void utf8_len_kernel(const int32_t *__restrict__ src_off, const uint32_t *__restrict__ src_valid,
+                                const long long *__restrict__ idx, const uint32_t *__restrict__ idx_valid, int64_t n,
+                                int32_t *__restrict__ len, uint8_t *__restrict__ valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ok = !idx_valid || ((idx_valid[i >> 5] >> (i & 31)) & 1u);
+    int32_t l = 0;
+    if (ok) {
+        const long long r = idx[i];
+        if (src_valid && !((src_valid[r >> 5] >> (r & 31)) & 1u)) ok = false;
+        else l = src_off[r + 1] - src_off[r];
+    }
+    len[i] = l;
+    if (valid) valid[i] = (uint8_t)ok;
+}
+
+// two-level exclusive scan of int32 (sums kept in 64 bits to detect > 2 GiB of string data)
+__global__ void scan_block_sums(const int32_t *__restrict__ in, int64_t n, unsigned long long *__restrict__ block_sums) {
+    __shared__ unsigned long long s[SC_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SC_THREADS * SC_ITEMS;
+    unsigned long long v = 0;
+    for (int k = 0; k < SC_ITEMS; k++) {
+        const int64_t i = base + (int64_t)k * SC_THREADS + threadIdx.x;
+        if (i < n) v += (unsigned long long)in[i];
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < SC_THREADS / 32; w++) t += s[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+__global__ void scan_sums_serial(unsigned long long *block_sums, int64_t n_blocks, unsigned long long *total) {
+    // one thread: n_blocks = n / 2048 (48k for 1e8 rows)
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long run = 0;
+    for (int64_t b = 0; b < n_blocks; b++) {
+        const unsigned long long v = block_sums[b];
+        block_sums[b] = run;
+        run += v;
+    }
+    *total = run;
+}
+__global__ void scan_finish(const int32_t *__restrict__ in, int64_t n, const unsigned long long *__restrict__ block_sums,
+                            int32_t *__restrict__ out_offsets) {
+    // each block rescans its 2048 elements sequentially per thread-chunk: thread t owns SC_ITEMS consecutive items
+    __shared__ unsigned long long s[SC_THREADS];
+    const int64_t base = (int64_t)blockIdx.x * SC_THREADS * SC_ITEMS + (int64_t)threadIdx.x * SC_ITEMS;
+    int32_t v[SC_ITEMS];
+    unsigned long long sum = 0;
+    for (int k = 0; k < SC_ITEMS; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        sum += (unsigned long long)v[k];
+    }
+    s[threadIdx.x] = sum;
+    __syncthreads();
+    // exclusive scan over the 256 thread sums (Hillis-Steele)
+    for (int o = 1; o < SC_THREADS; o <<= 1) {
+        unsigned long long t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = block_sums[blockIdx.x] + s[threadIdx.x] - sum;
+    for (int k = 0; k < SC_ITEMS; k++) {
+        if (base + k < n) out_offsets[base + k] = (int32_t)run;
+        run += (unsigned long long)v[k];
+    }
+}
+
+__global__ void utf8_copy_kernel(const int32_t *__restrict__ src_off, const uint8_t *__restrict__ src_data,
+                                 const long long *__restrict__ idx, const int32_t *__restrict__ out_off, int64_t n,
+                                 uint8_t *__restrict__ out_data) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t o0 = out_off[i], l = out_off[i + 1] - o0;
+    if (l <= 0) return;
+    const uint8_t *s = src_data + src_off[idx[i]];
+    uint8_t *d = out_data + o0;
+    for (int32_t b = 0; b < l; b++) d[b] = s[b];
+}
+
+} // namespace
+
+// hidden row-id column 0..n-1 (owned by the caller)
+int32_t nqe_make_rowid_column(nqe_ctx *ctx, int64_t n, DevColumn *c) {
+    NQE_TRY(nqe_column_alloc(ctx, NQE_INT64, n, false, c));
+    if (n > 0) {
+        iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((unsigned long long *)c->values, n);
+        ctx->launches++;
+        NQE_CUDA(ctx, cudaGetLastError());
+    }
+    return NQE_OK;
+}
+
+// arrow `take` for a Utf8 column: out[i] = src[idx[i]] (NULL when idx[i] is NULL or src[idx[i]] is NULL)
+int32_t nqe_take_utf8(nqe_ctx *ctx, const DevColumn &src, const DevColumn &idx, int64_t n, DevColumn *out) {
+    memset((void *)out, 0, sizeof *out);
+    *out = DevColumn();
+    out->dtype = NQE_UTF8;
+    out->length = n;
+    out->owned = true;
+    NQE_TRY(nqe_dev_alloc(ctx, &out->values, (size_t)(n + 1) * 4 + 64));
+    const bool nullable = src.validity || idx.validity;
+    void *len = nullptr, *vbytes = nullptr, *sums = nullptr;
+    int32_t rc = nqe_dev_alloc(ctx, &len, (size_t)(n + 1) * 4 + 64);
+    if (rc == NQE_OK && nullable) rc = nqe_dev_alloc(ctx, &vbytes, (size_t)n + 64);
+    const int64_t n_blocks = (n + SC_THREADS * SC_ITEMS - 1) / (SC_THREADS * SC_ITEMS) + 1;
+    if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, &sums, (size_t)n_blocks * 8);
+    if (rc == NQE_OK) {
+        cudaMemsetAsync(ctx->d_scratch + 40, 0, 2 * sizeof(uint64_t), ctx->stream);
+        if (n > 0) {
+            utf8_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+                (const int32_t *)src.values, (const uint32_t *)src.validity, (const long long *)idx.values,
+                (const uint32_t *)idx.validity, n, (int32_t *)len, (uint8_t *)vbytes);
+            scan_block_sums<<<(unsigned)n_blocks, SC_THREADS, 0, ctx->stream>>>((const int32_t *)len, n, (unsigned long long *)sums);
+            scan_sums_serial<<<1, 32, 0, ctx->stream>>>((unsigned long long *)sums, n_blocks, (unsigned long long *)(ctx->d_scratch + 40));
+            scan_finish<<<(unsigned)n_blocks, SC_THREADS, 0, ctx->stream>>>((const int32_t *)len, n, (const unsigned long long *)sums,
+                                                                           (int32_t *)out->values);
+            // offsets[n] = total bytes (low 32 bits of the 64-bit total; > 2 GiB is rejected below)
+            cudaMemcpyAsync((int32_t *)out->values + n, ctx->d_scratch + 40, 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            ctx->launches += 4;
+        } else {
+            cudaMemsetAsync(out->values, 0, 4, ctx->stream);
+        }
+        cudaMemcpyAsync(ctx->h_scratch + 40, ctx->d_scratch + 40, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = nqe_fail(ctx, NQE_ERR_CUDA, "utf8 take failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc == NQE_OK) {
+        const uint64_t total = ctx->h_scratch[40];
+        if (total > 0x7fffffffull) rc = nqe_fail(ctx, NQE_ERR_PANIC, "Utf8 column exceeds 2 GiB of string data (i32 offsets overflow)");
+        out->data_bytes = (int64_t)total;
+    }
+    if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, (void **)&out->data, (size_t)out->data_bytes + 64);
+    if (rc == NQE_OK && n > 0) {
+        utf8_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            (const int32_t *)src.values, src.data, (const long long *)idx.values, (const int32_t *)out->values, n, out->data);
+        ctx->launches++;
+        if (nullable) {
+            rc = nqe_dev_alloc(ctx, (void **)&out->validity, nqe_bitmap_bytes(n));
+            if (rc == NQE_OK) {
+                cudaMemsetAsync(ctx->d_scratch + 41, 0, sizeof(uint64_t), ctx->stream);
+                rc = nqe_pack_bytes(ctx, (const uint8_t *)vbytes, n, (uint32_t *)out->validity, (unsigned long long *)(ctx->d_scratch + 41));
+                cudaMemcpyAsync(ctx->h_scratch + 41, ctx->d_scratch + 41, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "utf8 take failed");
+                out->null_count = (int64_t)ctx->h_scratch[41];
+                if (rc == NQE_OK && out->null_count == 0) {
+                    nqe_dev_free(ctx, out->validity);
+                    out->validity = nullptr;
+                }
+            }
+        }
+    }
+    nqe_dev_free(ctx, len);
+    nqe_dev_free(ctx, vbytes);
+    nqe_dev_free(ctx, sums);
+    if (rc != NQE_OK) nqe_column_release(ctx, out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// operator wrappers: run the numeric operator with a hidden row-id column, then gather
+// the Utf8 columns with the surviving row ids
+// ---------------------------------------------------------------------------
+static DevColumn borrow(const DevColumn &c) {
+    DevColumn b = c;
+    b.owned = false;
+    return b;
+}
+
+// projs[i] with utf8_src[i] >= 0 is a bare reference to Utf8 column utf8_src[i] of `in`
+int32_t nqe_filter_project_strings(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                                   int32_t n_projs, const int *utf8_src, nqe_table **out) {
+    const int ncols = (int)in->cols.size();
+    nqe_table aug;
+    aug.ctx = ctx;
+    aug.nrows = in->nrows;
+    for (auto &c : in->cols) aug.cols.push_back(borrow(c));
+    DevColumn rowid;
+    NQE_TRY(nqe_make_rowid_column(ctx, in->nrows, &rowid));
+    aug.cols.push_back(borrow(rowid));
+    std::vector<nqe_expr> p2;
+    for (int i = 0; i < n_projs; i++)
+        if (utf8_src[i] < 0) p2.push_back(projs[i]);
+    nqe_expr_node rid{NQE_NODE_COLUMN, 0, ncols, 0, 0, 0, {0}};
+    p2.push_back(nqe_expr{&rid, 1, 0});
+    nqe_table *tmp = nullptr;
+    int32_t rc = (int)p2.size() > 16 ? nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "more than 15 output columns next to Utf8 columns")
+                                     : nqe_filter_project(ctx, &aug, predicate, p2.data(), (int32_t)p2.size(), &tmp);
+    nqe_table *res = nullptr;
+    if (rc == NQE_OK) {
+        nqe_table_new(ctx, tmp->nrows, &res);
+        res->cols.resize(n_projs);
+        const DevColumn &ids = tmp->cols.back();
+        int k = 0;
+        for (int i = 0; i < n_projs && rc == NQE_OK; i++) {
+            if (utf8_src[i] < 0) {
+                res->cols[i] = tmp->cols[k];
+                tmp->cols[k].owned = false; // moved
+                k++;
+            } else {
+                rc = nqe_take_utf8(ctx, in->cols[utf8_src[i]], ids, tmp->nrows, &res->cols[i]);
+            }
+        }
+    }
+    if (tmp) nqe_table_free(tmp);
+    nqe_column_release(ctx, &rowid);
+    if (rc != NQE_OK) {
+        if (res) nqe_table_free(res);
+        return rc;
+    }
+    *out = res;
+    return NQE_OK;
+}
+
+int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t left_key,
+                              int32_t right_key, nqe_table **out) {
+    const nqe_table *side[2] = {left, right};
+    const int key[2] = {left_key, right_key};
+    nqe_table aug[2];
+    DevColumn rowid[2];
+    std::vector<int> map[2]; // original column -> column in aug (numeric) or -1 (Utf8)
+    int akey[2] = {0, 0};
+    int32_t rc = NQE_OK;
+    for (int s = 0; s < 2 && rc == NQE_OK; s++) {
+        aug[s].ctx = ctx;
+        aug[s].nrows = side[s]->nrows;
+        for (size_t c = 0; c < side[s]->cols.size(); c++) {
+            if (side[s]->cols[c].dtype == NQE_UTF8) map[s].push_back(-1);
+            else {
+                map[s].push_back((int)aug[s].cols.size());
+                aug[s].cols.push_back(borrow(side[s]->cols[c]));
+            }
+        }
+        akey[s] = map[s][key[s]];
+        rc = nqe_make_rowid_column(ctx, side[s]->nrows, &rowid[s]);
+        aug[s].cols.push_back(borrow(rowid[s]));
+    }
+    nqe_table *tmp = nullptr;
+    if (rc == NQE_OK) rc = nqe_hash_join(ctx, &aug[0], &aug[1], akey[0], akey[1], &tmp);
+    nqe_table *res = nullptr;
+    if (rc == NQE_OK) {
+        nqe_table_new(ctx, tmp->nrows, &res);
+        const int nl_aug = (int)aug[0].cols.size();
+        const DevColumn *ids[2] = {&tmp->cols[nl_aug - 1], &tmp->cols.back()};
+        for (int s = 0; s < 2 && rc == NQE_OK; s++) {
+            for (size_t c = 0; c < side[s]->cols.size() && rc == NQE_OK; c++) {
+                DevColumn col;
+                if (map[s][c] >= 0) {
+                    const int t = (s ? nl_aug : 0) + map[s][c];
+                    col = tmp->cols[t];
+                    tmp->cols[t].owned = false; // moved
+                } else {
+                    rc = nqe_take_utf8(ctx, side[s]->cols[c], *ids[s], tmp->nrows, &col);
+                }
+                res->cols.push_back(col);
+            }
+        }
+    }
+    if (tmp) nqe_table_free(tmp);
+    nqe_column_release(ctx, &rowid[0]);
+    nqe_column_release(ctx, &rowid[1]);
+    if (rc != NQE_OK) {
+        if (res) nqe_table_free(res);
+        return rc;
+    }
+    *out = res;
+    return NQE_OK;
+}

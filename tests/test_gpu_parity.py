@@ -425,3 +425,53 @@ def test_distributed_plan_on_one_gpu_matches_oracle():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- Utf8 columns riding along
+def test_golden_selection_with_names():  # selection.rs:126-178 with the Utf8 column
+    t1 = golden_table("t1")
+    proj = O.projection(t1, [("col", 0), ("col", 1), ("col", 2)])
+    pred = ("bin", "Gt", ("bin", "Plus", ("col", 0), lit(1)), lit(5))
+    out = G.gpu_selection(proj, pred)
+    assert out.cols[0].to_pylist() == FX["test_selection"]["id"]
+    assert out.cols[1].to_pylist() == FX["test_selection"]["name"]
+
+
+def test_golden_readme_limit_offset_with_names():  # README.md:70-76
+    import nqe_b200 as nq
+    import pyarrow as pa
+    t1 = golden_table("t1")
+    sel = nq.SelectionPlan.create(G.scan(t1), G.expr(("bin", "Lt", ("col", 0), lit(9))))
+    proj = nq.ProjectionPlan.create(sel, pa.schema([("id", pa.int64()), ("name", pa.utf8()), ("age + 100", pa.int64())]),
+                                    [G.expr(("col", 0)), G.expr(("col", 1)), G.expr(("bin", "Plus", ("col", 2), lit(100)))])
+    plan = nq.PhysicalLimitPlan.create(nq.PhysicalOffsetPlan.create(proj, 2), 3)  # offset then limit (sql/planner.rs:49-52)
+    got = G.from_arrow(plan.execute()[0])
+    assert [list(r) for r in got.rows()] == FX["readme_limit_offset"]["rows"]
+
+
+def test_golden_readme_three_way_join_with_strings():  # README.md:77-85, exact printed order
+    emp, rank, dept = golden_table("employee"), golden_table("rank"), golden_table("department")
+    j1 = G.gpu_join(emp, rank, "rank", "id")
+    assert j1.rows() == O.hash_join(emp, rank, "rank", "id").rows()
+    j2 = G.gpu_join(j1, dept, "department_id", "id")
+    names = j2.names
+    proj = G.gpu_projection(j2, [("col", 0), ("col", 1), ("col", names.index("rank_name")), ("col", names.index("department_name"))],
+                            names=["id", "name", "rank_name", "department_name"])
+    assert [list(r) for r in proj.rows()] == FX["readme_join"]["rows"]
+
+
+def test_strings_through_filter_and_join_random():
+    rng = np.random.default_rng(21)
+    n = 20_000
+    words = ["", "a", "bb", "naïve", "query", "engine-" * 5, "π", "x" * 100]
+    s = [None if rng.random() < 0.1 else words[int(rng.integers(0, len(words)))] + str(int(rng.integers(0, 50))) for _ in range(n)]
+    b = O.Batch(["k", "s", "v"], [rand_col(rng, "i64", n, 0.1, lo=0, hi=500), O.col("utf8", s), rand_col(rng, "f64", n, 0.1)])
+    pred = ("bin", "Lt", ("col", 0), lit(250))
+    assert G.gpu_selection(b, pred).rows() == O.selection(b, pred).rows()
+    exprs = [("col", 1), ("bin", "Plus", ("col", 0), lit(1)), ("col", 1)]
+    assert G.gpu_projection(b, exprs, pred=pred).rows() == O.projection(O.selection(b, pred), exprs).rows()
+    nl = 300
+    ls = [None if i % 17 == 0 else f"dim-{i}" for i in range(nl)]
+    l = O.Batch(["id", "label"], [O.Col("i64", rng.permutation(nl).astype(np.int64)), O.col("utf8", ls)])
+    r = O.Batch(["k", "s", "v"], [O.Col("i64", rng.integers(0, 400, n)), b.cols[1], b.cols[2]])
+    assert G.gpu_join(l, r, "id", "k").rows() == O.hash_join(l, r, "id", "k").rows()
