@@ -46,9 +46,16 @@ struct JP {
     u32 *status;
     int num_tiles;
     int pad;
+    u64 *prof;
 };
-#define THREADS 256
 #define WARPS 8
+#if NQE_PROF
+#define PROF_T0 long long _t0 = clock64();
+#define PROF_ADD(i) { const long long _t1 = clock64(); _prof[i] += (u64)(_t1 - _t0); _t0 = _t1; }
+#else
+#define PROF_T0
+#define PROF_ADD(i)
+#endif
 #define LB_AGG (1ull << 62)
 #define LB_PREFIX (2ull << 62)
 #define LB_MASK ((1ull << 62) - 1)
@@ -263,6 +270,12 @@ extern "C" __global__ void __launch_bounds__(THREADS) nqe_fp_jit(const __grid_co
 #endif
 )SRC";
 
+// TMA-ring skeleton (the default when every referenced buffer is 16-byte aligned): see
+// jit_tma_skeleton.inc for the design.
+const char *kSkeletonTma =
+#include "build/jit_tma_skeleton.inc.h"
+    ;
+
 struct TNode {
     int kind, op, dtype, col, lit; // col: column slot; lit: literal slot
     int left = -1, right = -1;
@@ -273,12 +286,19 @@ struct Gen {
     std::vector<int> col_of_slot; // table column per slot
     std::vector<uint64_t> lits;
     std::vector<TNode> nodes;
+    std::vector<char> in_proj; // slot is read by some projection
+    bool parsing_proj = false;
 
     int slot_of(int col) {
-        for (size_t s = 0; s < col_of_slot.size(); s++)
-            if (col_of_slot[s] == col) return (int)s;
-        col_of_slot.push_back(col);
-        return (int)col_of_slot.size() - 1;
+        size_t s = 0;
+        for (; s < col_of_slot.size(); s++)
+            if (col_of_slot[s] == col) break;
+        if (s == col_of_slot.size()) {
+            col_of_slot.push_back(col);
+            in_proj.push_back(0);
+        }
+        if (parsing_proj) in_proj[s] = 1;
+        return (int)s;
     }
 
     // parse one postfix program; returns root index or -1 when the JIT does not apply
@@ -404,6 +424,7 @@ struct JitParams {
     uint32_t *status;
     int32_t num_tiles;
     int32_t pad;
+    unsigned long long *prof;
 };
 
 struct CachedKernel {
@@ -425,19 +446,20 @@ std::mutex &cache_mutex() {
 
 // Returns NQE_OK and sets *used = true when the specialised kernel was launched;
 // *used = false means "not applicable, use the interpreter kernels".
-int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
-                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
-                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
-                               std::string *source_out) {
+static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                                       int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                                       unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
+                                       std::string *source_out, bool allow_tma) {
     *used = false;
     Nvrtc &rt = nvrtc();
     if (!rt.ok && !source_out) return NQE_OK;
-    static int K = 0;
-    if (!K) {
+    static int CK = 0;
+    if (!CK) {
         const char *e = getenv("NQE_JIT_K");
-        K = e ? atoi(e) : 4;
-        if (K != 1 && K != 2 && K != 4 && K != 8) K = 4;
+        CK = e ? atoi(e) : 4;
+        if (CK != 1 && CK != 2 && CK != 4 && CK != 8) CK = 4;
     }
+    int K = CK;
     Gen g;
     g.in = in;
     int pred_root = -1;
@@ -446,6 +468,7 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
         if (pred_root < 0) return NQE_OK;
     }
     const size_t n_pred_cols = g.col_of_slot.size();
+    g.parsing_proj = true;
     std::vector<int> roots;
     for (int i = 0; i < n_projs; i++) {
         const int r = g.parse(&projs[i]);
@@ -460,16 +483,76 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
         D = e ? atoi(e) : 4;
         if (D < 1 || D > 8) D = 4;
     }
-    src << "#define K " << K << "\n#define D " << D << "\n#define HAS_PRED " << (predicate ? 1 : 0) << "\n";
+    // TMA-ring variant: knobs NQE_JIT_IMPL=tma|ca, NQE_JIT_TMA_K / _SP / _SW / _LAG / _WALKERS / _LBW / _OCC
+    static int impl = -1, TK = 4, SP = 4, SW = 4, LAG = 8, WALKERS = 2, lbw = 4, prof = 0;
+    if (impl < 0) {
+        auto knob = [](const char *name, int dflt, int lo, int hi) {
+            const char *e = getenv(name);
+            const int v = e ? atoi(e) : dflt;
+            return v < lo || v > hi ? dflt : v;
+        };
+        const char *e = getenv("NQE_JIT_IMPL");
+        impl = (e && !strcmp(e, "ca")) ? 0 : 1;
+        TK = knob("NQE_JIT_TMA_K", 4, 1, 16);
+        if (TK & (TK - 1)) TK = 4;
+        SP = knob("NQE_JIT_TMA_SP", 4, 2, 16);
+        SW = knob("NQE_JIT_TMA_SW", 4, 2, 16);
+        LAG = knob("NQE_JIT_TMA_LAG", 8, 0, 48);
+        WALKERS = knob("NQE_JIT_TMA_WALKERS", 2, 1, 4);
+        lbw = knob("NQE_JIT_TMA_LBW", 4, 1, 16); // look-back window: 32*lbw tiles per L2 round trip
+        prof = getenv("NQE_JIT_PROF") ? 1 : 0;
+    }
+    bool tma = allow_tma && impl == 1 && predicate && n_pred_cols > 0;
+    const size_t n_slots = g.col_of_slot.size();
+    uint32_t pstage = 0, ptx = 0, wstage = 0, wtx = 0;
+    std::vector<uint32_t> poff(n_slots), woff(n_slots), col_bytes(n_slots);
+    int sp = SP, sw = SW;
+    if (tma) {
+        const uint32_t tile = (uint32_t)TK * 256;
+        bool any_proj = false;
+        for (size_t s = 0; s < n_slots; s++) {
+            const DevColumn &c = in->cols[g.col_of_slot[s]];
+            if ((uintptr_t)c.values & 15) tma = false;
+            col_bytes[s] = c.dtype == NQE_BOOL ? tile / 8 : tile * 8;
+            const uint32_t padded = (col_bytes[s] + 127) & ~127u;
+            if (s < n_pred_cols) { poff[s] = pstage; pstage += padded; ptx += col_bytes[s]; }
+            if (g.in_proj[s]) { woff[s] = wstage; wstage += padded; wtx += col_bytes[s]; any_proj = true; }
+        }
+        if (!any_proj) tma = false; // projections of literals only: nothing to stage
+        while (sw > 2 && (size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) sw--;
+        while (sp > 2 && (size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) sp--;
+        if ((size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) tma = false;
+    }
+    const int nr = LAG + sw + WALKERS + 2; // ring slots of per-tile state: covers claim .. write of a tile
+    src << "#define NQE_PROF " << (tma ? prof : 0) << "\n";
+    if (tma) {
+        K = TK;
+        src << "#define K " << TK << "\n#define SP " << sp << "\n#define SW " << sw << "\n#define LAG " << LAG << "\n#define NR " << nr
+            << "\n#define WALKERS " << WALKERS << "\n#define HAS_PRED 1\n#define NQE_LB_WIDE " << lbw << "\n#define NQE_LB_BACKOFF 40\n"
+            << "#define PSTAGE_BYTES " << pstage << "u\n#define PRED_TX_BYTES " << ptx << "u\n#define WSTAGE_BYTES " << wstage
+            << "u\n#define WRITE_TX_BYTES " << wtx << "u\n#define THREADS 256\n";
+    } else {
+        K = CK;
+        src << "#define K " << K << "\n#define D " << D << "\n#define HAS_PRED " << (predicate ? 1 : 0) << "\n#define THREADS 256\n";
+    }
     // column slots used by the predicate are parsed first, so they are slots [0, n_pred_cols)
     static int HINTS = -1;
     if (HINTS < 0) {
         const char *e = getenv("NQE_JIT_L2_HINTS");
         HINTS = e ? atoi(e) : 0; // measured: no gain on B200 (profiles/README_r01.md)
     }
-    auto emit_loads = [&](std::ostringstream &o, size_t first, size_t last, const char *v, const char *e0, const char *full, bool decl,
-                          const char *pol = nullptr) {
-        for (size_t s = first; s < last; s++) {
+    std::vector<size_t> all_slots, pred_slots, proj_slots;
+    for (size_t s = 0; s < n_slots; s++) {
+        all_slots.push_back(s);
+        if (s < n_pred_cols) pred_slots.push_back(s);
+        if (g.in_proj[s]) proj_slots.push_back(s);
+    }
+    auto emit_decls = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v) {
+        for (size_t s : slots) o << "u64 " << v << s << "_[K];\n";
+    };
+    auto emit_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v, const char *e0, const char *full,
+                          bool decl, const char *pol = nullptr) {
+        for (size_t s : slots) {
             const int dt = in->cols[g.col_of_slot[s]].dtype;
             if (decl) o << "u64 " << v << s << "_[K];\n";
             o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; ";
@@ -482,11 +565,36 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
                     o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
         }
     };
+    // operands of a staged (full) tile come from shared memory: row j*256+tid of the stage's column block
+    auto emit_smem_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off) {
+        for (size_t s : slots) {
+            const int dt = in->cols[g.col_of_slot[s]].dtype;
+            o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) ";
+            if (dt == NQE_BOOL)
+                o << "c" << s << "_[j] = (((const u32 *)(stg + " << off[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
+            else
+                o << "c" << s << "_[j] = ((const u64 *)(stg + " << off[s] << "))[j * 256 + tid];\n";
+        }
+    };
+    auto emit_copies = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off, bool pred_ring) {
+        for (size_t s : slots) // a predicate column that a projection reads again is kept in L2 for the write pass
+            o << "bulk_g2s(dst + " << off[s] << ", (const u8 *)p.col[" << s << "] + (size_t)tile * " << col_bytes[s] << "u, " << col_bytes[s]
+              << "u, bar, " << (pred_ring && g.in_proj[s] ? "pol_keep" : "pol_stream") << ");\n";
+    };
     std::ostringstream loads, pred_loads, next_decl, next_loads;
-    emit_loads(loads, 0, g.col_of_slot.size(), "c", "e0", "full", true, "pol_stream");
-    emit_loads(pred_loads, 0, n_pred_cols, "c", "e0", "full", true, "pol_keep");
+    emit_loads(loads, tma ? proj_slots : all_slots, "c", "e0", "full", !tma, "pol_stream");
+    emit_loads(pred_loads, pred_slots, "c", "e0", "full", !tma, "pol_keep");
     for (size_t s = 0; s < n_pred_cols; s++) next_decl << "u64 n" << s << "_[K];\n";
-    emit_loads(next_loads, 0, n_pred_cols, "n", "n0", "nfull", false, "pol_keep");
+    emit_loads(next_loads, pred_slots, "n", "n0", "nfull", false, "pol_keep");
+    std::ostringstream decls, pred_decls, smem_loads, smem_pred_loads, pred_copies, write_copies;
+    if (tma) {
+        emit_decls(decls, proj_slots, "c");
+        emit_decls(pred_decls, pred_slots, "c");
+        emit_smem_loads(smem_loads, proj_slots, woff);
+        emit_smem_loads(smem_pred_loads, pred_slots, poff);
+        emit_copies(pred_copies, pred_slots, poff, true);
+        emit_copies(write_copies, proj_slots, woff, false);
+    }
     std::ostringstream stores;
     for (int o = 0; o < n_projs; o++) {
         const TNode &r = g.nodes[roots[o]];
@@ -510,7 +618,15 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
         }
         return s;
     };
-    std::string kernel = kSkeletonKernel;
+    std::string kernel = tma ? kSkeletonTma : kSkeletonKernel;
+    if (tma) {
+        kernel = replace_all(kernel, "ISSUE_PRED_COPIES", pred_copies.str());
+        kernel = replace_all(kernel, "ISSUE_WRITE_COPIES", write_copies.str());
+        kernel = replace_all(kernel, "DECL_PRED_COLUMNS", pred_decls.str());
+        kernel = replace_all(kernel, "DECL_COLUMNS", decls.str());
+        kernel = replace_all(kernel, "SMEM_LOAD_PRED_COLUMNS", smem_pred_loads.str());
+        kernel = replace_all(kernel, "SMEM_LOAD_COLUMNS", smem_loads.str());
+    }
     kernel = replace_all(kernel, "LOAD_PRED_COLUMNS", pred_loads.str());
     kernel = replace_all(kernel, "DECL_NEXT_COLUMNS", next_decl.str());
     kernel = replace_all(kernel, "LOAD_NEXT_COLUMNS", next_loads.str());
@@ -549,6 +665,10 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
                     rt.GetCUBINSize(prog, &n);
                     std::vector<char> cubin(n);
                     rt.GetCUBIN(prog, cubin.data());
+                    if (const char *dump = getenv("NQE_JIT_DUMP")) { // <dump>.cu / <dump>.cubin for cuobjdump -sass
+                        if (FILE *f = fopen((std::string(dump) + ".cu").c_str(), "w")) { fputs(source.c_str(), f); fclose(f); }
+                        if (FILE *f = fopen((std::string(dump) + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, n, f); fclose(f); }
+                    }
                     if (cudaLibraryLoadData(&ck.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
                         cudaLibraryGetKernel(&ck.kernel, ck.lib, "nqe_fp_jit") != cudaSuccess) {
                         cudaGetLastError();
@@ -576,7 +696,26 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
     jp.num_tiles = (int32_t)((in->nrows + tile - 1) / tile);
     if (jp.num_tiles == 0) { *used = true; return NQE_OK; }
     int grid = jp.num_tiles;
-    if (predicate) {
+    int block = 256;
+    size_t dyn = 0;
+    if (tma) {
+        block = 320 + 32 * WALKERS; // 8 worker warps + loader + publisher + the walker warps
+        dyn = (size_t)sp * pstage + (size_t)sw * wstage;
+        int occ = 0;
+        if (cudaFuncSetAttribute((const void *)ck.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)ck.kernel, block, dyn) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            return NQE_OK; // the caller retries with the register-staged variant
+        }
+        static int max_occ = -1; // knob: cap CTAs per SM (NQE_JIT_TMA_OCC)
+        if (max_occ < 0) {
+            const char *e = getenv("NQE_JIT_TMA_OCC");
+            max_occ = e ? atoi(e) : 0;
+        }
+        if (max_occ > 0 && occ > max_occ) occ = max_occ;
+        grid = ctx->sm_count * occ;
+        if (grid > jp.num_tiles) grid = jp.num_tiles;
+    } else if (predicate) {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)ck.kernel, 256, 0) != cudaSuccess || occ < 1) {
             cudaGetLastError();
@@ -585,9 +724,40 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
         grid = ctx->sm_count * occ;
         if (grid > jp.num_tiles) grid = jp.num_tiles;
     }
+    unsigned long long *d_prof = nullptr;
+    if (tma && prof) {
+        cudaMalloc(&d_prof, 32 * 8);
+        cudaMemsetAsync(d_prof, 0, 32 * 8, ctx->stream);
+        jp.prof = d_prof;
+    }
     void *args[] = {&jp};
-    NQE_CUDA(ctx, cudaLaunchKernel((const void *)ck.kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+    NQE_CUDA(ctx, cudaLaunchKernel((const void *)ck.kernel, dim3(grid), dim3(block), args, dyn, ctx->stream));
     ctx->launches++;
+    if (d_prof) { // per-phase cycle averages of the control warp / worker warp 0 (tuning aid)
+        unsigned long long h[32];
+        cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_prof);
+        const double it = h[5] ? (double)h[5] : 1.0;
+        fprintf(stderr, "[nqe jit prof] grid %d iters/cta %.1f | publisher: wait_cnt %.0f scan+publish %.0f; walkers: wait_pub %.0f walk %.0f; loader: wait_free %.0f issue %.0f"
+                        " | worker: idle %.0f count %.0f blocked %.0f write %.0f (cycles per tile)\n",
+                grid, it / grid, h[0] / it, h[1] / it, h[6] / it, h[2] / it, h[3] / it, h[4] / it, h[8] / it, h[9] / it, h[10] / it, h[11] / it);
+        fprintf(stderr, "[nqe jit prof] tile life, avg (max) cycles: claim->count %.0f (%llu) count->publish %.0f (%llu) publish->prefix %.0f (%llu)"
+                        " prefix->write %.0f (%llu) write %.0f (%llu)\n",
+                h[16] / it, h[24], h[17] / it, h[25], h[18] / it, h[26], h[19] / it, h[27], h[20] / it, h[28]);
+    }
     *used = true;
     return NQE_OK;
+}
+
+int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
+                               std::string *source_out) {
+    int32_t rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, tile_state, ticket, out_count, status,
+                                         used, source_out, true);
+    if (rc == NQE_OK && !*used && !source_out)
+        rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, tile_state, ticket, out_count, status, used,
+                                     source_out, false);
+    return rc;
 }

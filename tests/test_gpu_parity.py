@@ -120,6 +120,72 @@ def test_filter_project_random(n, null_frac):
     same(G.gpu_projection(b, exprs), O.projection(b, exprs))
 
 
+def _fp_arrow(n, seed, k):
+    """Numeric NULL-free table + `a < k` / (a, b + 100, x * 0.5, f) through the fused call; numpy-side expectation."""
+    import pyarrow as pa
+    from importlib import import_module
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1000, n).astype(np.int64)
+    b = rng.integers(-100, 100, n).astype(np.int64)
+    x = rng.normal(0, 10, n)
+    f = rng.integers(0, 2, n).astype(bool)
+    rb = pa.RecordBatch.from_arrays([pa.array(a), pa.array(b), pa.array(x), pa.array(f)], names=["a", "b", "x", "f"])
+    src = G.nq.ScanPlan.create(G.nq.MemTable.try_create(rb.schema, [rb]), None).execute_device()
+    pred = G.expr(("bin", "Lt", ("col", 0), lit(k)))
+    exprs = [G.expr(e) for e in [("col", 0), ("bin", "Plus", ("col", 1), lit(100)),
+                                 ("bin", "Multiply", ("col", 2), ("lit", "f64", 0.5)), ("col", 3)]]
+    got = pp._filter_project(src, pred, exprs, ["a", "b + 100", "x * 0.5", "f"]).to_arrow()
+    m = a < k
+    return got, [a[m], b[m] + 100, x[m] * 0.5, f[m]]
+
+
+@pytest.mark.parametrize("n", [1024 * 37, 1024 * 37 + 1, 3_000_017])
+@pytest.mark.parametrize("k", [0, 7, 500, 993, 1000])
+def test_filter_project_many_tiles(n, k):
+    """Multi-tile look-back chain, every selectivity, ragged and exact tile boundaries, Boolean column staged as a bitmap."""
+    got, want = _fp_arrow(n, n + k, k)
+    assert got.num_rows == len(want[0])
+    for i in range(4):
+        assert np.array_equal(got.column(i).to_numpy(zero_copy_only=False), want[i]), f"column {i}"
+
+
+def test_filter_project_full_size_config():
+    """BASELINE configs[1] at full size (1e8 rows generated in HBM): exact equality with the host-side generator."""
+    import torch
+    from importlib import import_module
+    synth = import_module("naive-query-engine_b200.synth")
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    ctx = G.nq.Context.default()
+    n = 100_000_000
+    bufs = []
+    for spec in synth.FILTER_TABLE:
+        t = torch.empty(n, dtype=torch.int64, device="cuda")
+        synth.device_column(ctx, spec, 0, n, t.data_ptr())
+        bufs.append(t)
+    ctx.sync()
+    tbl = G.nq.DeviceTable.from_device_pointers(ctx, ["id", "age", "score"], [2, 2, 4], [b.data_ptr() for b in bufs], n, keepalive=bufs)
+    pred = G.expr(("bin", "Lt", ("col", 0), lit(500)))
+    out = pp._filter_project(tbl, pred, [G.expr(("col", 0)), G.expr(("bin", "Plus", ("col", 1), lit(100)))], ["id", "age + 100"])
+    rows = out.num_rows
+    desc = [out.column_desc(i) for i in range(2)]
+    got = [torch.as_tensor(_CAI(d.values, rows), device="cuda").cpu().numpy() for d in desc]
+    ids = synth.mod_i64(42, 0, n, 1000)
+    m = ids < 500
+    assert rows == int(m.sum())
+    assert np.array_equal(got[0], ids[m])
+    del ids
+    age = synth.mod_i64(43, 0, n, 100)
+    assert np.array_equal(got[1], age[m] + 100)
+    out.free()
+    tbl.free()
+
+
+class _CAI:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
 @pytest.mark.parametrize("sel", ["none", "all"])
 def test_filter_all_or_nothing(sel):
     rng = np.random.default_rng(5)
