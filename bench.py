@@ -349,7 +349,8 @@ def run_gpu(args, rank, local_rank, world):
                        "timing": "CUDA events on the operator's stream, barrier+synchronize both sides, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
-                         "kernel": "nqe_fp_jit (filter_project, NVRTC shape-specialised; csrc/jit.cu)", "kernel_ms": kernel_ms,
+                         "kernel": "nqe_fp_jit (filter_project: NVRTC shape-specialised two-ring TMA dataflow kernel; "
+                                   "csrc/jit.cu + csrc/jit_tma_skeleton.inc)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
@@ -405,6 +406,29 @@ def run_secondary(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hb
         return {"rows_per_s": world * rows * steps / (ms / 1e3), "ms_per_step": ms / steps, "op_ms": k,
                 "out_rows": f.rows, "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k / 1e3) / 1e9,
                 "roofline_frac": alg_bytes / (k / 1e3) / 1e9 / hbm_peak}
+
+    # ---- configs[1] selectivity sweep (K in {10, 100, 900})
+    with torch.cuda.stream(stream):
+        ft, fb = device_table(nq, torch, ctx, synth.FILTER_TABLE, rank * n, n, [I64, I64, F64])
+    sweep = {}
+    lit, sv = nq.PhysicalLiteralExpr.create, nq.ScalarValue
+    for kk in (10, 100, 900):
+        pred = nq.PhysicalBinaryExpr.create(col(None, 0), "Lt", lit(sv.Int64(kk)))
+        projs = [col(None, 0), nq.PhysicalBinaryExpr.create(col(None, 1), "Plus", lit(sv.Int64(100)))]
+        kms = []
+        for _ in range(6):
+            out = pp._filter_project(ft, pred, projs, ["id", "age + 100"])
+            kms.append(ctx.last_op_ms)
+            rows = out.num_rows
+            out.free()
+        k = sorted(kms[2:])[len(kms[2:]) // 2]
+        alg = 16.0 * n + 16.0 * rows
+        sweep[f"id<{kk}"] = {"selectivity": rows / n, "op_ms": k, "rows_per_s": n / (k / 1e3), "algorithmic_bytes": alg,
+                             "roofline_frac": alg / (k / 1e3) / 1e9 / hbm_peak}
+    res["filter_project_selectivity_sweep"] = sweep
+    ft.free()
+    del fb
+    torch.cuda.empty_cache()
 
     # ---- configs[2]: group-by 1e8 rows, 1e5 groups
     with torch.cuda.stream(stream):

@@ -66,6 +66,19 @@ __device__ __forceinline__ unsigned long long *agg_rec(const AggParams &ap, uint
     return ap.table + (slot << ap.rec_shift);
 }
 
+// Sector 0 of a record = its first 32 bytes: the key and the first three state words.  The
+// layout (nqe_agg_layout) puts MIN/MAX states there, so ONE 256-bit load (LDG.256, L2 only:
+// an L1 miss would fetch the whole 128-byte line) answers "is this my key?" and "can my
+// value improve min/max?" at once -- a row costs one random sector read plus its reductions.
+struct Sector0 {
+    unsigned long long w[4];
+};
+__device__ __forceinline__ Sector0 ld_sector0(const AggParams &, const unsigned long long *rec) {
+    Sector0 s;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.w[0]), "=l"(s.w[1]), "=l"(s.w[2]), "=l"(s.w[3]) : "l"(rec));
+    return s;
+}
+
 // one probe step at `slot`: 1 = found/claimed, 0 = occupied by another key
 __device__ __forceinline__ int agg_probe_step(unsigned long long *r, unsigned long long seen, uint64_t key) {
     if (seen == EMPTY_KEY) seen = atomicCAS(r, (unsigned long long)EMPTY_KEY, (unsigned long long)key);
@@ -75,16 +88,16 @@ __device__ __forceinline__ int agg_probe_step(unsigned long long *r, unsigned lo
 // find-or-claim the records of K keys.  The first probe of all K keys is issued together
 // (K independent loads in flight: most keys resolve there at load factor <= 0.5); the rare
 // collisions are then walked one key at a time with a tight loop.  rec[j] == nullptr afterwards:
-// key j was not looked up (want bit clear) or the table is full (status flagged).
+// key j was not looked up (want bit clear) or the table is full (status flagged).  s0[j] is a
+// (possibly stale, which is safe: MIN/MAX states only move one way) copy of the record's sector 0.
 template <int K>
 __device__ __forceinline__ void find_slots(const AggParams &ap, const uint64_t (&key)[K], uint32_t want,
-                                           unsigned long long *(&rec)[K]) {
+                                           unsigned long long *(&rec)[K], Sector0 (&s0)[K]) {
     uint64_t slot[K];
-    unsigned long long seen[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
         slot[j] = agg_slot_of(ap, key[j]);
-        if ((want >> j) & 1u) seen[j] = ld_relaxed_u64(agg_rec(ap, slot[j]));
+        if ((want >> j) & 1u) s0[j] = ld_sector0(ap, agg_rec(ap, slot[j]));
     }
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -93,32 +106,36 @@ __device__ __forceinline__ void find_slots(const AggParams &ap, const uint64_t (
         if (key[j] == EMPTY_KEY) { // i64::MIN has its own record; word 0 != EMPTY marks it occupied
             rec[j] = agg_rec(ap, ap.mask + 1);
             *(volatile unsigned long long *)rec[j] = 0ull;
+            s0[j] = ld_sector0(ap, rec[j]);
             continue;
         }
         unsigned long long *r = agg_rec(ap, slot[j]);
-        if (agg_probe_step(r, seen[j], key[j])) { rec[j] = r; continue; }
+        if (agg_probe_step(r, s0[j].w[0], key[j])) { rec[j] = r; continue; }
         uint64_t s = slot[j];
         for (int probe = 1; probe < MAX_PROBE; probe++) {
             s = (s + 1) & ap.mask;
             r = agg_rec(ap, s);
-            if (agg_probe_step(r, ld_relaxed_u64(r), key[j])) { rec[j] = r; break; }
+            s0[j] = ld_sector0(ap, r);
+            if (agg_probe_step(r, s0[j].w[0], key[j])) { rec[j] = r; break; }
         }
         if (!rec[j]) atomicOr(ap.status, DEV_ERR_TABLE_FULL);
     }
 }
 
-__device__ __forceinline__ unsigned long long *find_slot(const AggParams &ap, uint64_t key) {
+__device__ __forceinline__ unsigned long long *find_slot(const AggParams &ap, uint64_t key, Sector0 *s0) {
     const uint64_t k1[1] = {key};
     unsigned long long *r1[1];
-    find_slots<1>(ap, k1, 1u, r1);
+    Sector0 s1[1];
+    find_slots<1>(ap, k1, 1u, r1, s1);
+    *s0 = s1[0];
     return r1[0];
 }
 
 // Fold one input row into its group's record.  src(id, &dtype, &bits) -> the argument value
 // of source id for this row is non-NULL.  States are sorted by source id, so a column that
-// feeds several states is fetched once.
+// feeds several states is fetched once.  s0 = the record's sector 0 as seen by the probe.
 template <typename Src>
-__device__ __forceinline__ void update_states(const AggParams &ap, unsigned long long *rec, const Src &src) {
+__device__ __forceinline__ void update_states(const AggParams &ap, unsigned long long *rec, const Sector0 &s0, const Src &src) {
     int last = -1, dtype = 0;
     bool valid = false;
     uint64_t bits = 0;
@@ -128,17 +145,19 @@ __device__ __forceinline__ void update_states(const AggParams &ap, unsigned long
             valid = src(last, &dtype, &bits);
         }
         if (!valid) continue; // NULL argument: the row does not touch this state
-        unsigned long long *w = rec + ap.st_off[s];
+        const int off = ap.st_off[s];
+        unsigned long long *w = rec + off;
         const int kind = ap.st_kind[s];
         if (kind == ST_CNT) { red_add_u64(w, 1ull); continue; }
         const double v = value_as_f64(dtype, bits);
-        if (kind == ST_SUM) red_add_f64(w, v);
-        else if (kind == ST_MAX) {
-            const unsigned long long k = nqe_f64_to_ord(v);
-            if (k > ld_relaxed_u64(w)) red_max_u64(w, k);
+        if (kind == ST_SUM) { red_add_f64(w, v); continue; }
+        const unsigned long long k = nqe_f64_to_ord(v);
+        // current state: from the probe's sector-0 copy when the word lives there (layout puts MIN/MAX first)
+        const unsigned long long cur = off == 1 ? s0.w[1] : off == 2 ? s0.w[2] : off == 3 ? s0.w[3] : ld_relaxed_u64(w);
+        if (kind == ST_MAX) {
+            if (k > cur) red_max_u64(w, k);
         } else if (v == v) { // MIN: `val < self.val` is never true for NaN (min.rs:49)
-            const unsigned long long k = nqe_f64_to_ord(v);
-            if (k < ld_relaxed_u64(w)) red_min_u64(w, k);
+            if (k < cur) red_min_u64(w, k);
         }
     }
 }

@@ -1,6 +1,8 @@
 // api.cu -- context, device tables, host<->HBM transfer (the ScanPlan side of the boundary)
 #include <cstring>
 
+#include <cstdlib>
+
 #include "nqe_internal.cuh"
 
 int32_t nqe_fail(nqe_ctx *ctx, int32_t code, const char *fmt, ...) {
@@ -58,6 +60,10 @@ extern "C" int32_t nqe_ctx_create(int32_t device, nqe_ctx **out) {
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    if (const char *e = getenv("NQE_L2_FETCH")) { // tuning knob: DRAM->L2 fetch granularity hint (32/64/128 bytes)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+        cudaGetLastError();
     }
     if (cudaGetLastError() != cudaSuccess || !ctx->h_scratch || !ctx->d_scratch) {
         nqe_ctx_destroy(ctx);

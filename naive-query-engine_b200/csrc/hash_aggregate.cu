@@ -39,21 +39,25 @@ __global__ void agg_init_kernel(AggParams ap, uint64_t n_records) {
 }
 
 // argument values of one input row, read from the columns registered in DevProgramSet
+template <bool SIMPLE>
 struct RowSource {
     const DevProgramSet &ps;
     int64_t e;
     __device__ __forceinline__ bool operator()(int slot, int *dtype, uint64_t *bits) const {
         const DevColRef &c = ps.cols[slot];
-        if (c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) return false;
+        if (!SIMPLE && c.validity && !((__ldg(c.validity + (e >> 5)) >> (e & 31)) & 1u)) return false;
         *dtype = c.dtype;
-        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : ld_cached_u64((const uint64_t *)c.values + e);
+        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : ld_stream_u64((const uint64_t *)c.values + e);
         return true;
     }
 };
 
-// program 0 of ps = group key expression
-__global__ void __launch_bounds__(AG_THREADS)
-group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap) {
+// program 0 of ps = group key expression.  SIMPLE: the key is a bare NULL-free column and no
+// argument column has a validity bitmap (the BASELINE shape): keys and values are streamed with
+// plain coalesced loads, no interpreter.
+template <bool SIMPLE>
+__global__ void __launch_bounds__(AG_THREADS, SIMPLE ? 4 : 3)
+group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap, int key_slot) {
     constexpr int TILE = AG_K * AG_THREADS;
     const int64_t num_tiles = (ap.n_rows + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -63,12 +67,20 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
         for (int j = 0; j < AG_K; j++)
             if (e0 + (int64_t)j * AG_THREADS < ap.n_rows) inrange |= 1u << j;
         RowRegs<AG_K> key;
-        run_program<AG_K>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
+        if (SIMPLE) {
+            const uint64_t *kc = (const uint64_t *)ps.cols[key_slot].values;
+#pragma unroll
+            for (int j = 0; j < AG_K; j++) key.v[j] = ((inrange >> j) & 1u) ? ld_stream_u64(kc + e0 + (int64_t)j * AG_THREADS) : 0ull;
+            key.valid = inrange;
+        } else {
+            run_program<AG_K>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
+        }
         unsigned long long *rec[AG_K];
-        find_slots<AG_K>(ap, key.v, key.valid, rec); // NULL keys are dropped (valid bit clear)
+        Sector0 s0[AG_K];
+        find_slots<AG_K>(ap, key.v, key.valid, rec, s0); // NULL keys are dropped (valid bit clear)
 #pragma unroll
         for (int j = 0; j < AG_K; j++)
-            if (rec[j]) update_states(ap, rec[j], RowSource{ps, e0 + (int64_t)j * AG_THREADS});
+            if (rec[j]) update_states(ap, rec[j], s0[j], RowSource<SIMPLE>{ps, e0 + (int64_t)j * AG_THREADS});
     }
 }
 
@@ -230,10 +242,16 @@ int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const 
         src2[i] = ap->st_src[order[i]];
         inv[order[i]] = i;
     }
+    // word offsets: MIN/MAX states first, so that they share sector 0 (the first 32 bytes) with the key
+    int next_off = 1;
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < ap->n_states; i++) {
+            const bool ext = kind2[i] == ST_MIN || kind2[i] == ST_MAX;
+            if (ext == (pass == 0)) ap->st_off[i] = next_off++;
+        }
     for (int i = 0; i < ap->n_states; i++) {
         ap->st_kind[i] = kind2[i];
         ap->st_src[i] = src2[i];
-        ap->st_off[i] = 1 + i;
     }
     for (int a = 0; a < n_aggs; a++) {
         ap->agg_state[a] = inv[ap->agg_state[a]];
@@ -362,6 +380,15 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             ctx->launches++;
         }
     } else {
+        // fast path: bare NULL-free key column, NULL-free arguments
+        int key_slot = 0;
+        bool simple = ps.prog_begin[1] - ps.prog_begin[0] == 1 && ps.ops[ps.prog_begin[0]].code == UOP_LOAD &&
+                      ps.ops[ps.prog_begin[0]].src == SRC_COL;
+        if (simple) {
+            key_slot = ps.ops[ps.prog_begin[0]].slot;
+            for (int q = 0; q < ps.n_cols; q++)
+                if (ps.cols[q].validity) simple = false;
+        }
         // --- size the table from a sampled cardinality estimate, grow on overflow
         uint64_t capacity = 1024;
         if (n > 0) {
@@ -397,7 +424,8 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 const int64_t tiles = (n + AG_K * AG_THREADS - 1) / (AG_K * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                group_aggregate_kernel<<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap);
+                if (simple) group_aggregate_kernel<true><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
+                else group_aggregate_kernel<false><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, 0);
                 ctx->launches++;
             }
             rc = read_scratch(ctx, 2);

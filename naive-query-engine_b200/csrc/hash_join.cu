@@ -45,7 +45,7 @@ struct Slot {
 
 struct JoinTable {
     unsigned long long *words; // slot s starts at words + (s << shift)
-    uint64_t mask;
+    uint64_t cap;     // number of slots (any size: slots are chosen by multiply-high)
     int32_t shift;    // 1: thin (2 words), 2: fat (4 words)
     int32_t has_dups;
     int32_t key_col;  // build-side key column
@@ -62,13 +62,25 @@ struct ColSrc {
 };
 
 __device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uint64_t s) { return jt.words + (s << jt.shift); }
+// Random accesses.  Measured on B200 (profiles/join_groupby_r01.md): a random 16-byte read costs
+// ~128 bytes of DRAM traffic whatever the load flavour (ld.global.nc, .cg, .L1::no_allocate) and
+// whatever cudaLimitMaxL2FetchGranularity says, so the plain read-only path is kept.
+__device__ __forceinline__ ulonglong2 ld_cg_v2(const unsigned long long *p) { return __ldg((const ulonglong2 *)p); }
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldg(p); }
+__device__ __forceinline__ ulonglong4 ld_v4(const unsigned long long *p) {
+    ulonglong4 v;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.x), "=l"(v.y), "=l"(v.z), "=l"(v.w) : "l"(p));
+    return v;
+}
+// slot of a key: multiply-high range reduction, so the capacity need not be a power of two
+__device__ __forceinline__ uint64_t join_slot_of(const JoinTable &jt, unsigned long long key) {
+    return __umul64hi(nqe_mix64(key), jt.cap);
+}
 __device__ __forceinline__ Slot ld_slot(const JoinTable &jt, uint64_t s) {
-    const ulonglong2 v = __ldg((const ulonglong2 *)slot_ptr(jt, s));
+    const ulonglong2 v = ld_cg_v2(slot_ptr(jt, s));
     return Slot{v.x, v.y};
 }
-__device__ __forceinline__ ulonglong2 ld_payload(const JoinTable &jt, uint64_t s) {
-    return __ldg((const ulonglong2 *)(slot_ptr(jt, s) + 2));
-}
+__device__ __forceinline__ ulonglong2 ld_payload(const JoinTable &jt, uint64_t s) { return ld_cg_v2(slot_ptr(jt, s) + 2); }
 
 __global__ void join_clear_kernel(JoinTable jt, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,8 +95,8 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = keys[i];
-    uint64_t s = nqe_mix64(key) & jt.mask;
-    for (uint64_t probe = 0; probe <= jt.mask; probe++) {
+    uint64_t s = join_slot_of(jt, key);
+    for (uint64_t probe = 0; probe < jt.cap; probe++) {
         unsigned long long *p = slot_ptr(jt, s);
         const unsigned long long old = atomicCAS(p + 1, EMPTY_ROW, (unsigned long long)i);
         if (old == EMPTY_ROW) {
@@ -95,7 +107,7 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
             }
             return;
         }
-        s = (s + 1) & jt.mask;
+        s = s + 1 == jt.cap ? 0 : s + 1;
     }
     atomicOr(status, DEV_ERR_TABLE_FULL);
 }
@@ -105,28 +117,38 @@ __global__ void join_dups_kernel(JoinTable jt, const unsigned long long *__restr
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = keys[i];
-    uint64_t s = nqe_mix64(key) & jt.mask;
+    uint64_t s = join_slot_of(jt, key);
     int matches = 0;
     while (true) {
         const Slot sl = ld_slot(jt, s);
         if (sl.row == EMPTY_ROW) break;
         if (sl.key == key) matches++;
-        s = (s + 1) & jt.mask;
+        s = s + 1 == jt.cap ? 0 : s + 1;
     }
     if (matches > 1) *flag = 1u;
 }
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
 // K rows is issued together (K independent loads in flight; at load factor <= 0.6 most rows
-// resolve there), collisions are then walked one row at a time.
-template <int K>
+// resolve there), collisions are then walked one row at a time.  FAT: the whole 32-byte slot
+// (key, row, two payload words) comes with ONE 256-bit load -- one random sector per probe row.
+template <int K, bool FAT>
 __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
-                                            unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
+                                            unsigned long long (&brow)[K], uint64_t (&slot)[K], ulonglong2 (&pay)[K]) {
     Slot first[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        slot[j] = nqe_mix64(key[j]) & jt.mask;
-        if ((want >> j) & 1u) first[j] = ld_slot(jt, slot[j]);
+        slot[j] = join_slot_of(jt, key[j]);
+        pay[j] = make_ulonglong2(0, 0);
+        if ((want >> j) & 1u) {
+            if (FAT) {
+                const ulonglong4 v = ld_v4(slot_ptr(jt, slot[j]));
+                first[j] = Slot{v.x, v.y};
+                pay[j] = make_ulonglong2(v.z, v.w);
+            } else {
+                first[j] = ld_slot(jt, slot[j]);
+            }
+        }
     }
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -135,8 +157,14 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
         Slot sl = first[j];
         while (sl.row != EMPTY_ROW) {
             if (sl.key == key[j]) { brow[j] = sl.row; break; }
-            slot[j] = (slot[j] + 1) & jt.mask;
-            sl = ld_slot(jt, slot[j]);
+            slot[j] = slot[j] + 1 == jt.cap ? 0 : slot[j] + 1;
+            if (FAT) {
+                const ulonglong4 v = ld_v4(slot_ptr(jt, slot[j]));
+                sl = Slot{v.x, v.y};
+                pay[j] = make_ulonglong2(v.z, v.w);
+            } else {
+                sl = ld_slot(jt, slot[j]);
+            }
         }
     }
 }
@@ -144,7 +172,7 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
 // number of matches of `key`; the smallest matching build row and its slot
 __device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigned long long key, unsigned long long *first,
                                                     uint64_t *first_slot) {
-    uint64_t s = nqe_mix64(key) & jt.mask;
+    uint64_t s = join_slot_of(jt, key);
     unsigned int c = 0;
     unsigned long long best = EMPTY_ROW;
     while (true) {
@@ -154,7 +182,7 @@ __device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigne
             c++;
             if (sl.row < best) { best = sl.row; *first_slot = s; }
         }
-        s = (s + 1) & jt.mask;
+        s = s + 1 == jt.cap ? 0 : s + 1;
     }
     *first = best;
     return c;
@@ -163,13 +191,13 @@ __device__ __forceinline__ unsigned int probe_count(const JoinTable &jt, unsigne
 // smallest matching build row strictly greater than `after` (and its slot)
 __device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, unsigned long long key, unsigned long long after,
                                                          uint64_t *slot_out) {
-    uint64_t s = nqe_mix64(key) & jt.mask;
+    uint64_t s = join_slot_of(jt, key);
     unsigned long long best = EMPTY_ROW;
     while (true) {
         const Slot sl = ld_slot(jt, s);
         if (sl.row == EMPTY_ROW) break;
         if (sl.key == key && sl.row > after && sl.row < best) { best = sl.row; *slot_out = s; }
-        s = (s + 1) & jt.mask;
+        s = s + 1 == jt.cap ? 0 : s + 1;
     }
     return best;
 }
@@ -201,7 +229,7 @@ __device__ __forceinline__ void emit_value(const ColSrc &c, int64_t src_row, voi
         const uint32_t w = __ldg((const uint32_t *)c.values + (src_row >> 5));
         ((uint8_t *)out_values)[pos] = valid ? (uint8_t)((w >> (src_row & 31)) & 1u) : 0;
     } else {
-        ((unsigned long long *)out_values)[pos] = valid ? __ldg((const unsigned long long *)c.values + src_row) : 0ull;
+        ((unsigned long long *)out_values)[pos] = valid ? ld_cg_u64((const unsigned long long *)c.values + src_row) : 0ull;
     }
     if (out_valid) out_valid[pos] = (uint8_t)valid;
 }
@@ -238,8 +266,9 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
             if (e < pp.n_probe) inrange |= 1u << j;
         }
+        ulonglong2 pay[K];
         if (!pp.jt.has_dups) {
-            probe_first<K>(pp.jt, key, inrange, first, slot);
+            probe_first<K, FAT>(pp.jt, key, inrange, first, slot, pay);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
         } else {
@@ -250,9 +279,8 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
                 cnt[j] = ((inrange >> j) & 1u) ? probe_count(pp.jt, key[j], &first[j], &slot[j]) : 0u;
             }
         }
-        // fat slots: the payload of the first match sits next to the key that was just read
-        ulonglong2 pay[K];
-        if (FAT) {
+        // fat slots, duplicate keys: the payload of the first match sits next to its key
+        if (FAT && pp.jt.has_dups) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 pay[j] = make_ulonglong2(0, 0);
@@ -385,7 +413,7 @@ struct JoinRowSource {
         }
         const int64_t r = jp.val_left[id] ? brow : prow;
         if (!col_valid(c, r)) return false;
-        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : __ldg((const unsigned long long *)c.values + r);
+        *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : ld_cg_u64((const unsigned long long *)c.values + r);
         return true;
     }
 };
@@ -399,17 +427,18 @@ __device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggP
     else {
         const int64_t grow = jp.group_left ? brow : prow;
         if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
-        gkey = __ldg((const unsigned long long *)jp.group.values + grow);
+        gkey = ld_cg_u64((const unsigned long long *)jp.group.values + grow);
     }
-    unsigned long long *r = find_slot(ap, gkey);
-    if (r) update_states(ap, r, JoinRowSource{jp, brow, prow, pay});
+    Sector0 s0;
+    unsigned long long *r = find_slot(ap, gkey, &s0);
+    if (r) update_states(ap, r, s0, JoinRowSource{jp, brow, prow, pay});
 }
 
+template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_constant__ AggParams ap) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
     const int64_t num_tiles = (jp.n_probe + TILE - 1) / TILE;
-    const bool fat = jp.jt.shift == 2;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * TILE + threadIdx.x;
         unsigned long long key[K], brow[K];
@@ -421,42 +450,41 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
             key[j] = e < jp.n_probe ? ld_stream_u64(jp.probe_keys + e) : 0ull;
             if (e < jp.n_probe) inrange |= 1u << j;
         }
-        probe_first<K>(jp.jt, key, inrange, brow, slot);
-        // group keys of the (first) matches: K independent loads
         ulonglong2 pay[K];
+        probe_first<K, FAT>(jp.jt, key, inrange, brow, slot, pay);
+        // group keys of the (first) matches: K independent loads
         uint64_t gkey[K];
         uint32_t have = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             gkey[j] = 0;
-            pay[j] = make_ulonglong2(0, 0);
             if (brow[j] == EMPTY_ROW) continue;
-            if (fat) pay[j] = ld_payload(jp.jt, slot[j]);
             if (jp.group_left && jp.group_pay >= 0) {
                 gkey[j] = jp.group_pay ? pay[j].y : pay[j].x;
             } else {
                 const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
                 if (!col_valid(jp.group, grow)) continue; // NULL group keys are dropped
-                gkey[j] = __ldg((const unsigned long long *)jp.group.values + grow);
+                gkey[j] = ld_cg_u64((const unsigned long long *)jp.group.values + grow);
             }
             have |= 1u << j;
         }
         unsigned long long *rec[K];
-        find_slots<K>(ap, gkey, have, rec);
+        Sector0 s0[K];
+        find_slots<K>(ap, gkey, have, rec, s0);
 #pragma unroll
         for (int j = 0; j < K; j++)
-            if (rec[j]) update_states(ap, rec[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS, pay[j]});
+            if (rec[j]) update_states(ap, rec[j], s0[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS, pay[j]});
         if (jp.jt.has_dups) {
             // duplicate build keys: walk on from the first match for the remaining ones
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 if (brow[j] == EMPTY_ROW) continue;
-                uint64_t s = (slot[j] + 1) & jp.jt.mask;
+                uint64_t s = slot[j] + 1 == jp.jt.cap ? 0 : slot[j] + 1;
                 while (true) {
                     const Slot sl = ld_slot(jp.jt, s);
                     if (sl.row == EMPTY_ROW) break;
                     if (sl.key == key[j]) join_agg_one(jp, ap, (int64_t)sl.row, e0 + (int64_t)j * HJ_THREADS, s);
-                    s = (s + 1) & jp.jt.mask;
+                    s = s + 1 == jp.jt.cap ? 0 : s + 1;
                 }
             }
         }
@@ -485,7 +513,7 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
     static int allow_fat = -1;
     if (allow_fat < 0) {
         const char *e = getenv("NQE_JOIN_FAT");
-        allow_fat = e ? atoi(e) : 0; // measured slower on B200: the 2x larger table loses more L2 hits than the gather costs
+        allow_fat = e ? atoi(e) : 1;
     }
     bool fat = allow_fat && left->cols.size() <= 3;
     int n_pay = 0;
@@ -499,11 +527,11 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
     }
     jt->n_pay = fat ? n_pay : 0;
     jt->shift = fat ? 2 : 1;
-    const uint64_t cap = nqe_next_pow2((uint64_t)((double)nl / 0.6) + 16);
+    const uint64_t cap = (uint64_t)((double)nl / 0.5) + 16; // load factor 0.5
     void *slots = nullptr;
     NQE_TRY(nqe_dev_alloc(ctx, &slots, (cap << jt->shift) * 8));
     jt->words = (unsigned long long *)slots;
-    jt->mask = cap - 1;
+    jt->cap = cap;
     uint32_t *status = (uint32_t *)(ctx->d_scratch + 1);
     uint32_t *dupflag = (uint32_t *)(ctx->d_scratch + 3);
     join_clear_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(*jt, cap);
@@ -725,7 +753,8 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             const int64_t tiles = (jp.n_probe + HJ_K * HJ_THREADS - 1) / (HJ_K * HJ_THREADS);
             int grid = ctx->sm_count * 8;
             if (grid > tiles) grid = (int)tiles;
-            join_aggregate_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
+            if (jp.jt.shift == 2) join_aggregate_kernel<true><<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
+            else join_aggregate_kernel<false><<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
             ctx->launches++;
         }
         cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);

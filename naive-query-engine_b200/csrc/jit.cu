@@ -484,7 +484,7 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         if (D < 1 || D > 8) D = 4;
     }
     // TMA-ring variant: knobs NQE_JIT_IMPL=tma|ca, NQE_JIT_TMA_K / _SP / _SW / _LAG / _WALKERS / _LBW / _OCC
-    static int impl = -1, TK = 4, SP = 4, SW = 4, LAG = 8, WALKERS = 2, lbw = 4, prof = 0;
+    static int impl = -1, TK = 8, SP = 2, SW = 2, LAG = 4, WALKERS = 2, lbw = 1, prof = 0;
     if (impl < 0) {
         auto knob = [](const char *name, int dflt, int lo, int hi) {
             const char *e = getenv(name);
@@ -493,41 +493,47 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         };
         const char *e = getenv("NQE_JIT_IMPL");
         impl = (e && !strcmp(e, "ca")) ? 0 : 1;
-        TK = knob("NQE_JIT_TMA_K", 4, 1, 16);
-        if (TK & (TK - 1)) TK = 4;
-        SP = knob("NQE_JIT_TMA_SP", 4, 2, 16);
-        SW = knob("NQE_JIT_TMA_SW", 4, 2, 16);
-        LAG = knob("NQE_JIT_TMA_LAG", 8, 0, 48);
+        // defaults = best of the B200 sweeps in profiles/filter_project_sweeps_r01.md
+        TK = knob("NQE_JIT_TMA_K", 8, 1, 16);
+        if (TK & (TK - 1)) TK = 8;
+        SP = knob("NQE_JIT_TMA_SP", 2, 2, 16);
+        SW = knob("NQE_JIT_TMA_SW", 2, 2, 16);
+        LAG = knob("NQE_JIT_TMA_LAG", 4, 0, 48);
         WALKERS = knob("NQE_JIT_TMA_WALKERS", 2, 1, 4);
-        lbw = knob("NQE_JIT_TMA_LBW", 4, 1, 16); // look-back window: 32*lbw tiles per L2 round trip
+        lbw = knob("NQE_JIT_TMA_LBW", 1, 1, 16); // look-back window: 32*lbw tiles per L2 round trip
         prof = getenv("NQE_JIT_PROF") ? 1 : 0;
     }
     bool tma = allow_tma && impl == 1 && predicate && n_pred_cols > 0;
     const size_t n_slots = g.col_of_slot.size();
     uint32_t pstage = 0, ptx = 0, wstage = 0, wtx = 0;
     std::vector<uint32_t> poff(n_slots), woff(n_slots), col_bytes(n_slots);
-    int sp = SP, sw = SW;
+    int sp = SP, sw = SW, tk = TK;
     if (tma) {
-        const uint32_t tile = (uint32_t)TK * 256;
         bool any_proj = false;
         for (size_t s = 0; s < n_slots; s++) {
-            const DevColumn &c = in->cols[g.col_of_slot[s]];
-            if ((uintptr_t)c.values & 15) tma = false;
-            col_bytes[s] = c.dtype == NQE_BOOL ? tile / 8 : tile * 8;
-            const uint32_t padded = (col_bytes[s] + 127) & ~127u;
-            if (s < n_pred_cols) { poff[s] = pstage; pstage += padded; ptx += col_bytes[s]; }
-            if (g.in_proj[s]) { woff[s] = wstage; wstage += padded; wtx += col_bytes[s]; any_proj = true; }
+            if ((uintptr_t)in->cols[g.col_of_slot[s]].values & 15) tma = false;
+            if (g.in_proj[s]) any_proj = true;
         }
         if (!any_proj) tma = false; // projections of literals only: nothing to stage
-        while (sw > 2 && (size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) sw--;
-        while (sp > 2 && (size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) sp--;
+        // rows per thread: the largest K <= the knob whose two rings leave room for two CTAs per SM
+        for (;; tk >>= 1) {
+            const uint32_t tile = (uint32_t)tk * 256;
+            pstage = ptx = wstage = wtx = 0;
+            for (size_t s = 0; s < n_slots; s++) {
+                col_bytes[s] = in->cols[g.col_of_slot[s]].dtype == NQE_BOOL ? tile / 8 : tile * 8;
+                const uint32_t padded = (col_bytes[s] + 127) & ~127u;
+                if (s < n_pred_cols) { poff[s] = pstage; pstage += padded; ptx += col_bytes[s]; }
+                if (g.in_proj[s]) { woff[s] = wstage; wstage += padded; wtx += col_bytes[s]; }
+            }
+            if ((size_t)sp * pstage + (size_t)sw * wstage <= 104 * 1024 || tk == 1) break;
+        }
         if ((size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) tma = false;
     }
     const int nr = LAG + sw + WALKERS + 2; // ring slots of per-tile state: covers claim .. write of a tile
     src << "#define NQE_PROF " << (tma ? prof : 0) << "\n";
     if (tma) {
-        K = TK;
-        src << "#define K " << TK << "\n#define SP " << sp << "\n#define SW " << sw << "\n#define LAG " << LAG << "\n#define NR " << nr
+        K = tk;
+        src << "#define K " << tk << "\n#define SP " << sp << "\n#define SW " << sw << "\n#define LAG " << LAG << "\n#define NR " << nr
             << "\n#define WALKERS " << WALKERS << "\n#define HAS_PRED 1\n#define NQE_LB_WIDE " << lbw << "\n#define NQE_LB_BACKOFF 40\n"
             << "#define PSTAGE_BYTES " << pstage << "u\n#define PRED_TX_BYTES " << ptx << "u\n#define WSTAGE_BYTES " << wstage
             << "u\n#define WRITE_TX_BYTES " << wtx << "u\n#define THREADS 256\n";

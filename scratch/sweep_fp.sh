@@ -1,16 +1,7 @@
 #!/bin/bash
-run() { timeout 60 env "$@" REPS=8 python scratch/exp_fp.py 2>&1 | tail -3; }
-run NQE_JIT_PROF=1
-run NQE_JIT_PROF=1 NQE_JIT_TMA_K=8 NQE_JIT_TMA_SP=3 NQE_JIT_TMA_SW=4
+run() { timeout 60 env "$@" REPS=10 python scratch/exp_fp.py 2>&1 | tail -1; }
 run
-run NQE_JIT_TMA_LAG=4
-run NQE_JIT_TMA_LAG=16
-run NQE_JIT_TMA_LAG=32
-run NQE_JIT_TMA_SP=6 NQE_JIT_TMA_SW=3
-run NQE_JIT_TMA_SP=3 NQE_JIT_TMA_SW=3
-run NQE_JIT_TMA_SP=2 NQE_JIT_TMA_SW=2 NQE_JIT_TMA_LAG=16
-run NQE_JIT_TMA_K=8 NQE_JIT_TMA_SP=3 NQE_JIT_TMA_SW=3
-run NQE_JIT_TMA_K=8 NQE_JIT_TMA_SP=4 NQE_JIT_TMA_SW=4 NQE_JIT_TMA_LAG=6
-run NQE_JIT_TMA_K=2 NQE_JIT_TMA_SP=4 NQE_JIT_TMA_SW=4 NQE_JIT_TMA_LAG=16
-run NQE_JIT_TMA_WALKERS=1
-run NQE_JIT_TMA_WALKERS=4
+run NQE_JIT_TMA_LAG=2
+run NQE_JIT_TMA_LAG=3
+run NQE_JIT_TMA_LAG=5
+run NQE_JIT_TMA_LAG=3 NQE_JIT_TMA_WALKERS=1
