@@ -202,8 +202,227 @@ __device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, un
     return best;
 }
 
+// ---------------------------------------------------------------------------
+// Partitioned probe (unique build keys, table larger than the L2).
+//
+// A probe row costs one random table access; for a table that does not fit in the 126 MB L2
+// that is ~128 bytes of DRAM traffic per row (measured) and the probe runs at DRAM
+// random-access speed.  Here the probe KEYS are first split -- stably -- into 2^log2p
+// partitions by the top bits of their hash, which are the top bits of their table slot, so
+// partition p only touches slot range p of the (unchanged) table and that range stays in L2
+// while its keys are probed.  The per-row results land in partition order in sequential
+// streams; the emit pass walks the probe side in its ORIGINAL order, recomputes every row's
+// position in those streams from the per-tile partition offsets (the inverse of the stable
+// split, again sequential per partition), and writes the joined rows probe-row-major exactly
+// like the direct path.  Everything except the L2-resident table is streamed.
+// ---------------------------------------------------------------------------
+constexpr int PJ_MAX_PARTS = 32; // one lane per partition in the tile histograms
+
+struct PartJoin {
+    const unsigned long long *keys; // probe keys, original order
+    int64_t n;
+    int32_t log2p;
+    int32_t num_tiles;              // tiles of HJ_K * HJ_THREADS rows
+    unsigned int *tile_cnt;         // [num_tiles][P]: rows of the tile per partition
+    unsigned int *tile_off;         // [num_tiles][P]: rows of that partition in earlier tiles
+    unsigned long long *part_base;  // [P + 1]: first position of the partition in the partitioned order
+    unsigned long long *pkeys;      // keys in partitioned order
+    unsigned long long *res0;       // per position: thin = build row (EMPTY_ROW: no match), fat = payload word 0
+    unsigned long long *res1;       // fat, two payload columns: payload word 1
+    unsigned int *mbits;            // fat: match bit per position
+};
+
+__device__ __forceinline__ int pj_part(unsigned long long key, int log2p) {
+    return log2p ? (int)(nqe_mix64(key) >> (64 - log2p)) : 0;
+}
+// lanes of the warp that are live and in the same partition as this lane
+__device__ __forceinline__ unsigned pj_same_mask(int pid, bool live, int log2p) {
+    unsigned m = __ballot_sync(0xffffffffu, live);
+    for (int b = 0; b < log2p; b++) {
+        const unsigned bb = __ballot_sync(0xffffffffu, (pid >> b) & 1);
+        m &= ((pid >> b) & 1) ? bb : ~bb;
+    }
+    return m;
+}
+
+// Per-(j, warp) partition histograms of one tile in shared memory (row order inside a tile is
+// j major, warp minor, lane).  Every thread of the CTA calls this; s_c is zeroed here.
+template <int K>
+__device__ __forceinline__ void pj_tile_hist(const unsigned long long (&key)[K], uint32_t inrange, int log2p,
+                                             unsigned short (*s_c)[PJ_MAX_PARTS], int (&pid)[K], unsigned (&rank)[K]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < K * HJ_WARPS * PJ_MAX_PARTS; i += HJ_THREADS) (&s_c[0][0])[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const bool live = (inrange >> j) & 1u;
+        pid[j] = pj_part(key[j], log2p);
+        const unsigned m = pj_same_mask(pid[j], live, log2p);
+        rank[j] = __popc(m & ((1u << lane) - 1u));
+        if (live && rank[j] == 0) s_c[j * HJ_WARPS + warp][pid[j]] = (unsigned short)__popc(m);
+    }
+    __syncthreads();
+}
+
+// pass 1: per-tile partition counts (+ partition totals)
+__global__ void __launch_bounds__(HJ_THREADS) pj_count_kernel(PartJoin pj, unsigned long long *totals) {
+    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned short s_c[K * HJ_WARPS][PJ_MAX_PARTS];
+    const int tid = threadIdx.x, P = 1 << pj.log2p;
+    unsigned long long mine = 0;
+    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K];
+        uint32_t inrange = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pj.n ? ld_stream_u64(pj.keys + e) : 0ull;
+            if (e < pj.n) inrange |= 1u << j;
+        }
+        int pid[K];
+        unsigned rank[K];
+        pj_tile_hist<K>(key, inrange, pj.log2p, s_c, pid, rank);
+        if (tid < P) {
+            unsigned c = 0;
+#pragma unroll
+            for (int i = 0; i < K * HJ_WARPS; i++) c += s_c[i][tid];
+            pj.tile_cnt[(size_t)tile * P + tid] = c;
+            mine += c;
+        }
+        __syncthreads();
+    }
+    if (tid < P && mine) atomicAdd(totals + tid, mine);
+}
+
+// pass 2: one CTA per partition: exclusive scan of its per-tile counts; partition bases
+__global__ void __launch_bounds__(1024) pj_scan_kernel(PartJoin pj, const unsigned long long *totals) {
+    __shared__ unsigned int s_w[32];
+    __shared__ unsigned int s_carry;
+    const int p = blockIdx.x, P = 1 << pj.log2p, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int q = 0; q < p; q++) b += totals[q];
+        pj.part_base[p] = b;
+        if (p == P - 1) pj.part_base[P] = b + totals[p];
+        s_carry = 0;
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < pj.num_tiles; t0 += 1024) {
+        const int t = t0 + tid;
+        const unsigned v = t < pj.num_tiles ? pj.tile_cnt[(size_t)t * P + p] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned w = s_w[lane];
+            unsigned wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned x = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += x;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned carry = s_carry;
+        if (t < pj.num_tiles) pj.tile_off[(size_t)t * P + p] = carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_w[warp] + incl;
+        __syncthreads();
+    }
+}
+
+// position of this thread's K rows in the partitioned order (all threads of the CTA call this)
+template <int K>
+__device__ __forceinline__ void pj_positions(const PartJoin &pj, int tile, const unsigned long long (&key)[K], uint32_t inrange,
+                                             unsigned short (*s_c)[PJ_MAX_PARTS], unsigned long long (&ppos)[K]) {
+    const int tid = threadIdx.x, warp = tid >> 5, P = 1 << pj.log2p;
+    int pid[K];
+    unsigned rank[K];
+    pj_tile_hist<K>(key, inrange, pj.log2p, s_c, pid, rank);
+    if (tid < P) { // exclusive prefix over the (j, warp) pairs, per partition
+        unsigned run = 0;
+#pragma unroll
+        for (int i = 0; i < K * HJ_WARPS; i++) {
+            const unsigned c = s_c[i][tid];
+            s_c[i][tid] = (unsigned short)run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; j++)
+        ppos[j] = pj.part_base[pid[j]] + pj.tile_off[(size_t)tile * P + pid[j]] + s_c[j * HJ_WARPS + warp][pid[j]] + rank[j];
+    __syncthreads(); // s_c is reused by the next tile
+}
+
+// pass 3: stable split of the probe keys
+__global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
+    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned short s_c[K * HJ_WARPS][PJ_MAX_PARTS];
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K], ppos[K];
+        uint32_t inrange = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pj.n ? ld_stream_u64(pj.keys + e) : 0ull;
+            if (e < pj.n) inrange |= 1u << j;
+        }
+        pj_positions<K>(pj, tile, key, inrange, s_c, ppos);
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if ((inrange >> j) & 1u) pj.pkeys[ppos[j]] = key[j];
+    }
+}
+
+// pass 4: probe in partitioned order (partition after partition, so one slot range of the table is hot in L2)
+template <bool FAT>
+__global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinTable jt) {
+    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K], brow[K];
+        uint64_t slot[K];
+        ulonglong2 pay[K];
+        uint32_t inrange = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pj.n ? ld_stream_u64(pj.pkeys + e) : 0ull;
+            if (e < pj.n) inrange |= 1u << j;
+        }
+        probe_first<K, FAT>(jt, key, inrange, brow, slot, pay);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            const bool live = (inrange >> j) & 1u;
+            if (FAT) {
+                const unsigned m = __ballot_sync(0xffffffffu, live && brow[j] != EMPTY_ROW);
+                if (live) {
+                    pj.res0[e] = pay[j].x;
+                    if (pj.res1) pj.res1[e] = pay[j].y;
+                    if ((tid & 31) == 0) pj.mbits[e >> 5] = m;
+                }
+            } else if (live) {
+                pj.res0[e] = brow[j];
+            }
+        }
+    }
+}
+
 struct ProbeParams {
     JoinTable jt;
+    PartJoin pj;            // pj.pkeys != nullptr: results come from the partitioned probe
     const unsigned long long *probe_keys;
     int64_t n_probe;
     int32_t n_left, n_right;
@@ -242,10 +461,11 @@ __device__ __forceinline__ void emit_row(const ProbeParams &pp, int64_t brow, in
     }
 }
 
-template <bool FAT>
+template <bool FAT, bool PART>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned short s_c[PART ? K * HJ_WARPS : 1][PJ_MAX_PARTS];
     __shared__ unsigned long long s_cnt[K * HJ_WARPS];
     __shared__ unsigned long long s_tile_excl;
     __shared__ int s_tile;
@@ -267,7 +487,28 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             if (e < pp.n_probe) inrange |= 1u << j;
         }
         ulonglong2 pay[K];
-        if (!pp.jt.has_dups) {
+        if (PART) {
+            // results of the partitioned probe, fetched from their position in the partitioned order
+            unsigned long long ppos[K];
+            pj_positions<K>(pp.pj, tile, key, inrange, s_c, ppos);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                slot[j] = 0;
+                first[j] = EMPTY_ROW;
+                cnt[j] = 0;
+                pay[j] = make_ulonglong2(0, 0);
+                if (!((inrange >> j) & 1u)) continue;
+                if (FAT) {
+                    cnt[j] = (__ldg(pp.pj.mbits + (ppos[j] >> 5)) >> (ppos[j] & 31)) & 1u;
+                    pay[j].x = ld_stream_u64(pp.pj.res0 + ppos[j]);
+                    if (pp.pj.res1) pay[j].y = ld_stream_u64(pp.pj.res1 + ppos[j]);
+                    first[j] = cnt[j] ? 0ull : EMPTY_ROW;
+                } else {
+                    first[j] = ld_stream_u64(pp.pj.res0 + ppos[j]);
+                    cnt[j] = first[j] != EMPTY_ROW;
+                }
+            }
+        } else if (!pp.jt.has_dups) {
             probe_first<K, FAT>(pp.jt, key, inrange, first, slot, pay);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
@@ -513,7 +754,7 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
     static int allow_fat = -1;
     if (allow_fat < 0) {
         const char *e = getenv("NQE_JOIN_FAT");
-        allow_fat = e ? atoi(e) : 1;
+        allow_fat = e ? atoi(e) : 0; // measured (profiles/join_groupby_r01.md): thin 16-byte slots + gather beat fat slots, whose table is twice as large
     }
     bool fat = allow_fat && left->cols.size() <= 3;
     int n_pay = 0;
@@ -592,6 +833,61 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     pp.ticket = (unsigned int *)(ctx->d_scratch + 2);
     const bool fat = pp.jt.shift == 2 && pp.key_from_probe;
 
+    // ---- partitioned probe: unique build keys and a table that does not fit in the L2
+    std::vector<void *> pj_bufs;
+    bool part = false;
+    if (rc == NQE_OK) {
+        static int allow_part = -1;
+        static size_t l2_budget = 0;
+        if (allow_part < 0) {
+            const char *e = getenv("NQE_JOIN_PART");
+            allow_part = e ? atoi(e) : 1;
+            e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
+            l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
+        }
+        const size_t table_bytes = (size_t)(pp.jt.cap << pp.jt.shift) * 8;
+        const bool thin_ok = pp.jt.shift == 1, fat_ok = fat;
+        if (allow_part && !pp.jt.has_dups && (thin_ok || fat_ok) && pp.n_probe >= (1 << 22) && table_bytes > 2 * l2_budget &&
+            pp.n_probe < (int64_t)1 << 32) {
+            int log2p = 1;
+            while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
+            PartJoin &pj = pp.pj;
+            pj.keys = pp.probe_keys;
+            pj.n = pp.n_probe;
+            pj.log2p = log2p;
+            pj.num_tiles = pp.num_tiles;
+            const size_t P = (size_t)1 << log2p, nt = (size_t)pp.num_tiles;
+            auto alloc = [&](void **p, size_t bytes) {
+                if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
+                if (rc == NQE_OK) pj_bufs.push_back(*p);
+            };
+            void *totals = nullptr;
+            alloc((void **)&pj.tile_cnt, nt * P * 4);
+            alloc((void **)&pj.tile_off, nt * P * 4);
+            alloc((void **)&pj.part_base, (P + 1) * 8);
+            alloc(&totals, P * 8);
+            alloc((void **)&pj.pkeys, (size_t)pp.n_probe * 8);
+            alloc((void **)&pj.res0, (size_t)pp.n_probe * 8);
+            if (fat && pp.jt.n_pay > 1) alloc((void **)&pj.res1, (size_t)pp.n_probe * 8);
+            if (fat) alloc((void **)&pj.mbits, ((size_t)pp.n_probe / 32 + 2) * 4);
+            if (rc == NQE_OK) {
+                cudaMemsetAsync(totals, 0, P * 8, ctx->stream);
+                int grid = ctx->sm_count * 8;
+                if (grid > pp.num_tiles) grid = pp.num_tiles;
+                pj_count_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, (unsigned long long *)totals);
+                pj_scan_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(pj, (const unsigned long long *)totals);
+                pj_scatter_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj);
+                if (fat) pj_probe_kernel<true><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                else pj_probe_kernel<false><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                ctx->launches += 4;
+                if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partitioned probe launch failed");
+                part = true;
+            } else {
+                pj.pkeys = nullptr;
+            }
+        }
+    }
+
     nqe_table *t = nullptr;
     int64_t cap = pp.n_probe > 0 ? pp.n_probe : 1;
     int64_t out_rows = 0;
@@ -622,7 +918,8 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
             if (pp.num_tiles > 0) {
-                auto kern = fat ? join_probe_kernel<true> : join_probe_kernel<false>;
+                auto kern = part ? (fat ? join_probe_kernel<true, true> : join_probe_kernel<false, true>)
+                                 : (fat ? join_probe_kernel<true, false> : join_probe_kernel<false, false>);
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);
@@ -665,6 +962,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     for (auto p : valid_bytes) nqe_dev_free(ctx, p);
     nqe_dev_free(ctx, lb);
     nqe_dev_free(ctx, pp.jt.words);
+    for (void *p : pj_bufs) nqe_dev_free(ctx, p);
     if (rc != NQE_OK) {
         if (t) nqe_table_free(t);
         return rc;

@@ -302,6 +302,37 @@ def test_hash_join_random(nl, nr, keyspace):
     same(got, want)  # identical order: probe-row-major, build rows ascending
 
 
+@pytest.mark.parametrize("n_pay", [1, 2, 3])
+def test_hash_join_partitioned_probe_large(n_pay):
+    """Build table larger than the L2 budget -> the partitioned (radix) probe path; result must equal the
+    probe-row-major order of the reference (hash_join.rs:80-103).  n_pay <= 2: fat slots, 3: thin slots + gather."""
+    import pyarrow as pa
+    rng = np.random.default_rng(77 + n_pay)
+    nl, nr = 2_000_000, 5_000_017
+    keys = rng.permutation(np.arange(1, 3 * nl + 1, dtype=np.int64))[:nl] * 1_000_003  # unique, sparse
+    pays = [rng.integers(-1 << 40, 1 << 40, nl).astype(np.int64) for _ in range(n_pay)]
+    fk = np.where(rng.random(nr) < 0.7, keys[rng.integers(0, nl, nr)], rng.integers(1, 1 << 50, nr) * 2 + 7).astype(np.int64)
+    b = rng.normal(0, 10, nr)
+    L = pa.RecordBatch.from_arrays([pa.array(keys)] + [pa.array(p_) for p_ in pays], names=["k"] + [f"p{i}" for i in range(n_pay)])
+    R = pa.RecordBatch.from_arrays([pa.array(fk), pa.array(b)], names=["fk", "b"])
+    nq = G.nq
+    join = nq.HashJoin.create(nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None),
+                              nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None), [("k", "fk")], "Inner")
+    got = join.execute()[0]
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    idx = np.searchsorted(sk, fk)
+    idx[idx >= nl] = nl - 1
+    m = sk[idx] == fk
+    brow = order[idx[m]]
+    assert got.num_rows == int(m.sum())
+    assert np.array_equal(got.column(0).to_numpy(), fk[m])
+    for i in range(n_pay):
+        assert np.array_equal(got.column(1 + i).to_numpy(), pays[i][brow]), f"payload {i}"
+    assert np.array_equal(got.column(1 + n_pay).to_numpy(), fk[m])
+    assert np.array_equal(got.column(2 + n_pay).to_numpy(), b[m])
+
+
 def test_hash_join_unique_build_keys_and_u64():
     rng = np.random.default_rng(9)
     nl, nr = 10_000, 50_000
