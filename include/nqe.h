@@ -159,6 +159,16 @@ int32_t nqe_table_slice(nqe_ctx *ctx, const nqe_table *t, int64_t offset, int64_
 int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate,
                            const nqe_expr *projs, int32_t n_projs, nqe_table **out);
 
+/* The same fused SelectionPlan + ProjectionPlan with HOST Arrow columns in and HOST buffers out -- what
+ * `execute()` hands back to the reference's caller (plan.rs:14-23, db.rs:36).  Rows are streamed through HBM
+ * in chunks on three CUDA streams (H2D of chunk c+1 | kernel of chunk c | D2H of chunk c-1); only the columns
+ * the expressions read are uploaded.  out_cols[i].values must point to a caller-owned buffer of at least
+ * cols[0].length rows (out_cols[i].length = its capacity in rows); dtype / null_count are filled in.
+ * Pinned (cudaHostAlloc / cudaHostRegister) buffers are copied asynchronously; other inputs take the
+ * non-overlapped upload -> operator -> download path. */
+int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *cols, int32_t n_cols, const nqe_expr *predicate,
+                                const nqe_expr *projs, int32_t n_projs, nqe_column_desc *out_cols, int64_t *out_rows);
+
 /* HashJoin::execute = build + probe (hash_join.rs:124-254).  left = build side.
  * Inner join on one Int64/UInt64 key pair; key validity is ignored (:67,:86);
  * output = all left columns ++ all right columns, probe-row-major, build rows

@@ -30,6 +30,7 @@ struct nqe_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // copy streams of the host pipeline (created on first use)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
     int64_t launches = 0;

@@ -265,6 +265,36 @@ def _filter_project(t: DeviceTable, predicate: Optional[PhysicalExpr], exprs: Se
     return DeviceTable(ctx, h, list(out_names) if n else list(t.names))
 
 
+def filter_project_host(ctx, names: Sequence[str], dtypes: Sequence[int], host_ptrs: Sequence[int], n_rows: int,
+                        predicate: Optional[PhysicalExpr], exprs: Sequence[PhysicalExpr], out_ptrs: Sequence[int],
+                        out_capacity_rows: int) -> Tuple[int, List[int]]:
+    """ProjectionPlan(SelectionPlan(scan)) over HOST column buffers with the result written into HOST buffers
+    (nqe_filter_project_host: chunked H2D | kernel | D2H pipeline, only referenced columns are uploaded).
+    host_ptrs / out_ptrs are addresses of 8-byte-value buffers (pinned memory is copied asynchronously).
+    Returns (result rows, result dtypes)."""
+    from ._ffi import ColumnDesc
+    keep = []
+    pred_ptr = None
+    if predicate is not None:
+        pe, arr = predicate.to_expr(list(names))
+        keep.append(arr)
+        pred_ptr = C.pointer(pe)
+    earr = (Expr * len(exprs))()
+    for i, e in enumerate(exprs):
+        ex, arr = e.to_expr(list(names))
+        keep.append(arr)
+        earr[i] = ex
+    cols = (ColumnDesc * len(names))()
+    for i, (dt, ptr) in enumerate(zip(dtypes, host_ptrs)):
+        cols[i].dtype, cols[i].length, cols[i].null_count, cols[i].values = dt, n_rows, 0, ptr
+    outs = (ColumnDesc * len(exprs))()
+    for i, ptr in enumerate(out_ptrs):
+        outs[i].length, outs[i].values = out_capacity_rows, ptr
+    rows = C.c_int64(0)
+    ctx.check(ctx.lib.nqe_filter_project_host(ctx.h, cols, len(names), pred_ptr, earr, len(exprs), outs, C.byref(rows)))
+    return int(rows.value), [int(outs[i].dtype) for i in range(len(exprs))]
+
+
 # --------------------------------------------------------------------------
 # PhysicalPlan nodes
 # --------------------------------------------------------------------------

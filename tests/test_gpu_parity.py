@@ -181,6 +181,29 @@ def test_filter_project_full_size_config():
     tbl.free()
 
 
+@pytest.mark.parametrize("n", [20_000_017, 100_003])
+def test_filter_project_host_pipeline(n):
+    """nqe_filter_project_host: pinned host columns in, pinned host buffers out; the large case runs the chunked
+    three-stream pipeline (only `id` and `age` are uploaded), the small one the plain upload/operator/download path."""
+    import torch
+    from importlib import import_module
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    synth = import_module("naive-query-engine_b200.synth")
+    ctx = G.nq.Context.default()
+    ids, age, score = synth.mod_i64(42, 0, n, 1000), synth.mod_i64(43, 0, n, 100), synth.unif_f64(44, 0, n, 100.0)
+    host = [torch.from_numpy(a.view(np.int64)).pin_memory() for a in (ids, age, score)]
+    outs = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(3)]
+    pred = G.expr(("bin", "Lt", ("col", 0), lit(500)))
+    exprs = [G.expr(("col", 0)), G.expr(("bin", "Plus", ("col", 1), lit(100))), G.expr(("bin", "Multiply", ("col", 2), ("lit", "f64", 2.0)))]
+    rows, dts = pp.filter_project_host(ctx, ["id", "age", "score"], [2, 2, 4], [h.data_ptr() for h in host], n, pred, exprs,
+                                       [o.data_ptr() for o in outs], n)
+    m = ids < 500
+    assert rows == int(m.sum()) and dts == [2, 2, 4]
+    assert np.array_equal(outs[0].numpy()[:rows], ids[m])
+    assert np.array_equal(outs[1].numpy()[:rows], age[m] + 100)
+    assert np.array_equal(outs[2].numpy()[:rows].view(np.float64), score[m] * 2.0)
+
+
 class _CAI:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
