@@ -196,6 +196,17 @@ int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const nqe_table 
 int32_t nqe_radix_partition(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts,
                             nqe_table **out, int64_t *counts);
 
+/* The same partition fused with the exchange (one process per GPU, NVLink 5 / NVSwitch peer memory):
+ * nqe_partition_counts returns how many rows of `in` go to each destination; after the ranks have exchanged
+ * those counts (an all-gather of n_parts words) every rank knows where its rows start in each receive
+ * buffer, and nqe_shuffle_scatter stores the rows straight into the destination GPUs' buffers.
+ * dst_columns[c * n_parts + p] = column c's receive buffer on rank p as mapped into THIS process (CUDA IPC /
+ * symmetric memory; for p == own rank a local pointer), dst_offsets[p] = first row this rank writes there.
+ * The caller synchronises all ranks (stream barrier) before reading its receive buffers.  n_parts, columns <= 8. */
+int32_t nqe_partition_counts(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts, int64_t *counts);
+int32_t nqe_shuffle_scatter(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts,
+                            void *const *dst_columns, const int64_t *dst_offsets);
+
 /* ---- synthetic benchmark columns, generated in HBM -------- */
 /* kind 0: mix64(seed+i) % mod  (Int64);  kind 1: scale*unif01(mix64(seed+i)) (Float64);
  * kind 2: (i * mul) % mod (Int64), i = start .. start+n-1 */

@@ -80,6 +80,8 @@ SYMBOLS = {
     "nqe_join_aggregate": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Agg), C.c_int32,
                                        C.POINTER(_P)]),
     "nqe_radix_partition": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "nqe_partition_counts": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "nqe_shuffle_scatter": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "nqe_synth_column": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                      C.c_double, _P]),
 }

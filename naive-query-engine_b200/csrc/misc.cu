@@ -107,6 +107,68 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(PartParams pp)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Radix partition fused with the exchange: the scatter kernel stores every row straight into the
+// receive buffer of its destination GPU (peer-mapped memory, NVLink 5 / NVSwitch), so the shuffle
+// is one pass over the local rows -- no partitioned staging copy and no separate all-to-all.
+// Destination runs are formed block-locally (counting sort of the tile in shared memory), so the
+// remote stores of one warp are consecutive rows of one destination.
+// ---------------------------------------------------------------------------
+struct ShuffleParams {
+    const unsigned long long *keys;
+    int64_t n;
+    int32_t n_parts;
+    int32_t n_cols;
+    const unsigned long long *in[8];
+    unsigned long long *dst[8 * 8];      // [col][part]: column receive buffer on rank `part`, as mapped here
+    unsigned long long *cursors;         // [n_parts] next row to write in the destination (starts at this rank's offset)
+};
+
+__global__ void __launch_bounds__(PT_THREADS) shuffle_scatter_kernel(const __grid_constant__ ShuffleParams sp) {
+    constexpr int TILE = PT_THREADS * PT_K;
+    __shared__ unsigned int s_cnt[MAX_PARTS], s_start[MAX_PARTS];
+    __shared__ unsigned long long s_base[MAX_PARTS];
+    __shared__ unsigned int s_src[TILE]; // tile-local source row, ordered by destination
+    const int tid = threadIdx.x;
+    const int64_t num_tiles = (sp.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TILE;
+        if (tid < MAX_PARTS) s_cnt[tid] = 0;
+        __syncthreads();
+        int dest[PT_K];
+        unsigned int rank[PT_K];
+#pragma unroll
+        for (int j = 0; j < PT_K; j++) {
+            const int64_t e = base + j * PT_THREADS + tid;
+            dest[j] = e < sp.n ? part_of(sp.keys[e], sp.n_parts) : -1;
+            if (dest[j] >= 0) rank[j] = atomicAdd(&s_cnt[dest[j]], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int run = 0;
+            for (int p = 0; p < sp.n_parts; p++) {
+                s_start[p] = run;
+                run += s_cnt[p];
+            }
+        }
+        if (tid < sp.n_parts && s_cnt[tid]) s_base[tid] = atomicAdd(sp.cursors + tid, (unsigned long long)s_cnt[tid]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PT_K; j++)
+            if (dest[j] >= 0) s_src[s_start[dest[j]] + rank[j]] = (unsigned)(j * PT_THREADS + tid) | ((unsigned)dest[j] << 24);
+        __syncthreads();
+        const int64_t n_here = sp.n - base < TILE ? sp.n - base : TILE;
+        for (int i = tid; i < n_here; i += PT_THREADS) {
+            const unsigned int v = s_src[i];
+            const int p = (int)(v >> 24);
+            const unsigned int local = v & 0xffffffu;
+            const unsigned long long d = s_base[p] + (unsigned)(i - s_start[p]);
+            for (int c = 0; c < sp.n_cols; c++) sp.dst[c * 8 + p][d] = sp.in[c][base + local]; // remote (or local) store
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void synth_kernel(int kind, uint64_t seed, int64_t start, int64_t n, uint64_t a, uint64_t b, double scale,
                              unsigned long long *out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -198,6 +260,77 @@ extern "C" int32_t nqe_table_slice(nqe_ctx *ctx, const nqe_table *t, int64_t off
     }
     *out = r;
     return NQE_OK;
+}
+
+static int32_t check_partition_input(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts, int max_parts,
+                                     size_t max_cols) {
+    if (n_parts < 1 || n_parts > max_parts) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "n_parts must be in [1,%d]", max_parts);
+    if (key_column < 0 || key_column >= (int)in->cols.size()) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad key column");
+    if (in->cols.size() > max_cols) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "more than %d columns", (int)max_cols);
+    const int kd = in->cols[key_column].dtype;
+    if (kd != NQE_INT64 && kd != NQE_UINT64) return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "partition key must be Int64/UInt64");
+    for (auto &c : in->cols)
+        if (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8 || c.validity)
+            return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "radix partition supports NULL-free 8-byte columns only");
+    return NQE_OK;
+}
+
+extern "C" int32_t nqe_partition_counts(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts, int64_t *counts) {
+    if (!ctx || !in || !counts) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    NQE_TRY(check_partition_input(ctx, in, key_column, n_parts, MAX_PARTS, 16));
+    PartParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.keys = (const unsigned long long *)in->cols[key_column].values;
+    pp.n = in->nrows;
+    pp.n_parts = n_parts;
+    pp.counts = (unsigned long long *)ctx->d_scratch;
+    cudaMemsetAsync(pp.counts, 0, 64 * sizeof(uint64_t), ctx->stream);
+    if (pp.n > 0) {
+        part_hist_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(pp);
+        ctx->launches++;
+    }
+    cudaMemcpyAsync(ctx->h_scratch, pp.counts, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nqe_fail(ctx, NQE_ERR_CUDA, "partition histogram failed");
+    for (int p = 0; p < n_parts; p++) counts[p] = (int64_t)ctx->h_scratch[p];
+    return NQE_OK;
+}
+
+extern "C" int32_t nqe_shuffle_scatter(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts,
+                                       void *const *dst_columns, const int64_t *dst_offsets) {
+    if (!ctx || !in || !dst_columns || !dst_offsets) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    NQE_TRY(check_partition_input(ctx, in, key_column, n_parts, 8, 8));
+    ShuffleParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.keys = (const unsigned long long *)in->cols[key_column].values;
+    sp.n = in->nrows;
+    sp.n_parts = n_parts;
+    sp.n_cols = (int)in->cols.size();
+    for (int c = 0; c < sp.n_cols; c++) {
+        sp.in[c] = (const unsigned long long *)in->cols[c].values;
+        for (int p = 0; p < n_parts; p++) sp.dst[c * 8 + p] = (unsigned long long *)dst_columns[c * n_parts + p];
+    }
+    OpTimer timer(ctx);
+    void *cur = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &cur, 64 * sizeof(uint64_t)));
+    for (int p = 0; p < n_parts; p++) ctx->h_scratch[p] = (uint64_t)dst_offsets[p];
+    cudaMemcpyAsync(cur, ctx->h_scratch, 64 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    sp.cursors = (unsigned long long *)cur;
+    int32_t rc = NQE_OK;
+    if (sp.n > 0) {
+        const int64_t tiles = (sp.n + PT_THREADS * PT_K - 1) / (PT_THREADS * PT_K);
+        int grid = ctx->sm_count * 4;
+        if (grid > tiles) grid = (int)tiles;
+        shuffle_scatter_kernel<<<grid, PT_THREADS, 0, ctx->stream>>>(sp);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "shuffle scatter launch failed");
+    }
+    // h_scratch is reused by later calls: the staging copy must have been consumed before returning
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "shuffle scatter failed: %s", cudaGetErrorString(cudaGetLastError()));
+    timer.stop();
+    nqe_dev_free(ctx, cur);
+    return rc;
 }
 
 extern "C" int32_t nqe_radix_partition(nqe_ctx *ctx, const nqe_table *in, int32_t key_column, int32_t n_parts,

@@ -2,8 +2,13 @@
 `torch.distributed` for the plumbing.
 
     rank r owns a row range of L (build) and R (probe)
-    1. radix-partition both sides on the join key          (nqe_radix_partition, dest = mix64(key) % P)
-    2. all-to-all the partitions over NCCL / NVLink        (dist.all_to_all_single, uneven splits)
+    1+2. radix partition fused with the exchange (`exchange_peer`): every rank counts its rows per
+       destination (nqe_partition_counts), the ranks all-gather those P x P counts, and one scatter
+       kernel (nqe_shuffle_scatter) stores each row straight into the destination GPU's receive
+       buffer through peer-mapped memory (NVLink 5 / NVSwitch; symmetric memory for the mapping)
+       -- no partitioned staging copy, no separate all-to-all.
+       Baseline kept for comparison and for engines without peer memory (`exchange`):
+       nqe_radix_partition then dist.all_to_all_single with uneven splits (NCCL).
     3. local fused join -> group-by on the received rows   (nqe_join_aggregate; min(group) carries the key,
                                                             because the reference's aggregate emits no key column)
     4. all-gather the partial states and merge them        (count -> sum of counts, sum -> sum, min, max;
@@ -27,6 +32,19 @@ class Engine:
 
     def partition(self, cols: Sequence, key: int, parts: int) -> Tuple[List, List[int]]:
         """-> (columns permuted so that rows of destination p are contiguous, counts[parts])"""
+        raise NotImplementedError
+
+    def partition_counts(self, cols: Sequence, key: int, parts: int) -> List[int]:
+        """rows of `cols` per destination (dest = mix64(key) % parts)"""
+        raise NotImplementedError
+
+    def alloc_exchange(self, capacity_rows: int, n_cols: int, group):
+        """receive buffers every rank of `group` can store into: .capacity, .local(c) -> this rank's column
+        c buffer (tensor), .barrier() -> all ranks' earlier work on the buffers is complete"""
+        raise NotImplementedError
+
+    def scatter_to_peers(self, cols: Sequence, key: int, parts: int, xbuf, offsets: Sequence[int]) -> None:
+        """store every row into column buffers of rank mix64(key) % parts, starting at row offsets[dest]"""
         raise NotImplementedError
 
     def join_partial_aggregate(self, lcols: Sequence, rcols: Sequence):
@@ -57,11 +75,43 @@ def exchange(dist, torch, engine: Engine, cols: Sequence, key: int, world: int):
     return outs, sum(send_l) - send_l[rank]
 
 
-def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int):
+def peer_offsets(count_matrix: Sequence[Sequence[int]], rank: int):
+    """count_matrix[src][dst] = rows src sends to dst.  -> (first row `rank` writes in every destination's
+    receive buffer, rows `rank` receives in total, the largest receive total over all ranks)."""
+    world = len(count_matrix)
+    offsets = [sum(count_matrix[s][d] for s in range(rank)) for d in range(world)]
+    totals = [sum(count_matrix[s][d] for s in range(world)) for d in range(world)]
+    return offsets, totals[rank], max(totals)
+
+
+def exchange_peer(dist, torch, engine: Engine, cols: Sequence, key: int, world: int, xbuf):
+    """Steps 1-2 fused: rows go straight into the destination ranks' receive buffers (`xbuf`, from
+    engine.alloc_exchange).  Returns (received columns -- views of this rank's buffer, rows sent to others)."""
+    rank = dist.get_rank()
+    counts = engine.partition_counts(cols, key, world)
+    mine = torch.tensor(counts, dtype=torch.int64, device=cols[0].device)
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    matrix = [[int(x) for x in t.tolist()] for t in allc]
+    offsets, total, need = peer_offsets(matrix, rank)
+    if need > xbuf.capacity:
+        raise RuntimeError(f"exchange buffer too small: {need} rows needed, capacity {xbuf.capacity}")
+    xbuf.barrier()  # every rank has finished reading what the previous exchange delivered
+    engine.scatter_to_peers(cols, key, world, xbuf, offsets)
+    xbuf.barrier()  # every rank's stores have landed
+    return [xbuf.local(c)[:total] for c in range(len(cols))], sum(counts) - counts[rank]
+
+
+def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int, xbufs=None):
     """Steps 1-4.  Every rank returns the full merged result
-    [key, count, sum, min, max] (tensors) and the number of rows it sent over the wire."""
-    l_recv, s1 = exchange(dist, torch, engine, lcols, 0, world)
-    r_recv, s2 = exchange(dist, torch, engine, rcols, 0, world)
+    [key, count, sum, min, max] (tensors) and the number of rows it sent over the wire.
+    xbufs = (build-side, probe-side) exchange buffers: rows travel through peer memory; None: NCCL all-to-all."""
+    if xbufs is not None:
+        l_recv, s1 = exchange_peer(dist, torch, engine, lcols, 0, world, xbufs[0])
+        r_recv, s2 = exchange_peer(dist, torch, engine, rcols, 0, world, xbufs[1])
+    else:
+        l_recv, s1 = exchange(dist, torch, engine, lcols, 0, world)
+        r_recv, s2 = exchange(dist, torch, engine, rcols, 0, world)
     partial = engine.join_partial_aggregate(l_recv, r_recv)
     g = int(partial[0].numel())
     sizes = torch.tensor([g], dtype=torch.int64, device=partial[0].device)
@@ -115,6 +165,42 @@ class CudaEngine(Engine):
             r._nqe_keepalive = out  # the views borrow the partitioned table's buffers
         t.free()
         return res, [int(x) for x in counts]
+
+    def partition_counts(self, cols, key, parts):
+        ctx = self.ctx
+        t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
+        counts = (C.c_int64 * parts)()
+        ctx.check(ctx.lib.nqe_partition_counts(ctx.h, t.h, key, parts, counts))
+        t.free()
+        return [int(x) for x in counts]
+
+    class _SymmExchange:
+        """Per-column symmetric-memory receive buffers (torch.distributed._symmetric_memory does the
+        CUDA IPC mapping and the stream barrier: plumbing); the stores are ours (nqe_shuffle_scatter)."""
+
+        def __init__(self, torch, capacity_rows, n_cols, group):
+            import torch.distributed._symmetric_memory as symm_mem
+            self.capacity = int(capacity_rows)
+            self.tensors = [symm_mem.empty(self.capacity, dtype=torch.int64, device="cuda") for _ in range(n_cols)]
+            self.handles = [symm_mem.rendezvous(t, group) for t in self.tensors]
+            self.ptrs = [[int(p) for p in h.buffer_ptrs] for h in self.handles]  # [col][rank]
+
+        def local(self, c):
+            return self.tensors[c]
+
+        def barrier(self):
+            self.handles[0].barrier(channel=0)
+
+    def alloc_exchange(self, capacity_rows, n_cols, group):
+        return self._SymmExchange(self.torch, capacity_rows, n_cols, group)
+
+    def scatter_to_peers(self, cols, key, parts, xbuf, offsets):
+        ctx = self.ctx
+        t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
+        dst = (C.c_void_p * (len(cols) * parts))(*[xbuf.ptrs[c][p] for c in range(len(cols)) for p in range(parts)])
+        offs = (C.c_int64 * parts)(*[int(o) for o in offsets])
+        ctx.check(ctx.lib.nqe_shuffle_scatter(ctx.h, t.h, key, parts, dst, offs))
+        t.free()
 
     def join_partial_aggregate(self, lcols, rcols):
         ctx, nq = self.ctx, self.nq

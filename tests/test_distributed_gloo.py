@@ -43,6 +43,42 @@ class OracleEngine:
         counts = np.bincount(dest, minlength=parts).tolist()
         return [torch.from_numpy(c.numpy()[order].copy()) for c in cols], counts
 
+    # ---- peer-memory exchange, emulated with files every rank maps (np.memmap) ----
+    def partition_counts(self, cols, key, parts):
+        k = cols[key].numpy()
+        dest = (_mix64(k.view(np.uint64)) % np.uint64(parts)).astype(np.int64)
+        return np.bincount(dest, minlength=parts).tolist()
+
+    def alloc_exchange(self, capacity_rows, n_cols, group, shared_dir=None, tag="x"):
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        class X:
+            pass
+        x = X()
+        x.capacity = capacity_rows
+        for c in range(n_cols):  # every rank creates its own receive files, then maps everybody's
+            np.memmap(os.path.join(shared_dir, f"{tag}_{rank}_{c}.bin"), dtype=np.int64, mode="w+", shape=(capacity_rows,)).flush()
+        dist.barrier()
+        x.maps = [[np.memmap(os.path.join(shared_dir, f"{tag}_{p}_{c}.bin"), dtype=np.int64, mode="r+", shape=(capacity_rows,))
+                   for p in range(world)] for c in range(n_cols)]
+        x.local = lambda c: torch.from_numpy(np.array(x.maps[c][rank]))
+
+        def barrier():
+            for row in x.maps:
+                for m in row:
+                    m.flush()
+            dist.barrier()
+        x.barrier = barrier
+        return x
+
+    def scatter_to_peers(self, cols, key, parts, xbuf, offsets):
+        k = cols[key].numpy()
+        dest = (_mix64(k.view(np.uint64)) % np.uint64(parts)).astype(np.int64)
+        for p in range(parts):
+            sel = np.nonzero(dest == p)[0]
+            for c, col in enumerate(cols):
+                xbuf.maps[c][p][offsets[p]:offsets[p] + len(sel)] = col.numpy()[sel]
+
     def join_partial_aggregate(self, lcols, rcols):
         O = self.O
         L = O.Batch(["k", "a"], [O.Col("i64", lcols[0].numpy()), O.Col("i64", lcols[1].numpy())])
@@ -80,7 +116,7 @@ def _tables(start_l, n_l, start_r, n_r):
     return lk, la, fk, rb
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, peer_dir=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -90,7 +126,11 @@ def _worker(rank, world, port, out_path):
     lk, la, fk, rb = _tables(rank * nl, nl, rank * nr, nr)
     lcols = [torch.from_numpy(lk), torch.from_numpy(la)]
     rcols = [torch.from_numpy(fk), torch.from_numpy(rb.view(np.int64).copy())]
-    merged, sent = D.shuffled_join_group_by(dist, torch, OracleEngine(), lcols, rcols, world)
+    engine = OracleEngine()
+    xbufs = None
+    if peer_dir is not None:  # rows travel through "peer memory" (files mapped by every rank)
+        xbufs = (engine.alloc_exchange(N_BUILD, 2, None, peer_dir, "l"), engine.alloc_exchange(N_PROBE, 2, None, peer_dir, "r"))
+    merged, sent = D.shuffled_join_group_by(dist, torch, engine, lcols, rcols, world, xbufs)
     if rank == 0:
         np.savez(out_path, key=merged[0].numpy(), count=merged[1].numpy(), sum=merged[2].numpy().view(np.float64),
                  min=merged[3].numpy().view(np.float64), max=merged[4].numpy().view(np.float64), sent=sent)
@@ -98,12 +138,22 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_shuffled_join_group_by_world2(tmp_path):
+def test_peer_offsets():
+    from importlib import import_module
+    D = import_module("naive-query-engine_b200.distributed")
+    m = [[5, 1, 2], [0, 7, 3], [4, 4, 4]]  # m[src][dst]
+    assert D.peer_offsets(m, 0) == ([0, 0, 0], 9, 12)
+    assert D.peer_offsets(m, 1) == ([5, 1, 2], 12, 12)
+    assert D.peer_offsets(m, 2) == ([5, 8, 5], 9, 12)
+
+
+@pytest.mark.parametrize("peer", [False, True])
+def test_shuffled_join_group_by_world2(tmp_path, peer):
     from oracle import oracle as O
     world = 2
     out = str(tmp_path / "merged.npz")
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (1 if peer else 0)
+    mp.spawn(_worker, args=(world, port, out, str(tmp_path) if peer else None), nprocs=world, join=True)
     got = np.load(out)
     lk, la, fk, rb = _tables(0, N_BUILD, 0, N_PROBE)
     L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", la)])

@@ -507,9 +507,11 @@ def test_synth_columns_match_oracle_generator():
         assert np.array_equal(got, want.view(np.int64))
 
 
-def test_distributed_plan_on_one_gpu_matches_oracle():
+@pytest.mark.parametrize("peer", [False, True])
+def test_distributed_plan_on_one_gpu_matches_oracle(peer):
     """distributed.py's CudaEngine through a 1-rank NCCL group (the >1-rank orchestration is
-    covered on CPU over gloo in test_distributed_gloo.py)."""
+    covered on CPU over gloo in test_distributed_gloo.py).  peer=True: rows go through
+    nqe_partition_counts + nqe_shuffle_scatter into symmetric-memory receive buffers."""
     import os
     from importlib import import_module
     import torch
@@ -529,7 +531,10 @@ def test_distributed_plan_on_one_gpu_matches_oracle():
         rb = O.gen_unif_f64(48, 0, n_probe, 100.0)
         dev = lambda a: torch.from_numpy(a.view(np.int64).copy()).cuda()
         eng = D.CudaEngine(nq, nq.Context.default(), torch)
-        merged, sent = D.shuffled_join_group_by(dist, torch, eng, [dev(lk), dev(la)], [dev(fk), dev(rb)], 1)
+        xbufs = None
+        if peer:
+            xbufs = (eng.alloc_exchange(n_build + 64, 2, dist.group.WORLD), eng.alloc_exchange(n_probe + 64, 2, dist.group.WORLD))
+        merged, sent = D.shuffled_join_group_by(dist, torch, eng, [dev(lk), dev(la)], [dev(fk), dev(rb)], 1, xbufs)
         got = [m.cpu().numpy() for m in merged]
         L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", la)])
         R = O.Batch(["fk", "b"], [O.Col("i64", fk), O.Col("f64", rb)])
