@@ -244,7 +244,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -256,18 +256,7 @@ def run_gpu(args, rank, local_rank, world):
     BOOL, I64, U64, F64 = 1, 2, 3, 4
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout; the driver wants exactly one JSON line there
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = nq.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -388,7 +377,7 @@ def run_gpu(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "secondary": secondary,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -548,7 +537,26 @@ def shuffled_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, 
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries (NCCL's version banner, for one) write to stdout; the driver expects exactly one JSON line
+    # there, so everything else that lands on fd 1 is sent to stderr for the duration of the run.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
