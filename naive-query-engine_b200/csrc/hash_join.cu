@@ -9,8 +9,8 @@
 //               are at most two NULL-free 8-byte columns (the PK-FK dimension-table
 //               shape): one 32-byte sector then holds everything the probe needs, so the
 //               dependent payload gather -- a second random HBM access -- disappears
-// A verification pass marks whether any key repeats, so unique-key probes stop at the
-// first match.
+// Slots are inserted with one 128-bit CAS, which also tells the build whether any key
+// repeats, so unique-key probes stop at the first match.
 //
 // Probe (hash_join.rs:80-103, 236-246): one pass over the probe side.  Every tile looks
 // its rows up (the first table probe of a thread's K rows is issued together, collisions
@@ -62,9 +62,11 @@ struct ColSrc {
 };
 
 __device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uint64_t s) { return jt.words + (s << jt.shift); }
-// Random accesses.  Measured on B200 (profiles/join_groupby_r01.md): a random 16-byte read costs
-// ~128 bytes of DRAM traffic whatever the load flavour (ld.global.nc, .cg, .L1::no_allocate) and
-// whatever cudaLimitMaxL2FetchGranularity says, so the plain read-only path is kept.
+// Random accesses.  Measured on B200 (scratch/l2gran.cu, profiles/join_groupby_r01.md): an L2 sector miss
+// reads 128 bytes from DRAM (the whole line is installed) whatever the load flavour (.nc, .cg,
+// .L1::no_allocate) and whatever cudaLimitMaxL2FetchGranularity says; the .L2::64B prefetch-size
+// qualifier halves the bytes but not the time -- random probes are bound by the DRAM request rate
+// (~1.7e10 /s), not by bytes -- so the plain read-only path is kept.
 __device__ __forceinline__ ulonglong2 ld_cg_v2(const unsigned long long *p) { return __ldg((const ulonglong2 *)p); }
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldg(p); }
 __device__ __forceinline__ ulonglong4 ld_v4(const unsigned long long *p) {
@@ -91,41 +93,43 @@ __global__ void join_clear_kernel(JoinTable jt, uint64_t n) {
     }
 }
 
-__global__ void join_build_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *status) {
+// 128-bit compare-and-swap of a whole {key, row} slot (ATOMG.CAS.128): the slot becomes visible with both
+// words at once, so an insert that walks over an occupied slot can compare keys reliably -- duplicate
+// build keys are detected while building, without a second pass over the build side.
+__device__ __forceinline__ ulonglong2 cas128(unsigned long long *p, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.global.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.x), "=l"(old.y) : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(p) : "memory");
+    return old;
+}
+
+__global__ void join_build_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *status,
+                                  uint32_t *dupflag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = keys[i];
     uint64_t s = join_slot_of(jt, key);
+    bool dup = false;
     for (uint64_t probe = 0; probe < jt.cap; probe++) {
         unsigned long long *p = slot_ptr(jt, s);
-        const unsigned long long old = atomicCAS(p + 1, EMPTY_ROW, (unsigned long long)i);
-        if (old == EMPTY_ROW) {
-            p[0] = key;
+        const ulonglong2 old = cas128(p, make_ulonglong2(0ull, EMPTY_ROW), make_ulonglong2(key, (unsigned long long)i));
+        if (old.y == EMPTY_ROW) {
             if (jt.shift == 2) {
                 p[2] = jt.n_pay > 0 ? jt.pay_src[0][i] : 0ull;
                 p[3] = jt.n_pay > 1 ? jt.pay_src[1][i] : 0ull;
             }
+            if (dup) *dupflag = 1u;
             return;
         }
+        if (old.x == key) dup = true; // an equal key was inserted earlier on this probe sequence
         s = s + 1 == jt.cap ? 0 : s + 1;
     }
     atomicOr(status, DEV_ERR_TABLE_FULL);
-}
-
-// does any key occur more than once on the build side?
-__global__ void join_dups_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *flag) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long key = keys[i];
-    uint64_t s = join_slot_of(jt, key);
-    int matches = 0;
-    while (true) {
-        const Slot sl = ld_slot(jt, s);
-        if (sl.row == EMPTY_ROW) break;
-        if (sl.key == key) matches++;
-        s = s + 1 == jt.cap ? 0 : s + 1;
-    }
-    if (matches > 1) *flag = 1u;
 }
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
@@ -227,6 +231,7 @@ struct PartJoin {
     unsigned int *tile_off;         // [num_tiles][P]: rows of that partition in earlier tiles
     unsigned long long *part_base;  // [P + 1]: first position of the partition in the partitioned order
     unsigned long long *pkeys;      // keys in partitioned order
+    unsigned int *ppos32;           // per probe row (original order): its position in the partitioned order
     unsigned long long *res0;       // per position: thin = build row (EMPTY_ROW: no match), fat = payload word 0
     unsigned long long *res1;       // fat, two payload columns: payload word 1
     unsigned int *mbits;            // fat: match bit per position
@@ -380,7 +385,10 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
         pj_positions<K>(pj, tile, key, inrange, s_c, ppos);
 #pragma unroll
         for (int j = 0; j < K; j++)
-            if ((inrange >> j) & 1u) pj.pkeys[ppos[j]] = key[j];
+            if ((inrange >> j) & 1u) {
+                pj.pkeys[ppos[j]] = key[j];
+                pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos[j];
+            }
     }
 }
 
@@ -417,6 +425,39 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
                 pj.res0[e] = brow[j];
             }
         }
+    }
+}
+
+// pass 5: results back into probe-row order.  Row i fetches the result at its position in the partitioned
+// order (sequential within each partition's stream), gathers the build-side columns and leaves a match bitmap;
+// the joined rows are then compacted by the filter/project kernel (predicate = the match bitmap).
+struct GatherParams {
+    PartJoin pj;
+    int32_t fat, n_gather;
+    const unsigned long long *src[HJ_MAX_COLS]; // thin: build column to gather by build row
+    unsigned long long *dst[HJ_MAX_COLS];       // thin: gathered column; fat: dst[0], dst[1] = payload words
+    unsigned int *match;                        // match bitmap in probe-row order
+};
+__global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ GatherParams gp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n32 = (gp.pj.n + 31) / 32 * 32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < gp.pj.n;
+        bool m = false;
+        if (live) {
+            const unsigned int p = gp.pj.ppos32[i];
+            if (gp.fat) {
+                m = (__ldg(gp.pj.mbits + (p >> 5)) >> (p & 31)) & 1u;
+                gp.dst[0][i] = ld_stream_u64(gp.pj.res0 + p);
+                if (gp.pj.res1) gp.dst[1][i] = ld_stream_u64(gp.pj.res1 + p);
+            } else {
+                const unsigned long long brow = ld_stream_u64(gp.pj.res0 + p);
+                m = brow != EMPTY_ROW;
+                for (int c = 0; c < gp.n_gather; c++) gp.dst[c][i] = m ? ld_cg_u64(gp.src[c] + brow) : 0ull;
+            }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) gp.match[i >> 5] = b;
     }
 }
 
@@ -779,9 +820,8 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
     ctx->launches++;
     if (nl > 0) {
         const unsigned long long *keys = (const unsigned long long *)left->cols[lk].values;
-        join_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, status);
-        join_dups_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, dupflag);
-        ctx->launches += 2;
+        join_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, status, dupflag);
+        ctx->launches++;
     }
     cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
@@ -846,7 +886,11 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
         }
         const size_t table_bytes = (size_t)(pp.jt.cap << pp.jt.shift) * 8;
-        const bool thin_ok = pp.jt.shift == 1, fat_ok = fat;
+        bool emit_fp = true; // emit through the filter/project kernel: NULL-free 8-byte build columns only
+        for (int c = 0; c < nl; c++)
+            if (left->cols[c].validity || left->cols[c].dtype == NQE_BOOL) emit_fp = false;
+        if (nl + nr + 1 > 16) emit_fp = false;
+        const bool thin_ok = pp.jt.shift == 1 && emit_fp, fat_ok = fat && emit_fp;
         if (allow_part && !pp.jt.has_dups && (thin_ok || fat_ok) && pp.n_probe >= (1 << 22) && table_bytes > 2 * l2_budget &&
             pp.n_probe < (int64_t)1 << 32) {
             int log2p = 1;
@@ -867,6 +911,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             alloc((void **)&pj.part_base, (P + 1) * 8);
             alloc(&totals, P * 8);
             alloc((void **)&pj.pkeys, (size_t)pp.n_probe * 8);
+            alloc((void **)&pj.ppos32, (size_t)pp.n_probe * 4);
             alloc((void **)&pj.res0, (size_t)pp.n_probe * 8);
             if (fat && pp.jt.n_pay > 1) alloc((void **)&pj.res1, (size_t)pp.n_probe * 8);
             if (fat) alloc((void **)&pj.mbits, ((size_t)pp.n_probe / 32 + 2) * 4);
@@ -886,6 +931,72 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
                 pj.pkeys = nullptr;
             }
         }
+    }
+    if (rc == NQE_OK && part) {
+        // ---- results back into probe-row order, then one fused compaction of the joined rows
+        GatherParams gp;
+        memset(&gp, 0, sizeof gp);
+        gp.pj = pp.pj;
+        gp.fat = fat ? 1 : 0;
+        const int64_t n = pp.n_probe;
+        std::vector<void *> gathered(nl, nullptr); // per build column: its values in probe-row order
+        auto alloc = [&](void **p, size_t bytes) {
+            if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
+            if (rc == NQE_OK) pj_bufs.push_back(*p);
+        };
+        alloc((void **)&gp.match, nqe_bitmap_bytes(n));
+        if (fat) {
+            for (int q = 0; q < pp.jt.n_pay; q++) {
+                alloc(&gathered[pp.jt.pay_col[q]], (size_t)n * 8);
+                gp.dst[q] = (unsigned long long *)gathered[pp.jt.pay_col[q]];
+            }
+        } else {
+            for (int c = 0; c < nl; c++) {
+                if (c == left_key) continue;
+                alloc(&gathered[c], (size_t)n * 8);
+                gp.src[gp.n_gather] = (const unsigned long long *)left->cols[c].values;
+                gp.dst[gp.n_gather] = (unsigned long long *)gathered[c];
+                gp.n_gather++;
+            }
+        }
+        if (rc == NQE_OK) {
+            pj_gather_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
+            ctx->launches++;
+            // joined table before compaction: [build columns (key = probe key) | probe columns | match]
+            nqe_table view;
+            view.ctx = ctx;
+            view.nrows = n;
+            view.cols.resize(nl + nr + 1);
+            for (int c = 0; c < nl; c++) {
+                DevColumn &d = view.cols[c];
+                d = left->cols[c];
+                d.length = n;
+                d.owned = false;
+                d.values = c == left_key ? right->cols[right_key].values : gathered[c];
+            }
+            for (int c = 0; c < nr; c++) {
+                view.cols[nl + c] = right->cols[c];
+                view.cols[nl + c].owned = false;
+            }
+            DevColumn &mc = view.cols[nl + nr];
+            mc.dtype = NQE_BOOL;
+            mc.length = n;
+            mc.values = gp.match;
+            mc.owned = false;
+            std::vector<nqe_expr_node> nodes(nl + nr + 1);
+            std::vector<nqe_expr> projs(nl + nr);
+            for (int c = 0; c <= nl + nr; c++) nodes[c] = nqe_expr_node{NQE_NODE_COLUMN, 0, c, 0, 0, 0, {0}};
+            for (int c = 0; c < nl + nr; c++) projs[c] = nqe_expr{&nodes[c], 1, 0};
+            const nqe_expr pred{&nodes[nl + nr], 1, 0};
+            nqe_table *joined = nullptr;
+            rc = nqe_filter_project(ctx, &view, &pred, projs.data(), nl + nr, &joined);
+            if (rc == NQE_OK) *out = joined;
+        }
+        timer.stop();
+        nqe_dev_free(ctx, lb);
+        nqe_dev_free(ctx, pp.jt.words);
+        for (void *p : pj_bufs) nqe_dev_free(ctx, p);
+        return rc;
     }
 
     nqe_table *t = nullptr;

@@ -35,6 +35,7 @@ struct nqe_ctx {
     std::string last_error;
     int64_t launches = 0;
     double last_op_ms = 0.0;
+    int timer_depth = 0;
     // small pinned scratch for result words read back after an operator
     uint64_t *h_scratch = nullptr; // pinned, 64 words
     uint64_t *d_scratch = nullptr; // device, 64 words
@@ -83,10 +84,15 @@ int32_t nqe_table_new(nqe_ctx *ctx, int64_t nrows, nqe_table **out);
 int32_t nqe_column_alloc(nqe_ctx *ctx, int32_t dtype, int64_t n, bool with_validity, DevColumn *c);
 void nqe_column_release(nqe_ctx *ctx, DevColumn *c);
 
+// Times the kernels of one operator call.  Operators may call each other (the partitioned join
+// emits through nqe_filter_project): only the outermost timer records.
 struct OpTimer {
     nqe_ctx *ctx;
-    explicit OpTimer(nqe_ctx *c) : ctx(c) { cudaEventRecord(c->ev0, c->stream); }
+    explicit OpTimer(nqe_ctx *c) : ctx(c) {
+        if (c->timer_depth++ == 0) cudaEventRecord(c->ev0, c->stream);
+    }
     void stop() {
+        if (--ctx->timer_depth > 0) return;
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
         float ms = 0.f;
