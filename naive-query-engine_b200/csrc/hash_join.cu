@@ -215,10 +215,11 @@ __device__ __forceinline__ unsigned long long probe_next(const JoinTable &jt, un
 // partitions by the top bits of their hash, which are the top bits of their table slot, so
 // partition p only touches slot range p of the (unchanged) table and that range stays in L2
 // while its keys are probed.  The per-row results land in partition order in sequential
-// streams; the emit pass walks the probe side in its ORIGINAL order, recomputes every row's
-// position in those streams from the per-tile partition offsets (the inverse of the stable
-// split, again sequential per partition), and writes the joined rows probe-row-major exactly
-// like the direct path.  Everything except the L2-resident table is streamed.
+// streams; the gather pass brings them back into the probe side's ORIGINAL row order (every row
+// remembers its position in the partitioned order; reads are sequential per partition stream),
+// leaving a match bitmap, and the joined rows are compacted -- probe-row-major exactly like the
+// direct path -- by the filter/project kernel with that bitmap as the predicate.  Everything
+// except the L2-resident table is streamed.
 // ---------------------------------------------------------------------------
 constexpr int PJ_MAX_PARTS = 32; // one lane per partition in the tile histograms
 
@@ -392,11 +393,28 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
     }
 }
 
+// streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
+// probed (default policy) is what stays resident
+__device__ __forceinline__ unsigned long long pj_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ld_ef(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_ef(unsigned long long *p, unsigned long long v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
 // pass 4: probe in partitioned order (partition after partition, so one slot range of the table is hot in L2)
 template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinTable jt) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
     const int tid = threadIdx.x;
+    const unsigned long long pol = pj_policy();
     for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TILE + tid;
         unsigned long long key[K], brow[K];
@@ -406,7 +424,7 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            key[j] = e < pj.n ? ld_stream_u64(pj.pkeys + e) : 0ull;
+            key[j] = e < pj.n ? ld_ef(pj.pkeys + e, pol) : 0ull;
             if (e < pj.n) inrange |= 1u << j;
         }
         probe_first<K, FAT>(jt, key, inrange, brow, slot, pay);
@@ -417,12 +435,12 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
             if (FAT) {
                 const unsigned m = __ballot_sync(0xffffffffu, live && brow[j] != EMPTY_ROW);
                 if (live) {
-                    pj.res0[e] = pay[j].x;
-                    if (pj.res1) pj.res1[e] = pay[j].y;
+                    st_ef(pj.res0 + e, pay[j].x, pol);
+                    if (pj.res1) st_ef(pj.res1 + e, pay[j].y, pol);
                     if ((tid & 31) == 0) pj.mbits[e >> 5] = m;
                 }
             } else if (live) {
-                pj.res0[e] = brow[j];
+                st_ef(pj.res0 + e, brow[j], pol);
             }
         }
     }
@@ -440,6 +458,7 @@ struct GatherParams {
 };
 __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ GatherParams gp) {
     const int lane = threadIdx.x & 31;
+    const unsigned long long pol = pj_policy();
     const int64_t n32 = (gp.pj.n + 31) / 32 * 32;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
         const bool live = i < gp.pj.n;
@@ -448,12 +467,16 @@ __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ 
             const unsigned int p = gp.pj.ppos32[i];
             if (gp.fat) {
                 m = (__ldg(gp.pj.mbits + (p >> 5)) >> (p & 31)) & 1u;
-                gp.dst[0][i] = ld_stream_u64(gp.pj.res0 + p);
-                if (gp.pj.res1) gp.dst[1][i] = ld_stream_u64(gp.pj.res1 + p);
+                st_ef(gp.dst[0] + i, ld_ef(gp.pj.res0 + p, pol), pol);
+                if (gp.pj.res1) st_ef(gp.dst[1] + i, ld_ef(gp.pj.res1 + p, pol), pol);
             } else {
-                const unsigned long long brow = ld_stream_u64(gp.pj.res0 + p);
+                const unsigned long long brow = ld_ef(gp.pj.res0 + p, pol);
                 m = brow != EMPTY_ROW;
-                for (int c = 0; c < gp.n_gather; c++) gp.dst[c][i] = m ? ld_cg_u64(gp.src[c] + brow) : 0ull;
+                for (int c = 0; c < gp.n_gather; c++) {
+                    unsigned long long v = 0;
+                    if (m) v = ld_cg_u64(gp.src[c] + brow);
+                    st_ef(gp.dst[c] + i, v, pol);
+                }
             }
         }
         const unsigned b = __ballot_sync(0xffffffffu, m);
@@ -463,7 +486,7 @@ __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ 
 
 struct ProbeParams {
     JoinTable jt;
-    PartJoin pj;            // pj.pkeys != nullptr: results come from the partitioned probe
+    PartJoin pj;            // scratch of the partitioned probe (host side only)
     const unsigned long long *probe_keys;
     int64_t n_probe;
     int32_t n_left, n_right;
@@ -502,11 +525,10 @@ __device__ __forceinline__ void emit_row(const ProbeParams &pp, int64_t brow, in
     }
 }
 
-template <bool FAT, bool PART>
+template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
-    __shared__ unsigned short s_c[PART ? K * HJ_WARPS : 1][PJ_MAX_PARTS];
     __shared__ unsigned long long s_cnt[K * HJ_WARPS];
     __shared__ unsigned long long s_tile_excl;
     __shared__ int s_tile;
@@ -528,28 +550,7 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             if (e < pp.n_probe) inrange |= 1u << j;
         }
         ulonglong2 pay[K];
-        if (PART) {
-            // results of the partitioned probe, fetched from their position in the partitioned order
-            unsigned long long ppos[K];
-            pj_positions<K>(pp.pj, tile, key, inrange, s_c, ppos);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                slot[j] = 0;
-                first[j] = EMPTY_ROW;
-                cnt[j] = 0;
-                pay[j] = make_ulonglong2(0, 0);
-                if (!((inrange >> j) & 1u)) continue;
-                if (FAT) {
-                    cnt[j] = (__ldg(pp.pj.mbits + (ppos[j] >> 5)) >> (ppos[j] & 31)) & 1u;
-                    pay[j].x = ld_stream_u64(pp.pj.res0 + ppos[j]);
-                    if (pp.pj.res1) pay[j].y = ld_stream_u64(pp.pj.res1 + ppos[j]);
-                    first[j] = cnt[j] ? 0ull : EMPTY_ROW;
-                } else {
-                    first[j] = ld_stream_u64(pp.pj.res0 + ppos[j]);
-                    cnt[j] = first[j] != EMPTY_ROW;
-                }
-            }
-        } else if (!pp.jt.has_dups) {
+        if (!pp.jt.has_dups) {
             probe_first<K, FAT>(pp.jt, key, inrange, first, slot, pay);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
@@ -1029,8 +1030,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
             if (pp.num_tiles > 0) {
-                auto kern = part ? (fat ? join_probe_kernel<true, true> : join_probe_kernel<false, true>)
-                                 : (fat ? join_probe_kernel<true, false> : join_probe_kernel<false, false>);
+                auto kern = fat ? join_probe_kernel<true> : join_probe_kernel<false>;
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);
