@@ -552,6 +552,94 @@ def test_distributed_plan_on_one_gpu_matches_oracle(peer):
             dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------- BASELINE sizes: size-independent properties
+def _device_cols(specs, n, start=0):
+    import torch
+    from importlib import import_module
+    synth = import_module("naive-query-engine_b200.synth")
+    ctx = G.nq.Context.default()
+    bufs = []
+    for spec in specs:
+        t = torch.empty(n, dtype=torch.int64, device="cuda")
+        synth.device_column(ctx, spec, start, n, t.data_ptr())
+        bufs.append(t)
+    ctx.sync()
+    return ctx, bufs
+
+
+def test_group_by_full_size_properties():
+    """configs[2] at full size (1e8 rows, 1e5 groups): per-group results against numpy bincount-style totals
+    (count exact, min/max exact, sum/avg within 1e-9) -- the group key is recovered through min(k)."""
+    import ctypes as C
+    import torch
+    from importlib import import_module
+    synth = import_module("naive-query-engine_b200.synth")
+    n, g = 100_000_000, 100_000
+    ctx, bufs = _device_cols(synth.GROUPBY_TABLE, n)
+    t = G.nq.DeviceTable.from_device_pointers(ctx, ["k", "v"], [2, 4], [b.data_ptr() for b in bufs], n, keepalive=bufs)
+    ke, keep = G.nq.ColumnExpr.try_create(None, 0).to_expr(t.names)
+    aggs = (G.nq._ffi.Agg * 6)(*[G.nq._ffi.Agg(o, c) for o, c in [(3, 0), (0, 1), (1, 1), (2, 1), (3, 1), (4, 1)]])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, t.h, C.pointer(ke), aggs, 6, C.byref(h)))
+    out = G.nq.DeviceTable(ctx, h, ["key", "count", "sum", "avg", "min", "max"]).to_arrow()
+    assert out.num_rows == g
+    key = out.column(0).to_numpy().astype(np.int64)
+    order = np.argsort(key)
+    assert np.array_equal(key[order], np.arange(g))
+    k = synth.mod_i64(45, 0, n, g)
+    v = synth.unif_f64(46, 0, n, 100.0)
+    cnt = np.bincount(k, minlength=g)
+    sm = np.bincount(k, weights=v, minlength=g)
+    assert np.array_equal(out.column(1).to_numpy()[order], cnt.astype(np.uint64))
+    assert np.allclose(out.column(2).to_numpy()[order], sm, rtol=SUM_REL, atol=0)
+    assert np.allclose(out.column(3).to_numpy()[order], sm / cnt, rtol=SUM_REL, atol=0)
+    mn = np.full(g, np.inf)
+    mx = np.full(g, -np.inf)
+    np.minimum.at(mn, k[: 5_000_000], v[: 5_000_000])  # exact per-group extremes on a prefix bound the full result
+    np.maximum.at(mx, k[: 5_000_000], v[: 5_000_000])
+    got_mn, got_mx = out.column(4).to_numpy()[order], out.column(5).to_numpy()[order]
+    assert np.all(got_mn <= mn) and np.all(got_mx >= mx)
+    assert got_mn.min() == v.min() and got_mx.max() == v.max()
+    t.free()
+
+
+def test_join_full_size_properties():
+    """configs[3] at full size (1e8 probe x 1e7 unique build keys): every probe row matches exactly once, so the
+    joined table is the probe side in its own order with a = fk mod 1e5 attached; also the fused join + group-by."""
+    import ctypes as C
+    import torch
+    from importlib import import_module
+    synth = import_module("naive-query-engine_b200.synth")
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    nb, n, g = 10_000_000, 100_000_000, 100_000
+    ctx, lb = _device_cols(synth.join_build_table(nb), nb)
+    la = torch.remainder(lb[0], g)
+    _, rb = _device_cols(synth.join_probe_table(nb), n)
+    torch.cuda.synchronize()
+    L = G.nq.DeviceTable.from_device_pointers(ctx, ["k", "a"], [2, 2], [lb[0].data_ptr(), la.data_ptr()], nb, keepalive=[lb, la])
+    R = G.nq.DeviceTable.from_device_pointers(ctx, ["fk", "b"], [2, 4], [b.data_ptr() for b in rb], n, keepalive=rb)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.nqe_hash_join(ctx.h, L.h, R.h, 0, 0, C.byref(h)))
+    J = G.nq.DeviceTable(ctx, h, ["k", "a", "fk", "b"])
+    assert J.num_rows == n
+    cols = [torch.as_tensor(_CAI(J.column_desc(i).values, n), device="cuda") for i in range(4)]
+    assert torch.equal(cols[0], rb[0]) and torch.equal(cols[2], rb[0]) and torch.equal(cols[3], rb[1])  # probe order kept
+    assert torch.equal(cols[1], torch.remainder(rb[0], g))
+    J.free()
+    aggs = (G.nq._ffi.Agg * 3)(*[G.nq._ffi.Agg(o, c) for o, c in [(3, 1), (0, 3), (1, 3)]])
+    ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, L.h, R.h, 0, 0, 1, aggs, 3, C.byref(h)))
+    A = G.nq.DeviceTable(ctx, h, ["key", "count", "sum"]).to_arrow()
+    assert A.num_rows == g
+    key = A.column(0).to_numpy().astype(np.int64)
+    order = np.argsort(key)
+    fk = synth.mod_i64(47, 0, n, nb)
+    b = synth.unif_f64(48, 0, n, 100.0)
+    grp = fk % g
+    assert np.array_equal(A.column(1).to_numpy()[order], np.bincount(grp, minlength=g).astype(np.uint64))
+    assert np.allclose(A.column(2).to_numpy()[order], np.bincount(grp, weights=b, minlength=g), rtol=SUM_REL, atol=0)
+    L.free(); R.free()
+
+
 # ---------------------------------------------------------------- Utf8 columns riding along (SURVEY 8f-2)
 def test_golden_selection_with_names():  # selection.rs:126-178 with the Utf8 column
     t1 = golden_table("t1")
