@@ -170,14 +170,14 @@ int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *cols, int32
                                 const nqe_expr *projs, int32_t n_projs, nqe_column_desc *out_cols, int64_t *out_rows);
 
 /* HashJoin::execute = build + probe (hash_join.rs:124-254).  left = build side.
- * Inner join on one Int64/UInt64 key pair; key validity is ignored (:67,:86);
+ * Inner join on one Int64/UInt64/Utf8 key pair; key validity is ignored (:67,:86);
  * output = all left columns ++ all right columns, probe-row-major, build rows
  * ascending within one probe row. */
 int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right,
                       int32_t left_key, int32_t right_key, nqe_table **out);
 
 /* PhysicalAggregatePlan::execute (aggregate/mod.rs:113-222).  group_expr == NULL
- * => one global row; otherwise group by that single expression (Int64/UInt64),
+ * => one global row; otherwise group by that single expression (Int64/UInt64, or a bare Utf8 column),
  * NULL keys dropped, NO key column in the output, group order unspecified
  * (the reference's is std-HashMap order). */
 int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *group_expr,

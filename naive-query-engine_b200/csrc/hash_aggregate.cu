@@ -20,6 +20,9 @@
 
 #include "agg_device.cuh"
 
+int32_t nqe_utf8_key_ids(nqe_ctx *ctx, const DevColumn &dict, const DevColumn *probe, DevColumn *dict_ids, DevColumn *probe_ids);
+static const char *agg_fn_name(int op);
+
 namespace {
 
 __global__ void agg_init_kernel(AggParams ap, uint64_t n_records) {
@@ -323,6 +326,28 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
     cudaSetDevice(ctx->device);
     *out = nullptr;
     const int64_t n = in->nrows;
+
+    // Utf8 group key (aggregate/mod.rs:170-216): a bare string column is replaced by its dictionary ids
+    if (group_expr && group_expr->n_nodes == 1 && group_expr->nodes[0].kind == NQE_NODE_COLUMN &&
+        group_expr->nodes[0].column >= 0 && group_expr->nodes[0].column < (int)in->cols.size() &&
+        in->cols[group_expr->nodes[0].column].dtype == NQE_UTF8) {
+        const int kc = group_expr->nodes[0].column;
+        for (int a = 0; a < n_aggs; a++) // update(row) on a Utf8 argument: unimplemented!() (sum.rs:108)
+            if (aggs[a].column == kc && aggs[a].op != NQE_AGG_COUNT)
+                return nqe_fail(ctx, NQE_ERR_PANIC, "%s func for Utf8 is not supported", agg_fn_name(aggs[a].op));
+        DevColumn ids;
+        NQE_TRY(nqe_utf8_key_ids(ctx, in->cols[kc], nullptr, &ids, nullptr));
+        nqe_table view;
+        view.ctx = ctx;
+        view.nrows = in->nrows;
+        view.cols = in->cols;
+        for (auto &c : view.cols) c.owned = false;
+        view.cols[kc] = ids;
+        view.cols[kc].owned = false;
+        const int32_t rc = nqe_hash_aggregate(ctx, &view, group_expr, aggs, n_aggs, out);
+        nqe_dev_free(ctx, ids.values);
+        return rc;
+    }
 
     DevProgramSet ps;
     memset(&ps, 0, sizeof ps);

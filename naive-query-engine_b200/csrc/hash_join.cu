@@ -779,8 +779,8 @@ int32_t check_join_keys(nqe_ctx *ctx, const nqe_table *left, const nqe_table *ri
         return nqe_fail(ctx, NQE_ERR_LOGICAL, "ColumnExpr must has name or idx"); // key column not found (column.rs:53-55)
     const int ld = left->cols[lk].dtype, rd = right->cols[rk].dtype;
     // hash_join.rs:139-162 / :185-226
-    if (ld == NQE_UTF8 || rd == NQE_UTF8)
-        return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 join keys are not implemented on the CUDA path yet");
+    if (ld == NQE_UTF8 && rd == NQE_UTF8) return NQE_OK; // dictionary ids, utf8.cu
+    if (ld == NQE_UTF8 || rd == NQE_UTF8) return nqe_fail(ctx, NQE_ERR_PANIC, "join key dtypes differ (downcast_ref unwrap on None)");
     if ((ld != NQE_INT64 && ld != NQE_UINT64) || (rd != NQE_INT64 && rd != NQE_UINT64))
         return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "join key dtype must be Int64, UInt64 or Utf8");
     if (ld != rd) return nqe_fail(ctx, NQE_ERR_PANIC, "join key dtypes differ (downcast_ref unwrap on None)");
@@ -1101,6 +1101,8 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     cudaSetDevice(ctx->device);
     *out = nullptr;
     NQE_TRY(check_join_keys(ctx, left, right, left_key, right_key));
+    if (left->cols[left_key].dtype == NQE_UTF8)
+        return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "fused join+aggregate over Utf8 join keys: run nqe_hash_join, then nqe_hash_aggregate");
     const int nl = (int)left->cols.size(), nr = (int)right->cols.size();
     auto col_at = [&](int c) -> const DevColumn * {
         if (c < 0 || c >= nl + nr) return nullptr;

@@ -107,9 +107,124 @@ __global__ void utf8_copy_kernel(const int32_t *__restrict__ src_off, const uint
     for (int32_t b = 0; b < l; b++) d[b] = s[b];
 }
 
+// ---------------------------------------------------------------------------
+// Utf8 keys (hash_join.rs:146-160,205-225; aggregate/mod.rs:170-216): strings are turned into
+// 64-bit ids -- id = a row of the dictionary column that holds the same string -- and the integer
+// join / group-by kernels run on the ids.  The dictionary is an open-addressing table of row
+// numbers (claimed by CAS; the strings themselves are the immutable input, so an occupied slot can
+// always be compared), hashed with FNV-1a over the bytes.
+// ---------------------------------------------------------------------------
+constexpr unsigned long long DICT_EMPTY = ~0ull;
+constexpr unsigned long long DICT_NOMATCH = 1ull << 63; // | probe row: never equal to a dictionary row
+
+__device__ __forceinline__ uint64_t utf8_hash(const uint8_t *p, int32_t len) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (int32_t i = 0; i < len; i++) h = (h ^ p[i]) * 0x100000001b3ULL;
+    h ^= h >> 32;
+    h *= 0xd6e8feb86659fd93ULL;
+    h ^= h >> 32;
+    return h;
+}
+__device__ __forceinline__ bool utf8_eq(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb) {
+    if (la != lb) return false;
+    for (int32_t i = 0; i < la; i++)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+struct DictParams {
+    unsigned long long *slots; // row numbers of the dictionary column
+    uint64_t cap;
+    const int32_t *d_off;      // dictionary column
+    const uint8_t *d_data;
+};
+
+__global__ void dict_clear_kernel(unsigned long long *slots, uint64_t cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) slots[i] = DICT_EMPTY;
+}
+
+// INSERT: rows of the dictionary column itself (ids[i] = the row that first claimed the string);
+// !INSERT: rows of another column looked up in the finished dictionary (absent -> DICT_NOMATCH | i)
+template <bool INSERT>
+__global__ void dict_ids_kernel(DictParams dp, const int32_t *__restrict__ off, const uint8_t *__restrict__ data, int64_t n,
+                                unsigned long long *__restrict__ ids, uint32_t *status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *s = data + off[i];
+    const int32_t len = off[i + 1] - off[i];
+    uint64_t slot = __umul64hi(utf8_hash(s, len), dp.cap);
+    for (uint64_t probe = 0; probe < dp.cap; probe++) {
+        unsigned long long r = INSERT ? atomicCAS(dp.slots + slot, DICT_EMPTY, (unsigned long long)i)
+                                      : *(volatile unsigned long long *)(dp.slots + slot);
+        if (r == DICT_EMPTY) {
+            ids[i] = INSERT ? (unsigned long long)i : (DICT_NOMATCH | (unsigned long long)i);
+            return;
+        }
+        if (utf8_eq(dp.d_data + dp.d_off[r], dp.d_off[r + 1] - dp.d_off[r], s, len)) {
+            ids[i] = r;
+            return;
+        }
+        slot = slot + 1 == dp.cap ? 0 : slot + 1;
+    }
+    atomicOr(status, DEV_ERR_TABLE_FULL);
+}
+
 } // namespace
 
 // hidden row-id column 0..n-1 (owned by the caller)
+// ids of a Utf8 key column.  probe == nullptr: ids of `dict` itself (group keys, the build side of a join);
+// otherwise also the ids of `probe` looked up in dict's dictionary (the probe side of a join).
+// The id columns are UInt64 and borrow the validity bitmaps of their sources.
+int32_t nqe_utf8_key_ids(nqe_ctx *ctx, const DevColumn &dict, const DevColumn *probe, DevColumn *dict_ids, DevColumn *probe_ids) {
+    const int64_t n = dict.length;
+    DictParams dp;
+    dp.cap = (uint64_t)n * 2 + 16;
+    dp.d_off = (const int32_t *)dict.values;
+    dp.d_data = dict.data;
+    void *slots = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, dp.cap * 8));
+    dp.slots = (unsigned long long *)slots;
+    uint32_t *status = (uint32_t *)(ctx->d_scratch + 1);
+    cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+    dict_clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dp.slots, dp.cap);
+    ctx->launches++;
+    int32_t rc = NQE_OK;
+    auto make_ids = [&](const DevColumn &src, DevColumn *out, bool insert) {
+        *out = DevColumn();
+        out->dtype = NQE_UINT64;
+        out->length = src.length;
+        if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, &out->values, (size_t)(src.length > 0 ? src.length : 1) * 8);
+        if (rc != NQE_OK || src.length == 0) return;
+        const unsigned grid = (unsigned)((src.length + 255) / 256);
+        if (insert)
+            dict_ids_kernel<true><<<grid, 256, 0, ctx->stream>>>(dp, (const int32_t *)src.values, src.data, src.length,
+                                                               (unsigned long long *)out->values, status);
+        else
+            dict_ids_kernel<false><<<grid, 256, 0, ctx->stream>>>(dp, (const int32_t *)src.values, src.data, src.length,
+                                                                (unsigned long long *)out->values, status);
+        ctx->launches++;
+    };
+    make_ids(dict, dict_ids, true);
+    if (probe) make_ids(*probe, probe_ids, false);
+    if (rc == NQE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = nqe_fail(ctx, NQE_ERR_CUDA, "utf8 dictionary failed: %s", cudaGetErrorString(cudaGetLastError()));
+    nqe_dev_free(ctx, slots);
+    if (rc != NQE_OK) {
+        nqe_dev_free(ctx, dict_ids->values);
+        dict_ids->values = nullptr;
+        if (probe) { nqe_dev_free(ctx, probe_ids->values); probe_ids->values = nullptr; }
+        return rc;
+    }
+    // validity travels with the ids (group-by drops NULL keys; the join ignores it, like the reference)
+    dict_ids->validity = dict.validity;
+    dict_ids->null_count = dict.null_count;
+    if (probe) {
+        probe_ids->validity = probe->validity;
+        probe_ids->null_count = probe->null_count;
+    }
+    return NQE_OK;
+}
+
 int32_t nqe_make_rowid_column(nqe_ctx *ctx, int64_t n, DevColumn *c) {
     NQE_TRY(nqe_column_alloc(ctx, NQE_INT64, n, false, c));
     if (n > 0) {
@@ -246,10 +361,13 @@ int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_tab
     const nqe_table *side[2] = {left, right};
     const int key[2] = {left_key, right_key};
     nqe_table aug[2];
-    DevColumn rowid[2];
+    DevColumn rowid[2], keyid[2];
     std::vector<int> map[2]; // original column -> column in aug (numeric) or -1 (Utf8)
     int akey[2] = {0, 0};
     int32_t rc = NQE_OK;
+    // Utf8 keys (hash_join.rs:146-160): both sides get an id column from the build side's dictionary
+    const bool utf8_key = left->cols[left_key].dtype == NQE_UTF8;
+    if (utf8_key) rc = nqe_utf8_key_ids(ctx, left->cols[left_key], &right->cols[right_key], &keyid[0], &keyid[1]);
     for (int s = 0; s < 2 && rc == NQE_OK; s++) {
         aug[s].ctx = ctx;
         aug[s].nrows = side[s]->nrows;
@@ -260,7 +378,15 @@ int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_tab
                 aug[s].cols.push_back(borrow(side[s]->cols[c]));
             }
         }
-        akey[s] = map[s][key[s]];
+        if (utf8_key) {
+            akey[s] = (int)aug[s].cols.size();
+            DevColumn k = borrow(keyid[s]);
+            k.validity = nullptr; // key validity is ignored (hash_join.rs:67,86)
+            k.null_count = 0;
+            aug[s].cols.push_back(k);
+        } else {
+            akey[s] = map[s][key[s]];
+        }
         rc = nqe_make_rowid_column(ctx, side[s]->nrows, &rowid[s]);
         aug[s].cols.push_back(borrow(rowid[s]));
     }
@@ -288,6 +414,8 @@ int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_tab
     if (tmp) nqe_table_free(tmp);
     nqe_column_release(ctx, &rowid[0]);
     nqe_column_release(ctx, &rowid[1]);
+    for (int s = 0; s < 2; s++)
+        if (keyid[s].values) nqe_dev_free(ctx, keyid[s].values);
     if (rc != NQE_OK) {
         if (res) nqe_table_free(res);
         return rc;

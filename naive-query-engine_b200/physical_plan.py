@@ -519,9 +519,12 @@ class PhysicalAggregatePlan(PhysicalPlan):
             aggs, n = self._aggs(names)
             g = self.group_expr[0].resolve(names)
             ctx = lt.ctx
-            h = C.c_void_p()
-            ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, lt.h, rt.h, lk, rk, g, aggs, n, C.byref(h)))
-            return DeviceTable(ctx, h, out_names)
+            UTF8 = 5
+            jdt = list(lt.dtypes()) + list(rt.dtypes())
+            if lt.dtypes()[lk] != UTF8 and jdt[g] != UTF8:  # Utf8 keys go through the dictionary path, unfused
+                h = C.c_void_p()
+                ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, lt.h, rt.h, lk, rk, g, aggs, n, C.byref(h)))
+                return DeviceTable(ctx, h, out_names)
         t = inp.execute_device()
         names = t.names
         out_names = [op.data_field(names).name for op in self.aggr_ops]

@@ -688,3 +688,47 @@ def test_strings_through_filter_and_join_random():
     l = O.Batch(["id", "label"], [O.Col("i64", rng.permutation(nl).astype(np.int64)), O.col("utf8", ls)])
     r = O.Batch(["k", "s", "v"], [O.Col("i64", rng.integers(0, 400, n)), b.cols[1], b.cols[2]])
     assert G.gpu_join(l, r, "id", "k").rows() == O.hash_join(l, r, "id", "k").rows()
+
+
+# ---------------------------------------------------------------- Utf8 join keys and group keys
+def _words(rng, n, vocab, null_frac=0.0):
+    vals = np.array([vocab[i] for i in rng.integers(0, len(vocab), n)], dtype=object)
+    valid = (rng.random(n) >= null_frac).astype(np.uint8) if null_frac else None
+    if valid is not None:
+        vals[valid == 0] = ""  # an Arrow NULL string slot spans no bytes: its raw value (what a join key sees) is ""
+    return O.Col("utf8", vals, valid)
+
+
+@pytest.mark.parametrize("nl,nr,null_frac", [(0, 5, 0.0), (7, 0, 0.0), (50, 400, 0.0), (300, 2000, 0.2), (5000, 20000, 0.1)])
+def test_hash_join_utf8_keys(nl, nr, null_frac):
+    """hash_join.rs:146-160,205-225: String keys; validity ignored; probe-row-major, build rows ascending."""
+    rng = np.random.default_rng(nl + nr)
+    vocab = ["", "a", "b", "ab", "ba", "alice", "bob", "x" * 40, "zürich", "naïve"] + [f"k{i}" for i in range(max(nl // 3, 1))]
+    L = O.Batch(["name", "v"], [_words(rng, nl, vocab, null_frac), rand_col(rng, "i64", nl, null_frac)])
+    R = O.Batch(["who", "w", "tag"], [_words(rng, nr, vocab + ["absent", "nobody"], null_frac), rand_col(rng, "f64", nr),
+                                       _words(rng, nr, ["t1", "t2"])])
+    same(G.gpu_join(L, R, "name", "who"), O.hash_join(L, R, "name", "who"))
+
+
+@pytest.mark.parametrize("n,null_frac", [(0, 0.0), (1, 0.0), (1000, 0.0), (30000, 0.15)])
+def test_group_by_utf8_key(n, null_frac):
+    """aggregate/mod.rs:170-216: String group keys; NULL keys dropped; count over the string column itself."""
+    rng = np.random.default_rng(n + 3)
+    vocab = ["", "a", "b", "alice", "bob", "carol", "x" * 33] + [f"g{i}" for i in range(50)]
+    b = O.Batch(["name", "v", "x"], [_words(rng, n, vocab, null_frac), rand_col(rng, "i64", n, null_frac), rand_col(rng, "f64", n, null_frac)])
+    aggs = [("count", 0), ("count", 1), ("sum", 1), ("avg", 2), ("min", 2), ("max", 1)]
+    want = O.aggregate(b, ("col", 0), aggs)
+    got = G.gpu_aggregate(b, ("col", 0), aggs)
+    same(got, want, rel=SUM_REL, ordered=False)
+
+
+def test_utf8_key_errors():
+    rng = np.random.default_rng(9)
+    b = O.Batch(["name", "v"], [_words(rng, 10, ["a", "b"]), rand_col(rng, "i64", 10)])
+    with pytest.raises(G.nq.NqeError) as e:  # sum over a Utf8 column panics in the reference (sum.rs:108)
+        G.gpu_aggregate(b, ("col", 0), [("sum", 0)])
+    assert e.value.code == 5
+    other = O.Batch(["id", "w"], [rand_col(rng, "i64", 10), rand_col(rng, "i64", 10)])
+    with pytest.raises(G.nq.NqeError) as e:  # Utf8 key against Int64 key: downcast unwrap panics
+        G.gpu_join(b, other, "name", "id")
+    assert e.value.code == 5
