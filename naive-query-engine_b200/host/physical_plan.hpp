@@ -388,10 +388,19 @@ struct PhysicalAggregatePlan : PhysicalPlan { // aggregate/mod.rs:29-222
             auto l = join->left->execute_device(), r = join->right->execute_device();
             auto k = join->keys(*l, *r);
             const auto names = join->schema();
-            for (auto &a : aggr_ops) { aggs.push_back(nqe_agg{a.op, a.col_expr->resolve(names)}); out_names.push_back(a.field_name(names)); }
-            ctx.check(nqe_join_aggregate(ctx.get(), l->get(), r->get(), k.first, k.second, gcol->resolve(names), aggs.data(),
-                                         (int32_t)aggs.size(), &out));
-            return std::make_shared<DeviceTable>(out, out_names);
+            // Utf8 join / group keys go through the dictionary path of nqe_hash_join / nqe_hash_aggregate, unfused
+            auto dtype_at = [&](int c) {
+                nqe_column_desc d;
+                const int nl = nqe_table_num_columns(l->get());
+                nqe_table_column(c < nl ? l->get() : r->get(), c < nl ? c : c - nl, &d);
+                return d.dtype;
+            };
+            if (dtype_at(k.first) != NQE_UTF8 && dtype_at(gcol->resolve(names)) != NQE_UTF8) {
+                for (auto &a : aggr_ops) { aggs.push_back(nqe_agg{a.op, a.col_expr->resolve(names)}); out_names.push_back(a.field_name(names)); }
+                ctx.check(nqe_join_aggregate(ctx.get(), l->get(), r->get(), k.first, k.second, gcol->resolve(names), aggs.data(),
+                                             (int32_t)aggs.size(), &out));
+                return std::make_shared<DeviceTable>(out, out_names);
+            }
         }
         auto t = input->execute_device();
         for (auto &a : aggr_ops) { aggs.push_back(nqe_agg{a.op, a.col_expr->resolve(t->names())}); out_names.push_back(a.field_name(t->names())); }

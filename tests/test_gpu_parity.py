@@ -150,6 +150,28 @@ def test_filter_project_many_tiles(n, k):
         assert np.array_equal(got.column(i).to_numpy(zero_copy_only=False), want[i]), f"column {i}"
 
 
+@pytest.mark.parametrize("ncols", [6, 12, 16])
+def test_filter_project_wide_table(ncols):
+    """Many referenced columns: the two-ring kernel shrinks its tile (K = 8 -> 4 -> 2 -> 1) so that both rings still
+    leave room for two CTAs per SM; every column is projected, half of them through an expression."""
+    import pyarrow as pa
+    from importlib import import_module
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    rng = np.random.default_rng(ncols)
+    n = 150_001
+    cols = [rng.integers(-1000, 1000, n).astype(np.int64) for _ in range(ncols)]
+    rb = pa.RecordBatch.from_arrays([pa.array(c) for c in cols], names=[f"c{i}" for i in range(ncols)])
+    src = G.nq.ScanPlan.create(G.nq.MemTable.try_create(rb.schema, [rb]), None).execute_device()
+    pred = G.expr(("bin", "Lt", ("col", 0), lit(300)))
+    exprs = [G.expr(("col", i) if i % 2 == 0 else ("bin", "Plus", ("col", i), lit(i))) for i in range(ncols)]
+    got = pp._filter_project(src, pred, exprs, [f"o{i}" for i in range(ncols)]).to_arrow()
+    m = cols[0] < 300
+    assert got.num_rows == int(m.sum())
+    for i in range(ncols):
+        want = cols[i][m] if i % 2 == 0 else cols[i][m] + i
+        assert np.array_equal(got.column(i).to_numpy(), want), f"column {i}"
+
+
 def test_filter_project_full_size_config():
     """BASELINE configs[1] at full size (1e8 rows generated in HBM): exact equality with the host-side generator."""
     import torch
