@@ -437,6 +437,10 @@ std::map<std::string, CachedKernel> &cache() {
     static std::map<std::string, CachedKernel> c;
     return c;
 }
+std::map<std::string, CachedKernel> &shape_cache() { // query shape -> kernel, in front of the source-text cache
+    static std::map<std::string, CachedKernel> c;
+    return c;
+}
 std::mutex &cache_mutex() {
     static std::mutex m;
     return m;
@@ -547,6 +551,31 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         const char *e = getenv("NQE_JIT_L2_HINTS");
         HINTS = e ? atoi(e) : 0; // measured: no gain on B200 (profiles/README_r01.md)
     }
+    // ---- shape key: everything the generated source depends on.  A hit skips source generation altogether
+    // (~40 us of string work per call, which would otherwise sit in front of every launch).
+    std::string shape_key;
+    {
+        std::ostringstream k;
+        k << tma << ',' << tk << ',' << sp << ',' << sw << ',' << LAG << ',' << WALKERS << ',' << lbw << ',' << prof << ',' << CK << ','
+          << D << ',' << HINTS << ',' << (predicate ? 1 : 0) << ',' << n_pred_cols << ',' << pred_root << ';';
+        for (size_t sl = 0; sl < n_slots; sl++) k << in->cols[g.col_of_slot[sl]].dtype << (g.in_proj[sl] ? 'p' : '-');
+        k << ';';
+        for (const TNode &t : g.nodes) k << t.kind << '.' << t.op << '.' << t.dtype << '.' << t.col << '.' << t.lit << '.' << t.left << '.' << t.right << ' ';
+        k << ';';
+        for (int r : roots) k << r << ' ';
+        shape_key = k.str();
+    }
+    CachedKernel ck;
+    bool have = false;
+    if (!source_out) {
+        std::lock_guard<std::mutex> lock(cache_mutex());
+        auto it = shape_cache().find(shape_key);
+        if (it != shape_cache().end()) {
+            ck = it->second;
+            have = true;
+        }
+    }
+    if (!have) {
     std::vector<size_t> all_slots, pred_slots, proj_slots;
     for (size_t s = 0; s < n_slots; s++) {
         all_slots.push_back(s);
@@ -647,7 +676,6 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     }
 
     // ---- compile (cached per source text)
-    CachedKernel ck;
     {
         std::lock_guard<std::mutex> lock(cache_mutex());
         auto it = cache().find(source);
@@ -685,6 +713,11 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
             }
             cache()[source] = ck;
         }
+    }
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex());
+        shape_cache()[shape_key] = ck;
+    }
     }
     if (ck.failed) return NQE_OK; // interpreter kernels take over
 
