@@ -227,9 +227,9 @@ struct PartJoin {
     const unsigned long long *keys; // probe keys, original order
     int64_t n;
     int32_t log2p;
-    int32_t num_tiles;              // tiles of HJ_K * HJ_THREADS rows
-    unsigned int *tile_cnt;         // [num_tiles][P]: rows of the tile per partition
-    unsigned int *tile_off;         // [num_tiles][P]: rows of that partition in earlier tiles
+    int32_t num_tiles;              // tiles of PJ_K * HJ_THREADS rows
+    unsigned int *tile_cnt;         // [P][num_tiles]: rows of the tile per partition
+    unsigned int *tile_off;         // [P][num_tiles]: rows of that partition in earlier tiles
     unsigned long long *part_base;  // [P + 1]: first position of the partition in the partitioned order
     unsigned long long *pkeys;      // keys in partitioned order
     unsigned int *ppos32;           // per probe row (original order): its position in the partitioned order
@@ -238,43 +238,57 @@ struct PartJoin {
     unsigned int *mbits;            // fat: match bit per position
 };
 
+// streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
+// probed (default policy) is what stays resident
+__device__ __forceinline__ unsigned long long pj_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ld_ef(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_ef(unsigned long long *p, unsigned long long v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ int pj_part(unsigned long long key, int log2p) {
     return log2p ? (int)(nqe_mix64(key) >> (64 - log2p)) : 0;
 }
-// lanes of the warp that are live and in the same partition as this lane
-__device__ __forceinline__ unsigned pj_same_mask(int pid, bool live, int log2p) {
-    unsigned m = __ballot_sync(0xffffffffu, live);
-    for (int b = 0; b < log2p; b++) {
-        const unsigned bb = __ballot_sync(0xffffffffu, (pid >> b) & 1);
-        m &= ((pid >> b) & 1) ? bb : ~bb;
-    }
-    return m;
-}
 
-// Per-(j, warp) partition histograms of one tile in shared memory (row order inside a tile is
-// j major, warp minor, lane).  Every thread of the CTA calls this; s_c is zeroed here.
+constexpr int PJ_K = 8; // rows per thread in the split passes: 2048-row tiles
+
+// Warp-level partition histogram of K row groups (32 rows each) from log2p ballot bit-planes:
+//   rank[j]   = number of lower lanes of this row group in the same partition as this lane's row
+//   cnt[j]    = rows of this row group that fall into partition `lane`   (lane < 2^log2p)
+// No shared memory and no atomics; row order inside a tile is j major, warp minor, lane.
 template <int K>
-__device__ __forceinline__ void pj_tile_hist(const unsigned long long (&key)[K], uint32_t inrange, int log2p,
-                                             unsigned short (*s_c)[PJ_MAX_PARTS], int (&pid)[K], unsigned (&rank)[K]) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < K * HJ_WARPS * PJ_MAX_PARTS; i += HJ_THREADS) (&s_c[0][0])[i] = 0;
-    __syncthreads();
+__device__ __forceinline__ void pj_warp_hist(const unsigned long long (&key)[K], uint32_t inrange, int log2p, int (&pid)[K],
+                                             unsigned (&rank)[K], unsigned (&cnt)[K]) {
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < K; j++) {
         const bool live = (inrange >> j) & 1u;
         pid[j] = pj_part(key[j], log2p);
-        const unsigned m = pj_same_mask(pid[j], live, log2p);
-        rank[j] = __popc(m & ((1u << lane) - 1u));
-        if (live && rank[j] == 0) s_c[j * HJ_WARPS + warp][pid[j]] = (unsigned short)__popc(m);
+        unsigned own = __ballot_sync(0xffffffffu, live), bucket = own;
+        for (int b = 0; b < log2p; b++) {
+            const unsigned bb = __ballot_sync(0xffffffffu, (pid[j] >> b) & 1);
+            own &= ((pid[j] >> b) & 1) ? bb : ~bb;
+            bucket &= ((lane >> b) & 1) ? bb : ~bb;
+        }
+        rank[j] = __popc(own & ltmask);
+        cnt[j] = __popc(bucket);
     }
-    __syncthreads();
 }
 
-// pass 1: per-tile partition counts (+ partition totals)
+// pass 1: per-tile partition counts (+ partition totals).  tile_cnt is partition-major: [p][tile].
 __global__ void __launch_bounds__(HJ_THREADS) pj_count_kernel(PartJoin pj, unsigned long long *totals) {
-    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
-    __shared__ unsigned short s_c[K * HJ_WARPS][PJ_MAX_PARTS];
-    const int tid = threadIdx.x, P = 1 << pj.log2p;
+    constexpr int K = PJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned int s_w[HJ_WARPS][PJ_MAX_PARTS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, P = 1 << pj.log2p;
     unsigned long long mine = 0;
     for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TILE + tid;
@@ -287,25 +301,31 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_count_kernel(PartJoin pj, unsig
             if (e < pj.n) inrange |= 1u << j;
         }
         int pid[K];
-        unsigned rank[K];
-        pj_tile_hist<K>(key, inrange, pj.log2p, s_c, pid, rank);
-        if (tid < P) {
-            unsigned c = 0;
+        unsigned rank[K], cnt[K], c = 0;
+        pj_warp_hist<K>(key, inrange, pj.log2p, pid, rank, cnt);
 #pragma unroll
-            for (int i = 0; i < K * HJ_WARPS; i++) c += s_c[i][tid];
-            pj.tile_cnt[(size_t)tile * P + tid] = c;
-            mine += c;
+        for (int j = 0; j < K; j++) c += cnt[j];
+        s_w[warp][lane] = c;
+        __syncthreads();
+        if (tid < P) {
+            unsigned t = 0;
+#pragma unroll
+            for (int w = 0; w < HJ_WARPS; w++) t += s_w[w][tid];
+            pj.tile_cnt[(size_t)tid * pj.num_tiles + tile] = t;
+            mine += t;
         }
         __syncthreads();
     }
     if (tid < P && mine) atomicAdd(totals + tid, mine);
 }
 
-// pass 2: one CTA per partition: exclusive scan of its per-tile counts; partition bases
+// pass 2: one CTA per partition: exclusive scan of its per-tile counts (contiguous); partition bases
 __global__ void __launch_bounds__(1024) pj_scan_kernel(PartJoin pj, const unsigned long long *totals) {
     __shared__ unsigned int s_w[32];
     __shared__ unsigned int s_carry;
     const int p = blockIdx.x, P = 1 << pj.log2p, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int *cnt = pj.tile_cnt + (size_t)p * pj.num_tiles;
+    unsigned int *off = pj.tile_off + (size_t)p * pj.num_tiles;
     if (tid == 0) {
         unsigned long long b = 0;
         for (int q = 0; q < p; q++) b += totals[q];
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(1024) pj_scan_kernel(PartJoin pj, const unsign
     __syncthreads();
     for (int t0 = 0; t0 < pj.num_tiles; t0 += 1024) {
         const int t = t0 + tid;
-        const unsigned v = t < pj.num_tiles ? pj.tile_cnt[(size_t)t * P + p] : 0u;
+        const unsigned v = t < pj.num_tiles ? cnt[t] : 0u;
         unsigned incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -337,85 +357,66 @@ __global__ void __launch_bounds__(1024) pj_scan_kernel(PartJoin pj, const unsign
         }
         __syncthreads();
         const unsigned carry = s_carry;
-        if (t < pj.num_tiles) pj.tile_off[(size_t)t * P + p] = carry + s_w[warp] + incl - v;
+        if (t < pj.num_tiles) off[t] = carry + s_w[warp] + incl - v;
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_w[warp] + incl;
         __syncthreads();
     }
 }
 
-// position of this thread's K rows in the partitioned order (all threads of the CTA call this)
-template <int K>
-__device__ __forceinline__ void pj_positions(const PartJoin &pj, int tile, const unsigned long long (&key)[K], uint32_t inrange,
-                                             unsigned short (*s_c)[PJ_MAX_PARTS], unsigned long long (&ppos)[K]) {
-    const int tid = threadIdx.x, warp = tid >> 5, P = 1 << pj.log2p;
-    int pid[K];
-    unsigned rank[K];
-    pj_tile_hist<K>(key, inrange, pj.log2p, s_c, pid, rank);
-    if (tid < P) { // exclusive prefix over the (j, warp) pairs, per partition
-        unsigned run = 0;
-#pragma unroll
-        for (int i = 0; i < K * HJ_WARPS; i++) {
-            const unsigned c = s_c[i][tid];
-            s_c[i][tid] = (unsigned short)run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < K; j++)
-        ppos[j] = pj.part_base[pid[j]] + pj.tile_off[(size_t)tile * P + pid[j]] + s_c[j * HJ_WARPS + warp][pid[j]] + rank[j];
-    __syncthreads(); // s_c is reused by the next tile
-}
-
-// pass 3: stable split of the probe keys
+// pass 3: stable split of the probe keys; every row also remembers its position in the partitioned order
 __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
-    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    constexpr int K = PJ_K, TILE = K * HJ_THREADS;
     __shared__ unsigned short s_c[K * HJ_WARPS][PJ_MAX_PARTS];
-    const int tid = threadIdx.x;
+    __shared__ unsigned long long s_base[PJ_MAX_PARTS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, P = 1 << pj.log2p;
+    const unsigned long long pol = pj_policy();
     for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TILE + tid;
-        unsigned long long key[K], ppos[K];
+        unsigned long long key[K];
         uint32_t inrange = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            key[j] = e < pj.n ? ld_stream_u64(pj.keys + e) : 0ull;
+            key[j] = e < pj.n ? ld_ef(pj.keys + e, pol) : 0ull;
             if (e < pj.n) inrange |= 1u << j;
         }
-        pj_positions<K>(pj, tile, key, inrange, s_c, ppos);
+        int pid[K];
+        unsigned rank[K], cnt[K];
+        pj_warp_hist<K>(key, inrange, pj.log2p, pid, rank, cnt);
+#pragma unroll
+        for (int j = 0; j < K; j++) s_c[j * HJ_WARPS + warp][lane] = (unsigned short)cnt[j];
+        if (tid < P) s_base[tid] = pj.part_base[tid] + pj.tile_off[(size_t)tid * pj.num_tiles + tile];
+        __syncthreads();
+        if (tid < P) { // exclusive prefix over the (j, warp) pairs, per partition
+            unsigned run = 0;
+#pragma unroll
+            for (int i = 0; i < K * HJ_WARPS; i++) {
+                const unsigned c = s_c[i][tid];
+                s_c[i][tid] = (unsigned short)run;
+                run += c;
+            }
+        }
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < K; j++)
             if ((inrange >> j) & 1u) {
-                pj.pkeys[ppos[j]] = key[j];
-                pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos[j];
+                const unsigned long long ppos = s_base[pid[j]] + s_c[j * HJ_WARPS + warp][pid[j]] + rank[j];
+                st_ef(pj.pkeys + ppos, key[j], pol);
+                pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos;
             }
+        __syncthreads(); // s_c / s_base are reused by the next tile
     }
 }
 
-// streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
-// probed (default policy) is what stays resident
-__device__ __forceinline__ unsigned long long pj_policy() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ unsigned long long ld_ef(const unsigned long long *p, unsigned long long pol) {
-    unsigned long long v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void st_ef(unsigned long long *p, unsigned long long v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
-
 // pass 4: probe in partitioned order (partition after partition, so one slot range of the table is hot in L2)
-template <bool FAT>
+template <bool FAT, int K>
 __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinTable jt) {
-    constexpr int K = HJ_K, TILE = K * HJ_THREADS;
+    constexpr int TILE = K * HJ_THREADS;
     const int tid = threadIdx.x;
     const unsigned long long pol = pj_policy();
-    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+    const int64_t num_tiles = (pj.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TILE + tid;
         unsigned long long key[K], brow[K];
         uint64_t slot[K];
@@ -900,8 +901,8 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             pj.keys = pp.probe_keys;
             pj.n = pp.n_probe;
             pj.log2p = log2p;
-            pj.num_tiles = pp.num_tiles;
-            const size_t P = (size_t)1 << log2p, nt = (size_t)pp.num_tiles;
+            pj.num_tiles = (int32_t)((pp.n_probe + 2048 - 1) / 2048); // PJ_K * HJ_THREADS rows per tile
+            const size_t P = (size_t)1 << log2p, nt = (size_t)pj.num_tiles;
             auto alloc = [&](void **p, size_t bytes) {
                 if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
                 if (rc == NQE_OK) pj_bufs.push_back(*p);
@@ -919,12 +920,18 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             if (rc == NQE_OK) {
                 cudaMemsetAsync(totals, 0, P * 8, ctx->stream);
                 int grid = ctx->sm_count * 8;
-                if (grid > pp.num_tiles) grid = pp.num_tiles;
+                if (grid > pj.num_tiles) grid = pj.num_tiles;
                 pj_count_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, (unsigned long long *)totals);
                 pj_scan_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(pj, (const unsigned long long *)totals);
                 pj_scatter_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj);
-                if (fat) pj_probe_kernel<true><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
-                else pj_probe_kernel<false><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                static int probe_k = 0; // knob NQE_JOIN_PROBE_K: independent probes in flight per thread
+                if (!probe_k) {
+                    const char *e = getenv("NQE_JOIN_PROBE_K");
+                    probe_k = e && atoi(e) == 8 ? 8 : 4;
+                }
+                if (fat) pj_probe_kernel<true, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                else if (probe_k == 8) pj_probe_kernel<false, 8><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                else pj_probe_kernel<false, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
                 ctx->launches += 4;
                 if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partitioned probe launch failed");
                 part = true;

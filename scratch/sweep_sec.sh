@@ -1,7 +1,5 @@
 #!/bin/bash
-run() { timeout 120 env "$@" WHICH=join,ja python scratch/exp_sec.py 2>&1 | tail -2; echo "   ^ $@"; }
+run() { timeout 120 env "$@" WHICH=join python scratch/exp_sec.py 2>&1 | tail -1; echo "   ^ $@"; }
 run X=1
-run NQE_JOIN_PART=0
-run NQE_JOIN_PART=0 NQE_JOIN_FAT=1
-run NQE_JOIN_FAT=1 NQE_JOIN_PART_MB=40
-run NQE_JOIN_PART_MB=12
+run NQE_JOIN_PROBE_K=8
+WHICH=join REPS=2 scratch/launchlist.sh 12 9 python scratch/exp_sec.py 2>&1 | tail -9
