@@ -236,6 +236,9 @@ struct PartJoin {
     unsigned long long *res0;       // per position: thin = build row (EMPTY_ROW: no match), fat = payload word 0
     unsigned long long *res1;       // fat, two payload columns: payload word 1
     unsigned int *mbits;            // fat: match bit per position
+    int32_t n_carry, pad;           // probe-side columns that travel with the keys (fused join -> aggregate)
+    const unsigned long long *carry_src[8];
+    unsigned long long *carry_dst[8];
 };
 
 // streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
@@ -403,7 +406,9 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
             if ((inrange >> j) & 1u) {
                 const unsigned long long ppos = s_base[pid[j]] + s_c[j * HJ_WARPS + warp][pid[j]] + rank[j];
                 st_ef(pj.pkeys + ppos, key[j], pol);
-                pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos;
+                if (pj.ppos32) pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos;
+                for (int c = 0; c < pj.n_carry; c++)
+                    st_ef(pj.carry_dst[c] + ppos, ld_ef(pj.carry_src[c] + e0 + (int64_t)j * HJ_THREADS, pol), pol);
             }
         __syncthreads(); // s_c / s_base are reused by the next tile
     }
@@ -1158,6 +1163,82 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     }
     jp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
     jp.n_probe = right->nrows;
+    // ---- partitioned probe (see "Partitioned probe" above), EXPERIMENTAL for the fused path (NQE_JOINAGG_PART=1):
+    // the probe keys and the probe-side columns the aggregates read are split stably by slot range and the fused
+    // kernel sweeps them partition after partition.  Measured (profiles/README_r01.md): the slot reads become L2
+    // hits (DRAM reads 21 GB -> 4 GB) but the fused kernel stays at ~4.9 ms -- at 122 registers (2 CTAs/SM) it is
+    // bound by the latency of its dependent L2 accesses, not by DRAM -- so with the split passes on top the
+    // direct probe is still faster end to end and remains the default.
+    std::vector<void *> pj_bufs;
+    if (rc == NQE_OK) {
+        static int allow_part = -1;
+        static size_t l2_budget = 0;
+        if (allow_part < 0) {
+            const char *e = getenv("NQE_JOINAGG_PART");
+            allow_part = e ? atoi(e) : 0;
+            e = getenv("NQE_JOIN_PART_MB");
+            l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
+        }
+        const size_t table_bytes = (size_t)(jp.jt.cap << jp.jt.shift) * 8;
+        bool ok = allow_part && !jp.jt.has_dups && jp.n_probe >= (1 << 22) && jp.n_probe < ((int64_t)1 << 32) &&
+                  table_bytes > 2 * l2_budget;
+        // probe-side columns the kernel reads: NULL-free 8-byte columns, at most 8 distinct
+        std::vector<const void *> srcs;
+        auto want = [&](const ColSrc &c) {
+            if (c.validity || c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) { ok = false; return; }
+            for (const void *p : srcs)
+                if (p == c.values) return;
+            srcs.push_back(c.values);
+        };
+        for (int a = 0; a < n_aggs && ok; a++)
+            if (!jp.val_left[a]) want(jp.val[a]);
+        if (ok && !jp.group_left) want(jp.group);
+        if (srcs.size() > 8) ok = false;
+        if (ok) {
+            PartJoin pj;
+            memset(&pj, 0, sizeof pj);
+            int log2p = 1;
+            while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
+            pj.keys = jp.probe_keys;
+            pj.n = jp.n_probe;
+            pj.log2p = log2p;
+            pj.num_tiles = (int32_t)((jp.n_probe + 2048 - 1) / 2048);
+            const size_t P = (size_t)1 << log2p, nt = (size_t)pj.num_tiles;
+            auto alloc = [&](void **p, size_t bytes) {
+                if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
+                if (rc == NQE_OK) pj_bufs.push_back(*p);
+            };
+            void *totals = nullptr;
+            alloc((void **)&pj.tile_cnt, nt * P * 4);
+            alloc((void **)&pj.tile_off, nt * P * 4);
+            alloc((void **)&pj.part_base, (P + 1) * 8);
+            alloc(&totals, P * 8);
+            alloc((void **)&pj.pkeys, (size_t)jp.n_probe * 8);
+            pj.n_carry = (int)srcs.size();
+            for (int c = 0; c < pj.n_carry; c++) {
+                pj.carry_src[c] = (const unsigned long long *)srcs[c];
+                alloc((void **)&pj.carry_dst[c], (size_t)jp.n_probe * 8);
+            }
+            if (rc == NQE_OK) {
+                cudaMemsetAsync(totals, 0, P * 8, ctx->stream);
+                int grid = ctx->sm_count * 8;
+                if (grid > pj.num_tiles) grid = pj.num_tiles;
+                pj_count_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, (unsigned long long *)totals);
+                pj_scan_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(pj, (const unsigned long long *)totals);
+                pj_scatter_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj);
+                ctx->launches += 3;
+                // the fused kernel now reads the partitioned copies
+                auto moved = [&](ColSrc &c) {
+                    for (int q = 0; q < pj.n_carry; q++)
+                        if (c.values == (const void *)pj.carry_src[q]) { c.values = pj.carry_dst[q]; return; }
+                };
+                jp.probe_keys = pj.pkeys;
+                for (int a = 0; a < n_aggs; a++)
+                    if (!jp.val_left[a]) moved(jp.val[a]);
+                if (!jp.group_left) moved(jp.group);
+            }
+        }
+    }
     nqe_table *t;
     nqe_table_new(ctx, 0, &t);
     // groups come from one column of one side: at most that side's row count
@@ -1190,6 +1271,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     timer.stop();
     nqe_dev_free(ctx, ap.table);
     nqe_dev_free(ctx, jp.jt.words);
+    for (void *p : pj_bufs) nqe_dev_free(ctx, p);
     if (rc != NQE_OK) {
         nqe_table_free(t);
         return rc;

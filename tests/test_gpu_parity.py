@@ -378,6 +378,50 @@ def test_hash_join_partitioned_probe_large(n_pay):
     assert np.array_equal(got.column(2 + n_pay).to_numpy(), b[m])
 
 
+@pytest.mark.parametrize("group_side", ["build", "probe"])
+def test_join_aggregate_partitioned_large(group_side):
+    """Fused join -> group-by with a build table larger than the L2 budget; 30 % of the probe rows find no match.
+    (With NQE_JOINAGG_PART=1 in the environment this exercises the radix-partitioned variant of the fused path.)"""
+    import ctypes as C
+    import pyarrow as pa
+    rng = np.random.default_rng(5)
+    nl, nr, g = 2_000_000, 5_000_011, 777
+    keys = rng.permutation(np.arange(1, 3 * nl + 1, dtype=np.int64))[:nl] * 1_000_003
+    a = rng.integers(0, g, nl).astype(np.int64)
+    pick = rng.integers(0, nl, nr)
+    hit = rng.random(nr) < 0.7
+    fk = np.where(hit, keys[pick], rng.integers(1, 1 << 50, nr) * 2 + 7).astype(np.int64)
+    b = np.round(rng.normal(0, 10, nr), 3)
+    c = rng.integers(0, g, nr).astype(np.int64)
+    L = pa.RecordBatch.from_arrays([pa.array(keys), pa.array(a)], names=["k", "a"])
+    R = pa.RecordBatch.from_arrays([pa.array(fk), pa.array(b), pa.array(c)], names=["fk", "b", "c"])
+    nq = G.nq
+    lt = nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None).execute_device()
+    rt = nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None).execute_device()
+    gcol = 1 if group_side == "build" else 4  # joined schema: k, a, fk, b, c
+    aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(o, col) for o, col in [(3, gcol), (0, 3), (1, 3), (3, 3), (4, 3)]])
+    h = C.c_void_p()
+    ctx = lt.ctx
+    ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, lt.h, rt.h, 0, 0, gcol, aggs, 5, C.byref(h)))
+    out = nq.DeviceTable(ctx, h, ["key", "count", "sum", "min", "max"]).to_arrow()
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    idx = np.minimum(np.searchsorted(sk, fk), nl - 1)
+    m = sk[idx] == fk
+    grp = a[order[idx[m]]] if group_side == "build" else c[m]
+    bv = b[m]
+    key = out.column(0).to_numpy().astype(np.int64)
+    o = np.argsort(key)
+    present = np.unique(grp)
+    assert np.array_equal(key[o], present)
+    cnt = np.bincount(grp, minlength=g)[present]
+    assert np.array_equal(out.column(1).to_numpy()[o], cnt.astype(np.uint64))
+    assert np.allclose(out.column(2).to_numpy()[o], np.bincount(grp, weights=bv, minlength=g)[present], rtol=SUM_REL, atol=1e-6)
+    mn = np.full(g, np.inf); mx = np.full(g, -np.inf)
+    np.minimum.at(mn, grp, bv); np.maximum.at(mx, grp, bv)
+    assert np.array_equal(out.column(3).to_numpy()[o], mn[present]) and np.array_equal(out.column(4).to_numpy()[o], mx[present])
+
+
 def test_hash_join_unique_build_keys_and_u64():
     rng = np.random.default_rng(9)
     nl, nr = 10_000, 50_000
