@@ -58,31 +58,31 @@ struct RowSource {
 // program 0 of ps = group key expression.  SIMPLE: the key is a bare NULL-free column and no
 // argument column has a validity bitmap (the BASELINE shape): keys and values are streamed with
 // plain coalesced loads, no interpreter.
-template <bool SIMPLE>
-__global__ void __launch_bounds__(AG_THREADS, SIMPLE ? 4 : 3)
+template <bool SIMPLE, int AGK>
+__global__ void __launch_bounds__(AG_THREADS, SIMPLE ? (AGK <= 2 ? 6 : AGK <= 4 ? 4 : 2) : 3)
 group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_constant__ AggParams ap, int key_slot) {
-    constexpr int TILE = AG_K * AG_THREADS;
+    constexpr int TILE = AGK * AG_THREADS;
     const int64_t num_tiles = (ap.n_rows + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * TILE + threadIdx.x;
         uint32_t inrange = 0;
 #pragma unroll
-        for (int j = 0; j < AG_K; j++)
+        for (int j = 0; j < AGK; j++)
             if (e0 + (int64_t)j * AG_THREADS < ap.n_rows) inrange |= 1u << j;
-        RowRegs<AG_K> key;
+        RowRegs<AGK> key;
         if (SIMPLE) {
             const uint64_t *kc = (const uint64_t *)ps.cols[key_slot].values;
 #pragma unroll
-            for (int j = 0; j < AG_K; j++) key.v[j] = ((inrange >> j) & 1u) ? ld_stream_u64(kc + e0 + (int64_t)j * AG_THREADS) : 0ull;
+            for (int j = 0; j < AGK; j++) key.v[j] = ((inrange >> j) & 1u) ? ld_stream_u64(kc + e0 + (int64_t)j * AG_THREADS) : 0ull;
             key.valid = inrange;
         } else {
-            run_program<AG_K>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
+            run_program<AGK>(ps, 0, e0, AG_THREADS, inrange, inrange, 0u, key, ap.status);
         }
-        unsigned long long *rec[AG_K];
-        Sector0 s0[AG_K];
-        find_slots<AG_K>(ap, key.v, key.valid, rec, s0); // NULL keys are dropped (valid bit clear)
+        unsigned long long *rec[AGK];
+        Sector0 s0[AGK];
+        find_slots<AGK>(ap, key.v, key.valid, rec, s0); // NULL keys are dropped (valid bit clear)
 #pragma unroll
-        for (int j = 0; j < AG_K; j++)
+        for (int j = 0; j < AGK; j++)
             if (rec[j]) update_states(ap, rec[j], s0[j], RowSource<SIMPLE>{ps, e0 + (int64_t)j * AG_THREADS});
     }
 }
@@ -446,11 +446,20 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             rc = nqe_agg_table_create(ctx, &ap, capacity);
             if (rc != NQE_OK) break;
             if (n > 0) {
-                const int64_t tiles = (n + AG_K * AG_THREADS - 1) / (AG_K * AG_THREADS);
+                static int agk = 0; // knob NQE_AGG_K: rows per thread of the fast path (2, 4 or 8)
+                if (!agk) {
+                    const char *e = getenv("NQE_AGG_K");
+                    agk = e ? atoi(e) : 4;
+                    if (agk != 2 && agk != 8) agk = 4;
+                }
+                const int kk = simple ? agk : AG_K;
+                const int64_t tiles = (n + kk * AG_THREADS - 1) / (kk * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                if (simple) group_aggregate_kernel<true><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
-                else group_aggregate_kernel<false><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, 0);
+                if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
+                else if (simple && agk == 8) group_aggregate_kernel<true, 8><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
+                else if (simple) group_aggregate_kernel<true, 4><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
+                else group_aggregate_kernel<false, AG_K><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, 0);
                 ctx->launches++;
             }
             rc = read_scratch(ctx, 2);
