@@ -662,7 +662,11 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
            : K == 4 ? launch_fp<4>(ctx, predicate != nullptr, ps, fp)
                     : launch_fp<8>(ctx, predicate != nullptr, ps, fp);
     int64_t out_rows = n;
+    bool needs_pack = false; // bitmaps for Boolean outputs / validity are packed by a second kernel: keep it inside the timer
+    for (int i = 0; i < n_projs; i++)
+        if (bool_bytes[i] || valid_bytes[i]) needs_pack = true;
     if (rc == NQE_OK) {
+        if (!needs_pack) timer.mark_end();
         cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = nqe_fail(ctx, NQE_ERR_CUDA, "filter_project kernel failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -91,9 +91,18 @@ struct OpTimer {
     explicit OpTimer(nqe_ctx *c) : ctx(c) {
         if (c->timer_depth++ == 0) cudaEventRecord(c->ev0, c->stream);
     }
+    bool marked = false;
+    // end of the timed kernels, recorded without blocking: a caller that synchronises the stream anyway
+    // (to read back a row count) marks first, so that stop() finds the event complete
+    void mark_end() {
+        if (ctx->timer_depth == 1 && !marked) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            marked = true;
+        }
+    }
     void stop() {
         if (--ctx->timer_depth > 0) return;
-        cudaEventRecord(ctx->ev1, ctx->stream);
+        if (!marked) cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

@@ -78,10 +78,18 @@ class PhysicalExpr:
         raise NotImplementedError
 
     def to_expr(self, names: Sequence[str]) -> Tuple[Expr, object]:
+        """Postfix lowering for the C ABI.  Expression trees are immutable after create(), so the lowered form
+        is kept per input schema (a plan node is usually executed against the same schema every time)."""
+        key = tuple(names)
+        cached = getattr(self, "_lowered", None)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
         nodes: List[ExprNode] = []
         self.lower(names, nodes)
         arr = (ExprNode * len(nodes))(*nodes)
-        return Expr(arr, len(nodes), 0), arr
+        ex = Expr(arr, len(nodes), 0)
+        self._lowered = (key, ex, arr)
+        return ex, arr
 
     def evaluate(self, batch) -> pa.Array:
         """PhysicalExpr::evaluate(&RecordBatch).into_array() -- runs on the GPU."""
