@@ -538,9 +538,9 @@ int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *
 }
 
 int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
-                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
-                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
-                               std::string *source_out);
+                               int32_t n_projs, void *const *out_values, uint8_t *const *out_valid,
+                               unsigned long long *tile_state, unsigned int *ticket, unsigned long long *out_count,
+                               uint32_t *status, bool *used, std::string *source_out);
 
 int32_t nqe_filter_project_strings(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
                                    int32_t n_projs, const int *utf8_src, nqe_table **out);
@@ -654,8 +654,13 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
     }
     OpTimer timer(ctx);
     bool jit_used = false;
-    if (rc == NQE_OK && !ps.any_nulls) // query-shape specialised kernel (jit.cu); falls through when not applicable
-        rc = nqe_jit_filter_project(ctx, in, predicate, projs, n_projs, fp.out_values, fp.tile_state, fp.ticket,
+    static int jit_nulls = -1; // knob NQE_JIT_NULLS=0: nullable inputs go to the interpreter kernels
+    if (jit_nulls < 0) {
+        const char *e = getenv("NQE_JIT_NULLS");
+        jit_nulls = e ? atoi(e) : 1;
+    }
+    if (rc == NQE_OK && (!ps.any_nulls || jit_nulls)) // query-shape specialised kernel (jit.cu); falls through when not applicable
+        rc = nqe_jit_filter_project(ctx, in, predicate, projs, n_projs, fp.out_values, fp.out_valid, fp.tile_state, fp.ticket,
                                     fp.out_count, fp.status, &jit_used, nullptr);
     if (rc == NQE_OK && !jit_used)
         rc = K == 2 ? launch_fp<2>(ctx, predicate != nullptr, ps, fp)

@@ -9,6 +9,9 @@
 // PCIe directions are busy at once, and the filter kernel hides under the copies.  Row order is
 // preserved: chunks are contiguous row ranges and their results are appended in order.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -16,7 +19,17 @@
 
 namespace {
 
-constexpr int64_t CHUNK_ROWS = 8 << 20; // 64 MiB per 8-byte column: ~1.2 ms of PCIe gen5 per column
+// rows per pipeline chunk; default 8 Mi = 64 MiB per 8-byte column: ~1.2 ms of PCIe gen5 per column
+// (knob NQE_HOST_CHUNK_ROWS, rounded down to a multiple of 2048)
+int64_t chunk_rows() {
+    static int64_t v = 0;
+    if (!v) {
+        const char *e = getenv("NQE_HOST_CHUNK_ROWS");
+        v = e ? atoll(e) : (int64_t)8 << 20;
+        v = std::max<int64_t>(1 << 16, v & ~(int64_t)2047);
+    }
+    return v;
+}
 
 void referenced_columns(const nqe_expr *e, std::vector<char> &used) {
     if (!e) return;
@@ -41,7 +54,9 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
                                            int64_t *out_rows) {
     if (!ctx || !cols || n_cols <= 0 || !out_cols || !out_rows || n_projs <= 0 || !projs) return NQE_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
+    const auto t_enter = std::chrono::steady_clock::now();
     const int64_t n = cols[0].length;
+    const int64_t CHUNK_ROWS = chunk_rows();
     std::vector<char> used(n_cols, 0);
     referenced_columns(predicate, used);
     for (int i = 0; i < n_projs; i++) referenced_columns(&projs[i], used);
@@ -114,6 +129,14 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
     };
     int64_t total = 0;
     double kernel_ms = 0.0;
+    // NQE_HOST_PROF=1: where the wall time of one call goes (setup, H2D stream busy time, D2H tail)
+    static const bool prof = getenv("NQE_HOST_PROF") && atoi(getenv("NQE_HOST_PROF"));
+    cudaEvent_t pe[3] = {nullptr, nullptr, nullptr}; // first upload issued, last upload done, last download done
+    const auto t_setup = std::chrono::steady_clock::now();
+    if (prof) {
+        for (auto &e : pe) cudaEventCreate(&e);
+        cudaEventRecord(pe[0], ctx->s_h2d);
+    }
     if (rc == NQE_OK) {
         upload(0);
         if (n_chunks > 1) upload(1);
@@ -122,6 +145,7 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
         const int b = c % NBUF;
         const int64_t r0 = (int64_t)c * CHUNK_ROWS, rows = std::min(CHUNK_ROWS, n - r0);
         if (c + 2 < n_chunks) upload(c + 2);
+        if (prof && c + 3 == n_chunks) cudaEventRecord(pe[1], ctx->s_h2d);
         // chunk table over the device buffers (unreferenced columns are never dereferenced)
         std::vector<nqe_column_desc> d(n_cols);
         for (int k = 0; k < n_cols; k++) {
@@ -161,9 +185,20 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
         pending_out[b] = out;
         total += r;
     }
+    if (prof) cudaEventRecord(pe[2], ctx->s_d2h);
     cudaStreamSynchronize(ctx->s_d2h);
     cudaStreamSynchronize(ctx->s_h2d);
     cudaStreamSynchronize(ctx->stream);
+    if (prof) {
+        float h2d = 0, all = 0;
+        if (n_chunks >= 3) cudaEventElapsedTime(&h2d, pe[0], pe[1]);
+        cudaEventElapsedTime(&all, pe[0], pe[2]);
+        const double setup = std::chrono::duration<double, std::milli>(t_setup - t_enter).count();
+        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+        fprintf(stderr, "[nqe host pipeline] chunks %d setup %.3f ms, uploads %.3f ms, first upload -> last download %.3f ms, call %.3f ms\n",
+                n_chunks, setup, h2d, all, wall);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
     for (auto *t : pending_out)
         if (t) nqe_table_free(t);
     for (void *p : dev_in) nqe_dev_free(ctx, p);

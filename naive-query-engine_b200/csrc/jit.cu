@@ -47,6 +47,8 @@ struct JP {
     int num_tiles;
     int pad;
     u64 *prof;
+    const u32 *valid[16];  // validity bitmap of column slot s, or null
+    u8 *out_valid[16];     // validity byte per output row, or null (output cannot be NULL)
 };
 #define WARPS 8
 #if NQE_PROF
@@ -279,6 +281,7 @@ const char *kSkeletonTma =
 struct TNode {
     int kind, op, dtype, col, lit; // col: column slot; lit: literal slot
     int left = -1, right = -1;
+    bool is_null = false; // NULL literal
 };
 
 struct Gen {
@@ -287,7 +290,9 @@ struct Gen {
     std::vector<uint64_t> lits;
     std::vector<TNode> nodes;
     std::vector<char> in_proj; // slot is read by some projection
+    std::vector<char> has_valid; // slot has a validity bitmap
     bool parsing_proj = false;
+    bool any_nulls = false; // some referenced column is nullable or a literal is NULL
 
     int slot_of(int col) {
         size_t s = 0;
@@ -296,6 +301,7 @@ struct Gen {
         if (s == col_of_slot.size()) {
             col_of_slot.push_back(col);
             in_proj.push_back(0);
+            has_valid.push_back(in->cols[col].validity ? 1 : 0);
         }
         if (parsing_proj) in_proj[s] = 1;
         return (int)s;
@@ -310,15 +316,17 @@ struct Gen {
             n.kind = s.kind; n.op = s.op;
             if (s.kind == NQE_NODE_COLUMN) {
                 const DevColumn &c = in->cols[s.column];
-                if (c.validity || c.dtype == NQE_UTF8) return -1;
+                if (c.dtype == NQE_UTF8) return -1;
+                if (c.validity) any_nulls = true;
                 n.dtype = c.dtype;
                 n.col = slot_of(s.column);
                 if (col_of_slot.size() > 16) return -1;
             } else if (s.kind == NQE_NODE_LITERAL) {
-                if (s.is_null) return -1;
                 n.dtype = s.dtype;
+                n.is_null = s.is_null != 0;
+                if (n.is_null) any_nulls = true;
                 n.lit = (int)lits.size();
-                lits.push_back(s.dtype == NQE_BOOL ? (s.value.u64 ? 1 : 0) : s.value.u64);
+                lits.push_back(n.is_null ? 0 : s.dtype == NQE_BOOL ? (s.value.u64 ? 1 : 0) : s.value.u64);
                 if (lits.size() > 32) return -1;
             } else if (s.kind == NQE_NODE_BINARY) {
                 n.right = st.back(); st.pop_back();
@@ -337,6 +345,56 @@ struct Gen {
 
     static const char *ctype(int dt) {
         return dt == NQE_INT64 ? "i64" : dt == NQE_UINT64 ? "u64" : dt == NQE_FLOAT64 ? "double" : "bool";
+    }
+
+    // NULL-aware form: one (value, valid) pair of temporaries per node, `t<n>v` / `t<n>k`, for row j of this
+    // thread.  live = "errors of this row count", rn = "the row's column inputs are forced NULL"
+    // (load_operand / apply_binary in expr_eval.cuh are the interpreter's statement of the same rules).
+    void emit_stmts(int n, std::ostringstream &o, const std::string &live, const std::string &rn) {
+        const TNode &t = nodes[n];
+        const std::string T = ctype(t.dtype), v = "t" + std::to_string(n) + "v", k = "t" + std::to_string(n) + "k";
+        if (t.kind == NQE_NODE_COLUMN || t.kind == NQE_NODE_LITERAL) {
+            o << "const " << T << " " << v << " = " << emit(n, "false") << ";\n";
+            if (t.kind == NQE_NODE_LITERAL) o << "const bool " << k << " = " << (t.is_null ? "false" : "true") << ";\n";
+            else o << "const bool " << k << " = " << (has_valid[t.col] ? "v" + std::to_string(t.col) + "_[j] && " : std::string()) << "!(" << rn << ");\n";
+            return;
+        }
+        if (t.kind == NQE_NODE_UNARY) {
+            emit_stmts(t.left, o, live, rn);
+            const std::string a = "t" + std::to_string(t.left) + "v";
+            o << "const double " << v << " = " << (t.op == NQE_FN_ABS ? "fabs(" : t.op == NQE_FN_SIN ? "sin(" : "cos(") << a << ");\n";
+            o << "const bool " << k << " = t" << t.left << "k;\n";
+            return;
+        }
+        emit_stmts(t.left, o, live, rn);
+        emit_stmts(t.right, o, live, rn);
+        const std::string a = "t" + std::to_string(t.left) + "v", b = "t" + std::to_string(t.right) + "v";
+        const std::string ak = "t" + std::to_string(t.left) + "k", bk = "t" + std::to_string(t.right) + "k";
+        const int lt = nodes[t.left].dtype;
+        static const char *cmp[] = {"==", "!=", "<", "<=", ">", ">="};
+        if (t.op <= NQE_OP_GT_EQ) {
+            o << "const bool " << v << " = " << a << " " << cmp[t.op] << " " << b << ";\nconst bool " << k << " = " << ak << " && " << bk << ";\n";
+        } else if (t.op == NQE_OP_AND || t.op == NQE_OP_OR) { // Kleene
+            o << "const bool " << v << "a = " << a << " && " << ak << ", " << v << "b = " << b << " && " << bk << ";\n";
+            if (t.op == NQE_OP_AND)
+                o << "const bool " << v << " = " << v << "a && " << v << "b;\nconst bool " << k << " = (" << ak << " && " << bk << ") || (" << ak
+                  << " && !" << v << "a) || (" << bk << " && !" << v << "b);\n";
+            else
+                o << "const bool " << v << " = " << v << "a || " << v << "b;\nconst bool " << k << " = (" << ak << " && " << bk << ") || " << v
+                  << "a || " << v << "b;\n";
+        } else {
+            o << "const bool " << k << " = " << ak << " && " << bk << ";\n";
+            const char *sfx = lt == NQE_INT64 ? "i64" : lt == NQE_UINT64 ? "u64" : "f64";
+            const std::string lv = "(" + live + ") && " + k;
+            if (t.op == NQE_OP_DIVIDE) o << "const " << T << " " << v << " = nqe_div_" << sfx << "(" << a << ", " << b << ", " << lv << ", p.status);\n";
+            else if (t.op == NQE_OP_MODULOS) o << "const " << T << " " << v << " = nqe_mod_" << sfx << "(" << a << ", " << b << ", " << lv << ", p.status);\n";
+            else if (lt == NQE_FLOAT64)
+                o << "const double " << v << " = " << (t.op == NQE_OP_PLUS ? "__dadd_rn" : t.op == NQE_OP_MINUS ? "__dsub_rn" : "__dmul_rn") << "(" << a << ", " << b << ");\n";
+            else {
+                const char *sym = t.op == NQE_OP_PLUS ? "+" : t.op == NQE_OP_MINUS ? "-" : "*";
+                o << "const " << T << " " << v << " = (" << T << ")((u64)" << a << " " << sym << " (u64)" << b << ");\n";
+            }
+        }
     }
 
     // typed C expression for row j of this thread
@@ -425,6 +483,8 @@ struct JitParams {
     int32_t num_tiles;
     int32_t pad;
     unsigned long long *prof;
+    const uint32_t *valid[16];
+    uint8_t *out_valid[16];
 };
 
 struct CachedKernel {
@@ -452,7 +512,8 @@ std::mutex &cache_mutex() {
 // Returns NQE_OK and sets *used = true when the specialised kernel was launched;
 // *used = false means "not applicable, use the interpreter kernels".
 static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
-                                       int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                                       int32_t n_projs, void *const *out_values, uint8_t *const *out_valid,
+                                       unsigned long long *tile_state,
                                        unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
                                        std::string *source_out, bool allow_tma) {
     *used = false;
@@ -511,12 +572,15 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     bool tma = allow_tma && impl == 1 && predicate && n_pred_cols > 0;
     const size_t n_slots = g.col_of_slot.size();
     uint32_t pstage = 0, ptx = 0, wstage = 0, wtx = 0;
-    std::vector<uint32_t> poff(n_slots), woff(n_slots), col_bytes(n_slots);
+    std::vector<uint32_t> poff(n_slots), woff(n_slots), col_bytes(n_slots), pvoff(n_slots), wvoff(n_slots);
     int sp = SP, sw = SW, tk = TK;
+    const bool nulls = g.any_nulls; // NULL-aware code: only the TMA-ring skeleton has it
+    if (nulls && !tma) return NQE_OK;
     if (tma) {
         bool any_proj = false;
         for (size_t s = 0; s < n_slots; s++) {
             if ((uintptr_t)in->cols[g.col_of_slot[s]].values & 15) tma = false;
+            if ((uintptr_t)in->cols[g.col_of_slot[s]].validity & 15) tma = false;
             if (g.in_proj[s]) any_proj = true;
         }
         if (!any_proj) tma = false; // projections of literals only: nothing to stage
@@ -529,13 +593,19 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                 const uint32_t padded = (col_bytes[s] + 127) & ~127u;
                 if (s < n_pred_cols) { poff[s] = pstage; pstage += padded; ptx += col_bytes[s]; }
                 if (g.in_proj[s]) { woff[s] = wstage; wstage += padded; wtx += col_bytes[s]; }
+                if (g.has_valid[s]) { // validity bitmap of the tile, staged next to the values
+                    const uint32_t vb = tile / 8, vpad = (vb + 127) & ~127u;
+                    if (s < n_pred_cols) { pvoff[s] = pstage; pstage += vpad; ptx += vb; }
+                    if (g.in_proj[s]) { wvoff[s] = wstage; wstage += vpad; wtx += vb; }
+                }
             }
             if ((size_t)sp * pstage + (size_t)sw * wstage <= 104 * 1024 || tk == 1) break;
         }
         if ((size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) tma = false;
     }
+    if (nulls && !tma) return NQE_OK;
     const int nr = LAG + sw + WALKERS + 2; // ring slots of per-tile state: covers claim .. write of a tile
-    src << "#define NQE_PROF " << (tma ? prof : 0) << "\n";
+    src << "#define NQE_PROF " << (tma ? prof : 0) << "\n#define NULLS " << (nulls ? 1 : 0) << "\n";
     if (tma) {
         K = tk;
         src << "#define K " << tk << "\n#define SP " << sp << "\n#define SW " << sw << "\n#define LAG " << LAG << "\n#define NR " << nr
@@ -558,10 +628,11 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     {
         std::ostringstream k;
         k << tma << ',' << tk << ',' << sp << ',' << sw << ',' << LAG << ',' << WALKERS << ',' << lbw << ',' << prof << ',' << CK << ','
-          << D << ',' << HINTS << ',' << (predicate ? 1 : 0) << ',' << n_pred_cols << ',' << pred_root << ';';
-        for (size_t sl = 0; sl < n_slots; sl++) k << in->cols[g.col_of_slot[sl]].dtype << (g.in_proj[sl] ? 'p' : '-');
+          << D << ',' << HINTS << ',' << (predicate ? 1 : 0) << ',' << n_pred_cols << ',' << pred_root << ',' << nulls << ';';
+        for (size_t sl = 0; sl < n_slots; sl++)
+            k << in->cols[g.col_of_slot[sl]].dtype << (g.in_proj[sl] ? 'p' : '-') << (g.has_valid[sl] ? 'v' : '-');
         k << ';';
-        for (const TNode &t : g.nodes) k << t.kind << '.' << t.op << '.' << t.dtype << '.' << t.col << '.' << t.lit << '.' << t.left << '.' << t.right << ' ';
+        for (const TNode &t : g.nodes) k << t.kind << '.' << t.op << '.' << t.dtype << '.' << t.col << '.' << t.lit << '.' << t.left << '.' << t.right << '.' << t.is_null << ' ';
         k << ';';
         for (int r : roots) k << r << ' ';
         shape_key = k.str();
@@ -584,7 +655,10 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         if (g.in_proj[s]) proj_slots.push_back(s);
     }
     auto emit_decls = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v) {
-        for (size_t s : slots) o << "u64 " << v << s << "_[K];\n";
+        for (size_t s : slots) {
+            o << "u64 " << v << s << "_[K];\n";
+            if (nulls && g.has_valid[s]) o << "bool v" << s << "_[K];\n";
+        }
     };
     auto emit_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v, const char *e0, const char *full,
                           bool decl, const char *pol = nullptr) {
@@ -599,10 +673,14 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                     o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_keep(p.col[" << s << "] + e, " << pol << ") : 0ull; }\n";
                 else
                     o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
+            if (nulls && g.has_valid[s])
+                o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; v" << s
+                  << "_[j] = (" << full << " || e < p.n_rows) ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) != 0 : false; }\n";
         }
     };
     // operands of a staged (full) tile come from shared memory: row j*256+tid of the stage's column block
-    auto emit_smem_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off) {
+    auto emit_smem_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off,
+                               const std::vector<uint32_t> &voff) {
         for (size_t s : slots) {
             const int dt = in->cols[g.col_of_slot[s]].dtype;
             o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) ";
@@ -610,12 +688,21 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                 o << "c" << s << "_[j] = (((const u32 *)(stg + " << off[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
             else
                 o << "c" << s << "_[j] = ((const u64 *)(stg + " << off[s] << "))[j * 256 + tid];\n";
+            if (nulls && g.has_valid[s])
+                o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) v" << s << "_[j] = ((((const u32 *)(stg + " << voff[s]
+                  << "))[j * 8 + warp] >> lane) & 1u) != 0;\n";
         }
     };
-    auto emit_copies = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off, bool pred_ring) {
-        for (size_t s : slots) // a predicate column that a projection reads again is kept in L2 for the write pass
+    auto emit_copies = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off,
+                           const std::vector<uint32_t> &voff, bool pred_ring) {
+        for (size_t s : slots) { // a predicate column that a projection reads again is kept in L2 for the write pass
+            const char *pol = pred_ring && g.in_proj[s] ? "pol_keep" : "pol_stream";
             o << "bulk_g2s(dst + " << off[s] << ", (const u8 *)p.col[" << s << "] + (size_t)tile * " << col_bytes[s] << "u, " << col_bytes[s]
-              << "u, bar, " << (pred_ring && g.in_proj[s] ? "pol_keep" : "pol_stream") << ");\n";
+              << "u, bar, " << pol << ");\n";
+            if (nulls && g.has_valid[s])
+                o << "bulk_g2s(dst + " << voff[s] << ", (const u8 *)p.valid[" << s << "] + (size_t)tile * (K * 32), K * 32, bar, " << pol
+                  << ");\n";
+        }
     };
     std::ostringstream loads, pred_loads, next_decl, next_loads;
     emit_loads(loads, tma ? proj_slots : all_slots, "c", "e0", "full", !tma, "pol_stream");
@@ -626,13 +713,33 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     if (tma) {
         emit_decls(decls, proj_slots, "c");
         emit_decls(pred_decls, pred_slots, "c");
-        emit_smem_loads(smem_loads, proj_slots, woff);
-        emit_smem_loads(smem_pred_loads, pred_slots, poff);
-        emit_copies(pred_copies, pred_slots, poff, true);
-        emit_copies(write_copies, proj_slots, woff, false);
+        emit_smem_loads(smem_loads, proj_slots, woff, wvoff);
+        emit_smem_loads(smem_pred_loads, pred_slots, poff, pvoff);
+        emit_copies(pred_copies, pred_slots, poff, pvoff, true);
+        emit_copies(write_copies, proj_slots, woff, wvoff, false);
     }
-    std::ostringstream stores;
-    for (int o = 0; o < n_projs; o++) {
+    std::ostringstream stores, qstmts;
+    std::string qvalid = "true", qvalue = "true";
+    if (nulls) {
+        g.emit_stmts(pred_root, qstmts, "inr", "false");
+        qvalid = "t" + std::to_string(pred_root) + "k";
+        qvalue = "t" + std::to_string(pred_root) + "v";
+    }
+    for (int o = 0; nulls && o < n_projs; o++) {
+        const TNode &r = g.nodes[roots[o]];
+        const std::string rv = "t" + std::to_string(roots[o]) + "v", rk = "t" + std::to_string(roots[o]) + "k";
+        stores << "{ u8 *ov = p.out_valid[" << o << "] ? p.out_valid[" << o << "] + tile_excl : (u8 *)0;\n";
+        if (r.dtype == NQE_BOOL) stores << "u8 *out = (u8 *)p.out[" << o << "] + tile_excl;\n";
+        else stores << "u64 *out = (u64 *)p.out[" << o << "] + tile_excl;\n";
+        stores << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) {\n";
+        g.emit_stmts(roots[o], stores, "keep[j] && !rn[j]", "rn[j]");
+        stores << "if (keep[j]) { out[idx[j]] = " << rk << " ? ";
+        if (r.dtype == NQE_FLOAT64) stores << "(u64)__double_as_longlong(" << rv << ")";
+        else if (r.dtype == NQE_BOOL) stores << "(u8)" << rv;
+        else stores << "(u64)" << rv;
+        stores << " : 0; if (ov) ov[idx[j]] = (u8)" << rk << "; } } }\n";
+    }
+    for (int o = 0; !nulls && o < n_projs; o++) {
         const TNode &r = g.nodes[roots[o]];
         stores << "{ ";
         if (r.dtype == NQE_BOOL) stores << "u8 *out = (u8 *)p.out[" << o << "] + tile_excl;\n";
@@ -656,6 +763,9 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     };
     std::string kernel = tma ? kSkeletonTma : kSkeletonKernel;
     if (tma) {
+        kernel = replace_all(kernel, "QSTMTS", qstmts.str());
+        kernel = replace_all(kernel, "QVALID", qvalid);
+        kernel = replace_all(kernel, "QVALUE", qvalue);
         kernel = replace_all(kernel, "ISSUE_PRED_COPIES", pred_copies.str());
         kernel = replace_all(kernel, "ISSUE_WRITE_COPIES", write_copies.str());
         kernel = replace_all(kernel, "DECL_PRED_COLUMNS", pred_decls.str());
@@ -726,6 +836,8 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     memset(&jp, 0, sizeof jp);
     for (size_t s = 0; s < g.col_of_slot.size(); s++) jp.col[s] = in->cols[g.col_of_slot[s]].values;
     for (int o = 0; o < n_projs; o++) jp.out[o] = out_values[o];
+    for (size_t s = 0; s < g.col_of_slot.size(); s++) jp.valid[s] = (const uint32_t *)in->cols[g.col_of_slot[s]].validity;
+    for (int o = 0; o < n_projs; o++) jp.out_valid[o] = out_valid ? out_valid[o] : nullptr;
     for (size_t i = 0; i < g.lits.size(); i++) jp.lit[i] = g.lits[i];
     jp.n_rows = in->nrows;
     jp.tile_state = tile_state;
@@ -797,13 +909,14 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
 }
 
 int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
-                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
+                               int32_t n_projs, void *const *out_values, uint8_t *const *out_valid,
+                               unsigned long long *tile_state,
                                unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
                                std::string *source_out) {
-    int32_t rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, tile_state, ticket, out_count, status,
-                                         used, source_out, true);
+    int32_t rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, out_valid, tile_state, ticket, out_count,
+                                         status, used, source_out, true);
     if (rc == NQE_OK && !*used && !source_out)
-        rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, tile_state, ticket, out_count, status, used,
-                                     source_out, false);
+        rc = jit_filter_project_impl(ctx, in, predicate, projs, n_projs, out_values, out_valid, tile_state, ticket, out_count, status,
+                                     used, source_out, false);
     return rc;
 }

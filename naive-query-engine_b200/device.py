@@ -124,8 +124,10 @@ class DeviceTable:
 
     @classmethod
     def from_device_pointers(cls, ctx: Context, names: Sequence[str], dtypes: Sequence[int], ptrs: Sequence[int],
-                             nrows: int, keepalive=None) -> "DeviceTable":
-        """Wrap NULL-free 8-byte device columns owned by the caller (e.g. torch tensors)."""
+                             nrows: int, keepalive=None, validity: Optional[Sequence[int]] = None,
+                             null_counts: Optional[Sequence[int]] = None) -> "DeviceTable":
+        """Wrap 8-byte device columns owned by the caller (e.g. torch tensors); `validity[i]` is the device address
+        of column i's LSB-first bitmap (0 = NULL-free column)."""
         n = len(ptrs)
         descs = (ColumnDesc * max(n, 1))()
         for i in range(n):
@@ -133,6 +135,9 @@ class DeviceTable:
             descs[i].length = nrows
             descs[i].null_count = 0
             descs[i].values = ptrs[i]
+            if validity is not None and validity[i]:
+                descs[i].validity = validity[i]
+                descs[i].null_count = null_counts[i] if null_counts is not None else -1
         h = C.c_void_p()
         ctx.check(ctx.lib.nqe_table_from_device(ctx.h, descs, n, C.byref(h)))
         return cls(ctx, h, names, keepalive)

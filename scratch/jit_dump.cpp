@@ -4,9 +4,9 @@
 #include <string>
 #include "nqe_internal.cuh"
 int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
-                               int32_t n_projs, void *const *out_values, unsigned long long *tile_state,
-                               unsigned int *ticket, unsigned long long *out_count, uint32_t *status, bool *used,
-                               std::string *source_out);
+                               int32_t n_projs, void *const *out_values, uint8_t *const *out_valid,
+                               unsigned long long *tile_state, unsigned int *ticket, unsigned long long *out_count,
+                               uint32_t *status, bool *used, std::string *source_out);
 int main() {
     nqe_ctx ctx;
     nqe_table t;
@@ -14,6 +14,7 @@ int main() {
     t.nrows = 100000000;
     t.cols.resize(3);
     for (int i = 0; i < 3; i++) { t.cols[i].dtype = i == 2 ? NQE_FLOAT64 : NQE_INT64; t.cols[i].values = (void *)0x10000; t.cols[i].length = t.nrows; }
+    if (getenv("WITH_NULLS")) for (int i = 0; i < 2; i++) { t.cols[i].validity = (uint8_t *)0x20000; t.cols[i].null_count = 5; }
     nqe_expr_node pn[3] = {{NQE_NODE_COLUMN, 0, 0, 0, 0, 0, {0}}, {NQE_NODE_LITERAL, 0, 0, NQE_INT64, 0, 0, {500}}, {NQE_NODE_BINARY, NQE_OP_LT, 0, 0, 0, 0, {0}}};
     nqe_expr pred{pn, 3, 0};
     nqe_expr_node a[1] = {{NQE_NODE_COLUMN, 0, 0, 0, 0, 0, {0}}};
@@ -22,7 +23,7 @@ int main() {
     void *outs[2] = {nullptr, nullptr};
     bool used = false;
     std::string src;
-    int rc = nqe_jit_filter_project(&ctx, &t, &pred, projs, 2, outs, nullptr, nullptr, nullptr, nullptr, &used, &src);
+    int rc = nqe_jit_filter_project(&ctx, &t, &pred, projs, 2, outs, nullptr, nullptr, nullptr, nullptr, nullptr, &used, &src);
     printf("rc=%d used=%d err=%s\n", rc, (int)used, ctx.last_error.c_str());
     FILE *f = fopen("/tmp/jit_src.cu", "w"); fputs(src.c_str(), f); fclose(f);
     return 0;

@@ -150,6 +150,33 @@ def test_filter_project_many_tiles(n, k):
         assert np.array_equal(got.column(i).to_numpy(zero_copy_only=False), want[i]), f"column {i}"
 
 
+@pytest.mark.parametrize("n", [2048 * 300, 1_000_003])
+@pytest.mark.parametrize("null_frac", [0.02, 0.5])
+def test_filter_project_many_tiles_nullable(n, null_frac):
+    """NULL-aware two-ring kernel over hundreds of tiles: validity bitmaps staged next to the values, Kleene OR,
+    rows whose predicate is NULL kept as all-NULL rows (selection.rs:46), divide with NULL/dropped zero divisors."""
+    from importlib import import_module
+    pp = import_module("naive-query-engine_b200.physical_plan")
+    rng = np.random.default_rng(n + int(null_frac * 100))
+    b = O.Batch(["a", "b", "x", "f"], [rand_col(rng, "i64", n, null_frac), rand_col(rng, "i64", n, null_frac, lo=1, hi=60),
+                                      rand_col(rng, "f64", n, null_frac), rand_col(rng, "bool", n, null_frac)])
+    pred = ("bin", "Or", ("bin", "Lt", ("col", 0), lit(10)), ("bin", "And", ("col", 3), ("bin", "GtEq", ("col", 2), ("lit", "f64", 1.5))))
+    exprs = [("col", 0), ("bin", "Plus", ("col", 1), lit(100)), ("bin", "Multiply", ("col", 2), ("lit", "f64", 0.5)), ("col", 3),
+             ("bin", "Divide", ("col", 0), ("col", 1)), ("bin", "LtEq", ("col", 0), ("col", 1)), ("lit", "i64", None)]
+    want = O.projection(O.selection(b, pred), exprs)
+    src = G.scan(b).execute_device()
+    got = pp._filter_project(src, G.expr(pred), [G.expr(e) for e in exprs], [f"o{i}" for i in range(len(exprs))]).to_arrow()
+    assert got.num_rows == want.num_rows
+    for i, w in enumerate(want.cols):
+        a = got.column(i)
+        gv = np.ones(len(a), dtype=np.uint8) if a.null_count == 0 else np.asarray(a.is_valid()).astype(np.uint8)
+        wv = np.ones(len(a), dtype=np.uint8) if w.valid is None else w.valid
+        assert np.array_equal(gv, wv), f"validity of column {i}"
+        g = a.fill_null(False if w.dtype == "bool" else 0).to_numpy(zero_copy_only=False)
+        m = wv != 0
+        assert np.array_equal(np.asarray(g)[m].astype(w.values.dtype), w.values[m]), f"values of column {i}"
+
+
 @pytest.mark.parametrize("ncols", [6, 12, 16])
 def test_filter_project_wide_table(ncols):
     """Many referenced columns: the two-ring kernel shrinks its tile (K = 8 -> 4 -> 2 -> 1) so that both rings still
