@@ -443,6 +443,48 @@ __global__ void pack_bytes_kernel(const uint8_t *__restrict__ bytes, int64_t n, 
     if (zeros && (threadIdx.x & 31) == 0 && z) atomicAdd(zeros, (unsigned long long)z);
 }
 
+// the same for up to 32 byte maps of one operator call in ONE launch (blockIdx.y = map); the row count is read from
+// device memory when `n_dev` is set, so the launch can be queued right behind the kernel that produces the count
+struct PackParams {
+    const uint8_t *bytes[32];
+    uint32_t *words[32];
+    unsigned long long *zeros[32];
+    const unsigned long long *n_dev;
+    int64_t n;
+};
+__global__ void pack_bytes_multi_kernel(const __grid_constant__ PackParams pk) {
+    const int64_t n = pk.n_dev ? (int64_t)*pk.n_dev : pk.n;
+    const int64_t nwords = (n + 31) / 32;
+    if ((int64_t)blockIdx.x * blockDim.x >= nwords) return;
+    const uint8_t *__restrict__ bytes = pk.bytes[blockIdx.y];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int z = 0;
+    if (w < nwords) {
+        uint32_t bits = 0;
+        const int64_t b0 = w * 32;
+        if (b0 + 32 <= n) {
+            const uint4 *p = (const uint4 *)(bytes + b0);
+            const uint4 a = p[0], b = p[1];
+            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) bits |= ((u[q] >> (8 * k)) & 1u) << (q * 4 + k);
+            z = 32 - __popc(bits);
+        } else {
+            for (int k = 0; b0 + k < n; k++) {
+                const uint32_t v = bytes[b0 + k] & 1u;
+                bits |= v << k;
+                z += 1 - v;
+            }
+        }
+        pk.words[blockIdx.y][w] = bits;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (pk.zeros[blockIdx.y] && (threadIdx.x & 31) == 0 && z) atomicAdd(pk.zeros[blockIdx.y], (unsigned long long)z);
+}
+
 template <int K>
 int32_t launch_fp(nqe_ctx *ctx, bool has_pred, const DevProgramSet &ps, FilterParams &fp) {
     constexpr int TILE = K * FP_THREADS;
@@ -667,34 +709,37 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
            : K == 4 ? launch_fp<4>(ctx, predicate != nullptr, ps, fp)
                     : launch_fp<8>(ctx, predicate != nullptr, ps, fp);
     int64_t out_rows = n;
-    bool needs_pack = false; // bitmaps for Boolean outputs / validity are packed by a second kernel: keep it inside the timer
-    for (int i = 0; i < n_projs; i++)
-        if (bool_bytes[i] || valid_bytes[i]) needs_pack = true;
+    // bitmaps for Boolean outputs / validity: one more launch, queued behind the kernel (it reads the row count on the
+    // device), so the operator still needs a single host synchronisation
+    PackParams pk;
+    memset(&pk, 0, sizeof pk);
+    int n_maps = 0;
+    for (int i = 0; i < n_projs; i++) {
+        if (bool_bytes[i]) { pk.bytes[n_maps] = bool_bytes[i]; pk.words[n_maps] = (uint32_t *)t->cols[i].values; n_maps++; }
+        if (valid_bytes[i]) {
+            pk.bytes[n_maps] = valid_bytes[i];
+            pk.words[n_maps] = (uint32_t *)t->cols[i].validity;
+            pk.zeros[n_maps] = (unsigned long long *)(ctx->d_scratch + 8 + i);
+            n_maps++;
+        }
+    }
+    if (rc == NQE_OK && n_maps && n > 0) {
+        pk.n = n;
+        pk.n_dev = predicate ? fp.out_count : nullptr;
+        const int64_t nwords = (n + 31) / 32;
+        pack_bytes_multi_kernel<<<dim3((unsigned)((nwords + 255) / 256), (unsigned)n_maps), 256, 0, ctx->stream>>>(pk);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "pack kernel launch failed");
+    }
     if (rc == NQE_OK) {
-        if (!needs_pack) timer.mark_end();
-        cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        timer.mark_end();
+        cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = nqe_fail(ctx, NQE_ERR_CUDA, "filter_project kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (rc == NQE_OK) {
         if (predicate) out_rows = n ? (int64_t)ctx->h_scratch[0] : 0;
         rc = status_to_error(ctx, (uint32_t)ctx->h_scratch[1]);
-    }
-    // bitmaps for Boolean outputs / validity
-    if (rc == NQE_OK) {
-        bool any = false;
-        for (int i = 0; i < n_projs && rc == NQE_OK; i++) {
-            if (bool_bytes[i]) { rc = nqe_pack_bytes(ctx, bool_bytes[i], out_rows, (uint32_t *)t->cols[i].values, nullptr); any = true; }
-            if (rc == NQE_OK && valid_bytes[i]) {
-                rc = nqe_pack_bytes(ctx, valid_bytes[i], out_rows, (uint32_t *)t->cols[i].validity,
-                                    (unsigned long long *)(ctx->d_scratch + 8 + i));
-                any = true;
-            }
-        }
-        if (rc == NQE_OK && any) {
-            cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "pack kernel failed");
-        }
     }
     timer.stop();
     for (int i = 0; i < n_projs; i++) {

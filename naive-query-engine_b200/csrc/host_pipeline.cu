@@ -103,7 +103,17 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
         NQE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         NQE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
-    const int n_chunks = (int)((n + CHUNK_ROWS - 1) / CHUNK_ROWS);
+    // chunk boundaries: full chunks, then a tapered tail (quarter chunks) -- what follows the last upload (its kernel and
+    // the download of its result) is not hidden under anything, so the last chunks are small
+    std::vector<int64_t> start;
+    {
+        const int64_t small = std::max<int64_t>(1 << 16, (CHUNK_ROWS / 4) & ~(int64_t)2047);
+        int64_t r = 0;
+        while (n - r > CHUNK_ROWS + CHUNK_ROWS / 2) { start.push_back(r); r += CHUNK_ROWS; }
+        while (r < n) { start.push_back(r); r += std::min(small, n - r); }
+        start.push_back(n);
+    }
+    const int n_chunks = (int)start.size() - 1;
     constexpr int NBUF = 3; // chunk c's inputs live until its kernel is done; two more can be in flight
     std::vector<void *> dev_in((size_t)NBUF * n_cols, nullptr);
     int32_t rc = NQE_OK;
@@ -119,7 +129,7 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
     std::vector<nqe_table *> pending_out(NBUF, nullptr);
     auto upload = [&](int c) {
         const int b = c % NBUF;
-        const int64_t r0 = (int64_t)c * CHUNK_ROWS, rows = std::min(CHUNK_ROWS, n - r0);
+        const int64_t r0 = start[c], rows = start[c + 1] - r0;
         if (c >= NBUF) cudaStreamWaitEvent(ctx->s_h2d, done[b], 0); // the kernel of chunk c-NBUF has read this buffer
         for (int k = 0; k < n_cols; k++)
             if (used[k])
@@ -143,7 +153,7 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
     }
     for (int c = 0; c < n_chunks && rc == NQE_OK; c++) {
         const int b = c % NBUF;
-        const int64_t r0 = (int64_t)c * CHUNK_ROWS, rows = std::min(CHUNK_ROWS, n - r0);
+        const int64_t rows = start[c + 1] - start[c];
         if (c + 2 < n_chunks) upload(c + 2);
         if (prof && c + 3 == n_chunks) cudaEventRecord(pe[1], ctx->s_h2d);
         // chunk table over the device buffers (unreferenced columns are never dereferenced)

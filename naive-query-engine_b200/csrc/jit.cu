@@ -356,7 +356,7 @@ struct Gen {
         if (t.kind == NQE_NODE_COLUMN || t.kind == NQE_NODE_LITERAL) {
             o << "const " << T << " " << v << " = " << emit(n, "false") << ";\n";
             if (t.kind == NQE_NODE_LITERAL) o << "const bool " << k << " = " << (t.is_null ? "false" : "true") << ";\n";
-            else o << "const bool " << k << " = " << (has_valid[t.col] ? "v" + std::to_string(t.col) + "_[j] && " : std::string()) << "!(" << rn << ");\n";
+            else o << "const bool " << k << " = " << (has_valid[t.col] ? "((v" + std::to_string(t.col) + "m >> j) & 1u) != 0 && " : std::string()) << "!(" << rn << ");\n";
             return;
         }
         if (t.kind == NQE_NODE_UNARY) {
@@ -657,7 +657,7 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     auto emit_decls = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v) {
         for (size_t s : slots) {
             o << "u64 " << v << s << "_[K];\n";
-            if (nulls && g.has_valid[s]) o << "bool v" << s << "_[K];\n";
+            if (nulls && g.has_valid[s]) o << "u32 v" << s << "m = 0;\n"; // bit j = row j of this thread is valid
         }
     };
     auto emit_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v, const char *e0, const char *full,
@@ -675,7 +675,7 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                     o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ldg_stream(p.col[" << s << "] + e) : 0ull; }\n";
             if (nulls && g.has_valid[s])
                 o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; v" << s
-                  << "_[j] = (" << full << " || e < p.n_rows) ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) != 0 : false; }\n";
+                  << "m |= ((" << full << " || e < p.n_rows) ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) : 0u) << j; }\n";
         }
     };
     // operands of a staged (full) tile come from shared memory: row j*256+tid of the stage's column block
@@ -689,8 +689,8 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
             else
                 o << "c" << s << "_[j] = ((const u64 *)(stg + " << off[s] << "))[j * 256 + tid];\n";
             if (nulls && g.has_valid[s])
-                o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) v" << s << "_[j] = ((((const u32 *)(stg + " << voff[s]
-                  << "))[j * 8 + warp] >> lane) & 1u) != 0;\n";
+                o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) v" << s << "m |= ((((const u32 *)(stg + " << voff[s]
+                  << "))[j * 8 + warp] >> lane) & 1u) << j;\n";
         }
     };
     auto emit_copies = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off,
@@ -725,19 +725,47 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         qvalid = "t" + std::to_string(pred_root) + "k";
         qvalue = "t" + std::to_string(pred_root) + "v";
     }
-    for (int o = 0; nulls && o < n_projs; o++) {
-        const TNode &r = g.nodes[roots[o]];
-        const std::string rv = "t" + std::to_string(roots[o]) + "v", rk = "t" + std::to_string(roots[o]) + "k";
-        stores << "{ u8 *ov = p.out_valid[" << o << "] ? p.out_valid[" << o << "] + tile_excl : (u8 *)0;\n";
-        if (r.dtype == NQE_BOOL) stores << "u8 *out = (u8 *)p.out[" << o << "] + tile_excl;\n";
-        else stores << "u64 *out = (u64 *)p.out[" << o << "] + tile_excl;\n";
-        stores << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) {\n";
-        g.emit_stmts(roots[o], stores, "keep[j] && !rn[j]", "rn[j]");
-        stores << "if (keep[j]) { out[idx[j]] = " << rk << " ? ";
-        if (r.dtype == NQE_FLOAT64) stores << "(u64)__double_as_longlong(" << rv << ")";
-        else if (r.dtype == NQE_BOOL) stores << "(u8)" << rv;
-        else stores << "(u64)" << rv;
-        stores << " : 0; if (ov) ov[idx[j]] = (u8)" << rk << "; } } }\n";
+    if (nulls) {
+        // NULL-aware write pass: rows outermost, so that a row's operands (and their valid flags) are loaded, used by
+        // every output and dead again -- the (value, valid) pairs would otherwise not fit in the 80 registers that two
+        // CTAs per SM allow
+        auto row_loads = [&](std::ostringstream &o, bool smem) {
+            if (!smem) o << "const i64 e = e0 + (i64)j * THREADS; const bool inr = e < p.n_rows;\n";
+            for (size_t s : proj_slots) {
+                const int dt = in->cols[g.col_of_slot[s]].dtype;
+                if (smem) {
+                    if (dt == NQE_BOOL) o << "c" << s << "_[j] = (((const u32 *)(stg + " << woff[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
+                    else o << "c" << s << "_[j] = ((const u64 *)(stg + " << woff[s] << "))[j * 256 + tid];\n";
+                    if (g.has_valid[s]) o << "v" << s << "m |= ((((const u32 *)(stg + " << wvoff[s] << "))[j * 8 + warp] >> lane) & 1u) << j;\n";
+                } else {
+                    if (dt == NQE_BOOL) o << "c" << s << "_[j] = inr ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull;\n";
+                    else o << "c" << s << "_[j] = inr ? ldg_stream(p.col[" << s << "] + e) : 0ull;\n";
+                    if (g.has_valid[s]) o << "v" << s << "m |= (inr ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) : 0u) << j;\n";
+                }
+            }
+        };
+        std::ostringstream body;
+        for (int o = 0; o < n_projs; o++) {
+            const TNode &r = g.nodes[roots[o]];
+            const std::string rv = "t" + std::to_string(roots[o]) + "v", rk = "t" + std::to_string(roots[o]) + "k";
+            stores << "u8 *const ov" << o << " = p.out_valid[" << o << "] ? p.out_valid[" << o << "] + tile_excl : (u8 *)0;\n";
+            if (r.dtype == NQE_BOOL) stores << "u8 *const out" << o << " = (u8 *)p.out[" << o << "] + tile_excl;\n";
+            else stores << "u64 *const out" << o << " = (u64 *)p.out[" << o << "] + tile_excl;\n";
+            body << "{\n";
+            g.emit_stmts(roots[o], body, "KEEPJ && !RNJ", "RNJ");
+            body << "if (KEEPJ) { out" << o << "[idx[j]] = " << rk << " ? ";
+            if (r.dtype == NQE_FLOAT64) body << "(u64)__double_as_longlong(" << rv << ")";
+            else if (r.dtype == NQE_BOOL) body << "(u8)" << rv;
+            else body << "(u64)" << rv;
+            body << " : 0; if (ov" << o << ") ov" << o << "[idx[j]] = (u8)" << rk << "; } }\n";
+        }
+        stores << "if (full) {\n_Pragma(\"unroll\") for (int j = 0; j < K; j++) {\n";
+        row_loads(stores, true);
+        stores << body.str() << "} } else {\n_Pragma(\"unroll\") for (int j = 0; j < K; j++) {\n";
+        row_loads(stores, false);
+        stores << body.str() << "} }\n";
+        smem_loads.str("");
+        loads.str("");
     }
     for (int o = 0; !nulls && o < n_projs; o++) {
         const TNode &r = g.nodes[roots[o]];
