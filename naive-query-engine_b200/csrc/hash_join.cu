@@ -52,6 +52,13 @@ struct JoinTable {
     int32_t n_pay;    // fat: number of payload columns (<= 2)
     int32_t pay_col[2];
     const unsigned long long *pay_src[2];
+    // "payload in the row word": when the plan needs exactly ONE build-side value per match (the only non-key
+    // build column of a join, or the group key of a fused join -> group-by) the slot's second word holds that
+    // value instead of the build row number, so a match costs one random access, not two (slot, then column[row]).
+    // A payload equal to EMPTY_ROW cannot be stored (it marks a free slot): the build reports it and the host
+    // rebuilds with row numbers.
+    const unsigned long long *rowpay;
+    int32_t rowpay_col, pad;
 };
 
 struct ColSrc {
@@ -113,11 +120,16 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = keys[i];
+    const unsigned long long rowword = jt.rowpay ? jt.rowpay[i] : (unsigned long long)i;
+    if (rowword == EMPTY_ROW) { // only possible for a payload
+        dupflag[2] = 1u;
+        return;
+    }
     uint64_t s = join_slot_of(jt, key);
     bool dup = false;
     for (uint64_t probe = 0; probe < jt.cap; probe++) {
         unsigned long long *p = slot_ptr(jt, s);
-        const ulonglong2 old = cas128(p, make_ulonglong2(0ull, EMPTY_ROW), make_ulonglong2(key, (unsigned long long)i));
+        const ulonglong2 old = cas128(p, make_ulonglong2(0ull, EMPTY_ROW), make_ulonglong2(key, rowword));
         if (old.y == EMPTY_ROW) {
             if (jt.shift == 2) {
                 p[2] = jt.n_pay > 0 ? jt.pay_src[0][i] : 0ull;
@@ -414,6 +426,110 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
     }
 }
 
+// ---- split, second generation (knob NQE_JOIN_SPLIT=2; 1 = the kernels above).  Same three passes and the same
+// tile-major order of every partition's stream (an order that follows the probe rows keeps the gather pass's reads
+// nearly sequential -- claiming runs with a global atomic instead of scanning tile counts was measured: the
+// scatter got faster but the gather's DRAM reads went from 1.3 to 3.5 GB), but
+//   * histograms and ranks come from shared-memory atomics (one ATOMS per row, the returned value is the row's rank
+//     inside its tile's run) instead of log2p ballot bit-planes per row group,
+//   * the keys are staged in shared memory in partition-major order and leave as contiguous runs: coalesced stores
+//     instead of up to 2^log2p distinct lines per warp store.
+// Inside a tile's run the order is arrival order, which nothing depends on: every row remembers its position.
+__global__ void __launch_bounds__(HJ_THREADS) pj2_count_kernel(PartJoin pj, unsigned long long *totals) {
+    constexpr int K = PJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned int s_hist[PJ_MAX_PARTS];
+    const int tid = threadIdx.x, P = 1 << pj.log2p;
+    unsigned long long mine = 0;
+    if (tid < PJ_MAX_PARTS) s_hist[tid] = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pj.n ? ld_stream_u64(pj.keys + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if (e0 + (int64_t)j * HJ_THREADS < pj.n) atomicAdd(&s_hist[pj_part(key[j], pj.log2p)], 1u);
+        __syncthreads();
+        if (tid < P) {
+            const unsigned c = s_hist[tid];
+            pj.tile_cnt[(size_t)tid * pj.num_tiles + tile] = c;
+            mine += c;
+            s_hist[tid] = 0;
+        }
+        __syncthreads();
+    }
+    if (tid < P && mine) atomicAdd(totals + tid, mine);
+}
+
+__global__ void __launch_bounds__(HJ_THREADS) pj2_scatter_kernel(PartJoin pj) {
+    constexpr int K = PJ_K, TILE = K * HJ_THREADS;
+    __shared__ unsigned long long s_keys[TILE];
+    __shared__ unsigned char s_pid[TILE];
+    __shared__ unsigned int s_cnt[PJ_MAX_PARTS], s_start[PJ_MAX_PARTS + 1];
+    __shared__ unsigned long long s_gbase[PJ_MAX_PARTS];
+    const int tid = threadIdx.x, lane = tid & 31, P = 1 << pj.log2p;
+    const unsigned long long pol = pj_policy();
+    if (tid < 32) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TILE + tid;
+        unsigned long long key[K];
+        int pid[K];
+        unsigned rank[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            key[j] = e < pj.n ? ld_ef(pj.keys + e, pol) : 0ull;
+        }
+        if (tid < P) s_gbase[tid] = pj.part_base[tid] + pj.tile_off[(size_t)tid * pj.num_tiles + tile];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            pid[j] = pj_part(key[j], pj.log2p);
+            rank[j] = 0;
+            if (e0 + (int64_t)j * HJ_THREADS < pj.n) rank[j] = atomicAdd(&s_cnt[pid[j]], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) { // local starts of the partitions' runs in the staging order
+            const unsigned c = tid < P ? s_cnt[tid] : 0u;
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            s_start[tid] = incl - c;
+            if (tid == 31) s_start[32] = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
+            if (e < pj.n) {
+                const unsigned local = s_start[pid[j]] + rank[j];
+                s_keys[local] = key[j];
+                s_pid[local] = (unsigned char)pid[j];
+                pj.ppos32[e] = (unsigned int)(s_gbase[pid[j]] + rank[j]);
+            }
+        }
+        __syncthreads();
+        const unsigned total = s_start[32];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const unsigned idx = tid + j * HJ_THREADS;
+            if (idx < total) {
+                const int p = s_pid[idx];
+                st_ef(pj.pkeys + s_gbase[p] + (idx - s_start[p]), s_keys[idx], pol);
+            }
+        }
+        if (tid < 32) s_cnt[tid] = 0;
+        __syncthreads(); // staging buffers and counters are reused by the next tile
+    }
+}
+
 // pass 4: probe in partitioned order (partition after partition, so one slot range of the table is hot in L2)
 template <bool FAT, int K>
 __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinTable jt) {
@@ -458,10 +574,43 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
 struct GatherParams {
     PartJoin pj;
     int32_t fat, n_gather;
+    int32_t row_is_payload, pad; // thin: the probe results ARE the one gathered column's values (JoinTable::rowpay)
     const unsigned long long *src[HJ_MAX_COLS]; // thin: build column to gather by build row
     unsigned long long *dst[HJ_MAX_COLS];       // thin: gathered column; fat: dst[0], dst[1] = payload words
     unsigned int *match;                        // match bitmap in probe-row order
 };
+// Tile-aligned variant for the second-generation split: inside a tile's run the positions are in arrival order, so the
+// four results that share a 32-byte sector belong to four arbitrary rows of the SAME 2048-row tile.  One CTA therefore
+// handles a whole tile and reads the results through L1 (plain read-only loads, no evict_first): the sector is fetched once.
+__global__ void __launch_bounds__(256) pj_gather_tile_kernel(const __grid_constant__ GatherParams gp) {
+    constexpr int K = PJ_K, TILE = K * 256;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long pol = pj_policy();
+    const int64_t num_tiles = (gp.pj.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        unsigned int pos[K];
+        unsigned long long r[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t i = tile * TILE + j * 256 + threadIdx.x;
+            pos[j] = i < gp.pj.n ? __ldg(gp.pj.ppos32 + i) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t i = tile * TILE + j * 256 + threadIdx.x;
+            r[j] = i < gp.pj.n ? __ldg(gp.pj.res0 + pos[j]) : EMPTY_ROW;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t i = tile * TILE + j * 256 + threadIdx.x;
+            const bool m = r[j] != EMPTY_ROW;
+            if (i < gp.pj.n) st_ef(gp.dst[0] + i, m ? r[j] : 0ull, pol);
+            const unsigned b = __ballot_sync(0xffffffffu, m);
+            if (lane == 0 && (i - lane) < gp.pj.n) gp.match[i >> 5] = b;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ GatherParams gp) {
     const int lane = threadIdx.x & 31;
     const unsigned long long pol = pj_policy();
@@ -478,7 +627,8 @@ __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ 
             } else {
                 const unsigned long long brow = ld_ef(gp.pj.res0 + p, pol);
                 m = brow != EMPTY_ROW;
-                for (int c = 0; c < gp.n_gather; c++) {
+                if (gp.row_is_payload) st_ef(gp.dst[0] + i, m ? brow : 0ull, pol);
+                else for (int c = 0; c < gp.n_gather; c++) {
                     unsigned long long v = 0;
                     if (m) v = ld_cg_u64(gp.src[c] + brow);
                     st_ef(gp.dst[c] + i, v, pol);
@@ -679,7 +829,7 @@ struct JoinAggParams {
     int64_t n_probe;
     ColSrc group;          // group key column
     int32_t group_left;    // 1: taken from the build row, 0: from the probe row
-    int32_t group_pay;     // fat table: 0/1 = group key is payload word 0/1, -1 = not in the slot
+    int32_t group_pay;     // fat table: 0/1 = group key is payload word 0/1; 2 = the slot's row word; -1 = not in the slot
     ColSrc val[AG_MAX];
     int32_t val_left[AG_MAX];
     int32_t val_pay[AG_MAX]; // fat table: payload word holding this build-side argument, or -1
@@ -712,7 +862,8 @@ __device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggP
     ulonglong2 pay = make_ulonglong2(0, 0);
     if (jp.jt.shift == 2) pay = ld_payload(jp.jt, slot);
     uint64_t gkey;
-    if (jp.group_left && jp.group_pay >= 0) gkey = jp.group_pay ? pay.y : pay.x;
+    if (jp.group_pay == 2) gkey = (uint64_t)brow; // the slot's row word is the group key (JoinTable::rowpay)
+    else if (jp.group_left && jp.group_pay >= 0) gkey = jp.group_pay ? pay.y : pay.x;
     else {
         const int64_t grow = jp.group_left ? brow : prow;
         if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
@@ -748,7 +899,9 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
         for (int j = 0; j < K; j++) {
             gkey[j] = 0;
             if (brow[j] == EMPTY_ROW) continue;
-            if (jp.group_left && jp.group_pay >= 0) {
+            if (jp.group_pay == 2) {
+                gkey[j] = brow[j];
+            } else if (jp.group_left && jp.group_pay >= 0) {
                 gkey[j] = jp.group_pay ? pay[j].y : pay[j].x;
             } else {
                 const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
@@ -794,17 +947,27 @@ int32_t check_join_keys(nqe_ctx *ctx, const nqe_table *left, const nqe_table *ri
 }
 
 // build the multimap over left->cols[lk]
-int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt) {
+// rowpay_col >= 0: store that column's value in the slots' row word (see JoinTable); falls back to row numbers when a
+// value collides with the free-slot marker or (dups_ok == false) the build keys are not unique
+int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt, int rowpay_col = -1, bool dups_ok = true) {
     const int64_t nl = left->nrows;
     memset(jt, 0, sizeof *jt);
     jt->key_col = lk;
+    jt->rowpay_col = -1;
+    if (rowpay_col >= 0) {
+        const DevColumn &pc = left->cols[rowpay_col];
+        if (!pc.validity && (pc.dtype == NQE_INT64 || pc.dtype == NQE_UINT64 || pc.dtype == NQE_FLOAT64)) {
+            jt->rowpay = (const unsigned long long *)pc.values;
+            jt->rowpay_col = rowpay_col;
+        }
+    }
     // fat slots when every non-key build column is a NULL-free 8-byte column and there are at most two
     static int allow_fat = -1;
     if (allow_fat < 0) {
         const char *e = getenv("NQE_JOIN_FAT");
         allow_fat = e ? atoi(e) : 0; // measured (profiles/join_groupby_r01.md): thin 16-byte slots + gather beat fat slots, whose table is twice as large
     }
-    bool fat = allow_fat && left->cols.size() <= 3;
+    bool fat = allow_fat && left->cols.size() <= 3 && !jt->rowpay;
     int n_pay = 0;
     for (size_t c = 0; c < left->cols.size() && fat; c++) {
         if ((int)c == lk) continue;
@@ -830,11 +993,16 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
         join_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, keys, nl, status, dupflag);
         ctx->launches++;
     }
-    cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return nqe_fail(ctx, NQE_ERR_CUDA, "join build failed: %s", cudaGetErrorString(cudaGetLastError()));
     if ((uint32_t)ctx->h_scratch[1] & DEV_ERR_TABLE_FULL) return nqe_fail(ctx, NQE_ERR_CUDA, "join table overflow");
     jt->has_dups = (uint32_t)ctx->h_scratch[3] ? 1 : 0;
+    if (jt->rowpay && ((uint32_t)ctx->h_scratch[4] || (jt->has_dups && !dups_ok))) {
+        nqe_dev_free(ctx, jt->words);
+        cudaMemsetAsync(ctx->d_scratch + 1, 0, 4 * sizeof(uint64_t), ctx->stream); // status, ticket, dup flag, payload flag
+        return build_table(ctx, left, lk, jt, -1, true);
+    }
     return NQE_OK;
 }
 
@@ -863,9 +1031,97 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
     ProbeParams pp;
     memset(&pp, 0, sizeof pp);
-    int32_t rc = build_table(ctx, left, left_key, &pp.jt);
-    pp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
+    static int allow_part = -1, allow_rowpay = 1;
+    static size_t l2_budget = 0;
+    if (allow_part < 0) {
+        const char *e = getenv("NQE_JOIN_PART");
+        allow_part = e ? atoi(e) : 1;
+        e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
+        l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
+        e = getenv("NQE_JOIN_ROWPAY");
+        allow_rowpay = e ? atoi(e) : 1;
+    }
     pp.n_probe = right->nrows;
+    // the partitioned probe (below) will run if the build keys turn out unique; with a single non-key build column its
+    // values ride in the slots' row word and the gather pass has nothing left to chase
+    const bool part_sizes = allow_part && pp.n_probe >= (1 << 22) && pp.n_probe < (int64_t)1 << 32 &&
+                            ((size_t)((double)left->nrows / 0.5) + 16) * 16 > 2 * l2_budget && nl + nr + 1 <= 16;
+    const int rowpay_col = allow_rowpay && part_sizes && nl == 2 && !left->cols[left_key].validity ? 1 - left_key : -1;
+    pp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
+    // The split of the probe keys depends only on sizes, not on the table: it runs on the auxiliary stream WHILE the
+    // table is built (the build is bound by its random 128-bit CAS traffic, the split by its scattered stores; measured
+    // alone: 0.49 ms and 0.91 ms).  If the build then finds duplicate keys the split is simply not used.
+    std::vector<void *> pj_bufs;
+    int32_t rc = NQE_OK;
+    bool split_started = false;
+    static int allow_overlap = -1;
+    if (allow_overlap < 0) {
+        const char *e = getenv("NQE_JOIN_OVERLAP");
+        allow_overlap = e ? atoi(e) : 1;
+    }
+    if (part_sizes) {
+        const size_t table_bytes = ((size_t)((double)left->nrows / 0.5) + 16) * 16;
+        int log2p = 1;
+        while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
+        PartJoin &pj = pp.pj;
+        pj.keys = pp.probe_keys;
+        pj.n = pp.n_probe;
+        pj.log2p = log2p;
+        pj.num_tiles = (int32_t)((pp.n_probe + 2048 - 1) / 2048); // PJ_K * HJ_THREADS rows per tile
+        const size_t P = (size_t)1 << log2p, nt = (size_t)pj.num_tiles;
+        auto alloc = [&](void **p, size_t bytes) {
+            if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
+            if (rc == NQE_OK) pj_bufs.push_back(*p);
+        };
+        void *totals = nullptr;
+        alloc((void **)&pj.tile_cnt, nt * P * 4);
+        alloc((void **)&pj.tile_off, nt * P * 4);
+        alloc((void **)&pj.part_base, (P + 1) * 8);
+        alloc(&totals, P * 8);
+        alloc((void **)&pj.pkeys, (size_t)pp.n_probe * 8);
+        alloc((void **)&pj.ppos32, (size_t)pp.n_probe * 4);
+        alloc((void **)&pj.res0, (size_t)pp.n_probe * 8);
+        if (rc == NQE_OK && !ctx->s_aux) {
+            if (cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+                rc = nqe_fail(ctx, NQE_ERR_CUDA, "auxiliary stream creation failed");
+        }
+        if (rc == NQE_OK) {
+            cudaStream_t ss = allow_overlap ? ctx->s_aux : ctx->stream;
+            if (allow_overlap) {
+                cudaEventRecord(ctx->ev_fork, ctx->stream); // the buffers above were allocated in ctx->stream's order
+                cudaStreamWaitEvent(ss, ctx->ev_fork, 0);
+            }
+            static int split_ctas = 0; // knob NQE_JOIN_SPLIT_CTAS: CTAs per SM of the split passes (fewer leave room for the build)
+            if (!split_ctas) {
+                const char *e = getenv("NQE_JOIN_SPLIT_CTAS");
+                split_ctas = e && atoi(e) > 0 ? atoi(e) : 8;
+            }
+            int grid = ctx->sm_count * split_ctas;
+            if (grid > pj.num_tiles) grid = pj.num_tiles;
+            static int split_gen = 0; // knob NQE_JOIN_SPLIT: 1 = stable ballot-histogram split, 2 = atomic-rank staged split
+            if (!split_gen) {
+                const char *e = getenv("NQE_JOIN_SPLIT");
+                split_gen = e ? atoi(e) : 3;
+                if (split_gen < 1 || split_gen > 3) split_gen = 3;
+            }
+            // 1: ballot histograms + stable scatter; 2: atomic histograms + staged (arrival-order) scatter;
+            // 3: atomic histograms for the count, stable scatter (default: the stable order keeps the gather's reads sequential)
+            cudaMemsetAsync(totals, 0, P * 8, ss);
+            if (split_gen == 1) pj_count_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj, (unsigned long long *)totals);
+            else pj2_count_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj, (unsigned long long *)totals);
+            pj_scan_kernel<<<(unsigned)P, 1024, 0, ss>>>(pj, (const unsigned long long *)totals);
+            if (split_gen == 2) pj2_scatter_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj);
+            else pj_scatter_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj);
+            ctx->launches += 3;
+            if (allow_overlap) cudaEventRecord(ctx->ev_join, ss);
+            if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "probe-side split launch failed");
+            split_started = true;
+        }
+    }
+    if (rc == NQE_OK) rc = build_table(ctx, left, left_key, &pp.jt, rowpay_col, false);
+    if (split_started && allow_overlap) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); // also orders the frees below
     pp.n_left = nl;
     pp.n_right = nr;
     pp.key_from_probe = left->cols[left_key].validity == nullptr;
@@ -881,54 +1137,23 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     const bool fat = pp.jt.shift == 2 && pp.key_from_probe;
 
     // ---- partitioned probe: unique build keys and a table that does not fit in the L2
-    std::vector<void *> pj_bufs;
     bool part = false;
-    if (rc == NQE_OK) {
-        static int allow_part = -1;
-        static size_t l2_budget = 0;
-        if (allow_part < 0) {
-            const char *e = getenv("NQE_JOIN_PART");
-            allow_part = e ? atoi(e) : 1;
-            e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
-            l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
-        }
-        const size_t table_bytes = (size_t)(pp.jt.cap << pp.jt.shift) * 8;
+    if (rc == NQE_OK && split_started) {
         bool emit_fp = true; // emit through the filter/project kernel: NULL-free 8-byte build columns only
         for (int c = 0; c < nl; c++)
             if (left->cols[c].validity || left->cols[c].dtype == NQE_BOOL) emit_fp = false;
-        if (nl + nr + 1 > 16) emit_fp = false;
         const bool thin_ok = pp.jt.shift == 1 && emit_fp, fat_ok = fat && emit_fp;
-        if (allow_part && !pp.jt.has_dups && (thin_ok || fat_ok) && pp.n_probe >= (1 << 22) && table_bytes > 2 * l2_budget &&
-            pp.n_probe < (int64_t)1 << 32) {
-            int log2p = 1;
-            while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
+        if (!pp.jt.has_dups && (thin_ok || fat_ok)) {
             PartJoin &pj = pp.pj;
-            pj.keys = pp.probe_keys;
-            pj.n = pp.n_probe;
-            pj.log2p = log2p;
-            pj.num_tiles = (int32_t)((pp.n_probe + 2048 - 1) / 2048); // PJ_K * HJ_THREADS rows per tile
-            const size_t P = (size_t)1 << log2p, nt = (size_t)pj.num_tiles;
             auto alloc = [&](void **p, size_t bytes) {
                 if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
                 if (rc == NQE_OK) pj_bufs.push_back(*p);
             };
-            void *totals = nullptr;
-            alloc((void **)&pj.tile_cnt, nt * P * 4);
-            alloc((void **)&pj.tile_off, nt * P * 4);
-            alloc((void **)&pj.part_base, (P + 1) * 8);
-            alloc(&totals, P * 8);
-            alloc((void **)&pj.pkeys, (size_t)pp.n_probe * 8);
-            alloc((void **)&pj.ppos32, (size_t)pp.n_probe * 4);
-            alloc((void **)&pj.res0, (size_t)pp.n_probe * 8);
             if (fat && pp.jt.n_pay > 1) alloc((void **)&pj.res1, (size_t)pp.n_probe * 8);
             if (fat) alloc((void **)&pj.mbits, ((size_t)pp.n_probe / 32 + 2) * 4);
             if (rc == NQE_OK) {
-                cudaMemsetAsync(totals, 0, P * 8, ctx->stream);
                 int grid = ctx->sm_count * 8;
                 if (grid > pj.num_tiles) grid = pj.num_tiles;
-                pj_count_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, (unsigned long long *)totals);
-                pj_scan_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(pj, (const unsigned long long *)totals);
-                pj_scatter_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj);
                 static int probe_k = 0; // knob NQE_JOIN_PROBE_K: independent probes in flight per thread
                 if (!probe_k) {
                     const char *e = getenv("NQE_JOIN_PROBE_K");
@@ -937,11 +1162,9 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
                 if (fat) pj_probe_kernel<true, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
                 else if (probe_k == 8) pj_probe_kernel<false, 8><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
                 else pj_probe_kernel<false, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
-                ctx->launches += 4;
+                ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partitioned probe launch failed");
                 part = true;
-            } else {
-                pj.pkeys = nullptr;
             }
         }
     }
@@ -951,6 +1174,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
         memset(&gp, 0, sizeof gp);
         gp.pj = pp.pj;
         gp.fat = fat ? 1 : 0;
+        gp.row_is_payload = pp.jt.rowpay ? 1 : 0;
         const int64_t n = pp.n_probe;
         std::vector<void *> gathered(nl, nullptr); // per build column: its values in probe-row order
         auto alloc = [&](void **p, size_t bytes) {
@@ -973,7 +1197,13 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             }
         }
         if (rc == NQE_OK) {
-            pj_gather_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
+            static int gather_gen = 0; // knob NQE_JOIN_GATHER: 2 = tile-aligned gather through L1 (payload-in-row tables only)
+            if (!gather_gen) {
+                const char *e = getenv("NQE_JOIN_GATHER");
+                gather_gen = e && atoi(e) == 2 ? 2 : 1;
+            }
+            if (gather_gen == 2 && gp.row_is_payload && !gp.fat) pj_gather_tile_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
+            else pj_gather_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
             ctx->launches++;
             // joined table before compaction: [build columns (key = probe key) | probe columns | match]
             nqe_table view;
@@ -1012,6 +1242,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
         return rc;
     }
 
+    if (rc == NQE_OK && pp.jt.rowpay) rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: payload-in-row table outside the partitioned probe");
     nqe_table *t = nullptr;
     int64_t cap = pp.n_probe > 0 ? pp.n_probe : 1;
     int64_t out_rows = 0;
@@ -1150,10 +1381,20 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
 
     OpTimer timer(ctx);
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
-    int32_t rc = build_table(ctx, left, left_key, &jp.jt);
+    // only the group key is needed from the build side: it rides in the slots' row word
+    bool only_group_from_build = jp.group_left && group_column != left_key;
+    for (int a = 0; a < n_aggs; a++)
+        if (jp.val_left[a]) only_group_from_build = false;
+    static int allow_rowpay = -1;
+    if (allow_rowpay < 0) {
+        const char *e = getenv("NQE_JOIN_ROWPAY");
+        allow_rowpay = e ? atoi(e) : 1;
+    }
+    int32_t rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
     // which build-side columns can be served from the fat slot's payload words
     jp.group_pay = -1;
     for (int a = 0; a < n_aggs; a++) jp.val_pay[a] = -1;
+    if (jp.jt.rowpay) jp.group_pay = 2;
     if (jp.jt.shift == 2) {
         for (int q = 0; q < jp.jt.n_pay; q++) {
             if (jp.group_left && group_column == jp.jt.pay_col[q]) jp.group_pay = q;

@@ -31,6 +31,8 @@ struct nqe_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // copy streams of the host pipeline (created on first use)
+    cudaStream_t s_aux = nullptr;                  // second compute stream: independent passes of one operator overlap
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
     int64_t launches = 0;

@@ -374,15 +374,18 @@ def test_hash_join_random(nl, nr, keyspace):
     same(got, want)  # identical order: probe-row-major, build rows ascending
 
 
-@pytest.mark.parametrize("n_pay", [1, 2, 3])
-def test_hash_join_partitioned_probe_large(n_pay):
+@pytest.mark.parametrize("n_pay,poison", [(1, False), (1, True), (2, False), (3, False)])
+def test_hash_join_partitioned_probe_large(n_pay, poison):
     """Build table larger than the L2 budget -> the partitioned (radix) probe path; result must equal the
-    probe-row-major order of the reference (hash_join.rs:80-103).  n_pay <= 2: fat slots, 3: thin slots + gather."""
+    probe-row-major order of the reference (hash_join.rs:80-103).  n_pay == 1: the payload rides in the slots' row word
+    (poison: some payloads equal the free-slot marker, so the build falls back to row numbers); 2, 3: thin slots + gather."""
     import pyarrow as pa
     rng = np.random.default_rng(77 + n_pay)
     nl, nr = 2_000_000, 5_000_017
     keys = rng.permutation(np.arange(1, 3 * nl + 1, dtype=np.int64))[:nl] * 1_000_003  # unique, sparse
     pays = [rng.integers(-1 << 40, 1 << 40, nl).astype(np.int64) for _ in range(n_pay)]
+    if poison:  # a single payload column rides in the slots' row word -- unless a value equals the free-slot marker
+        pays[0][rng.integers(0, nl, 50)] = -1
     fk = np.where(rng.random(nr) < 0.7, keys[rng.integers(0, nl, nr)], rng.integers(1, 1 << 50, nr) * 2 + 7).astype(np.int64)
     b = rng.normal(0, 10, nr)
     L = pa.RecordBatch.from_arrays([pa.array(keys)] + [pa.array(p_) for p_ in pays], names=["k"] + [f"p{i}" for i in range(n_pay)])
@@ -543,6 +546,25 @@ def test_join_aggregate_fused(nl, nr, groups):
     want2 = O.aggregate(O.hash_join_c(l2, r2, 0, 0), ("col", 3), aggs2)
     got2 = G.gpu_join_aggregate(l2, r2, "k", "fk", 3, aggs2)
     same(got2, want2, rel=SUM_REL, ordered=False, sort_cols=[3])
+
+
+@pytest.mark.parametrize("poison", [False, True])
+@pytest.mark.parametrize("dups", [False, True])
+def test_join_aggregate_group_key_in_slot(poison, dups):
+    """Only the group key is needed from the build side: it rides in the join table's row word (one random access per
+    probe row).  poison: a group key equal to the free-slot marker (-1) forces the fall-back to row numbers."""
+    rng = np.random.default_rng(11 + 2 * poison + dups)
+    nl, nr, groups = 30_000, 200_000, 700
+    k = rng.integers(0, nl // 3, nl) if dups else rng.permutation(nl)
+    a = rng.integers(0, groups, nl)
+    if poison:
+        a[rng.integers(0, nl, 20)] = -1
+    l = O.Batch(["k", "a", "z"], [O.Col("i64", k.astype(np.int64)), O.Col("i64", a.astype(np.int64)), rand_col(rng, "f64", nl)])
+    r = O.Batch(["fk", "b"], [O.Col("i64", rng.integers(0, int(nl * 1.2), nr)), rand_col(rng, "f64", nr, 0.05)])
+    aggs = [("count", 4), ("sum", 4), ("avg", 4), ("min", 4), ("max", 4), ("count", 3)]
+    want = O.aggregate(O.hash_join_c(l, r, 0, 0), ("col", 1), aggs)
+    got = G.gpu_join_aggregate(l, r, "k", "fk", 1, aggs)
+    same(got, want, rel=SUM_REL, ordered=False, sort_cols=[3, 4, 5])
 
 
 # ---------------------------------------------------------------- limit / offset / partition / synth
