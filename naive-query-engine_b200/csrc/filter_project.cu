@@ -705,6 +705,12 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
         rc = nqe_jit_filter_project(ctx, in, predicate, projs, n_projs, fp.out_values, fp.out_valid, fp.tile_state, fp.ticket,
                                     fp.out_count, fp.status, &jit_used, nullptr);
     if (rc == NQE_OK && !jit_used)
+        for (const DevColumn &c : in->cols)
+            if (c.via >= 0) { // gathered columns (library-internal) exist only in the specialised kernel: the caller falls back
+                rc = nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "gathered columns need the shape-specialised kernel");
+                break;
+            }
+    if (rc == NQE_OK && !jit_used)
         rc = K == 2 ? launch_fp<2>(ctx, predicate != nullptr, ps, fp)
            : K == 4 ? launch_fp<4>(ctx, predicate != nullptr, ps, fp)
                     : launch_fp<8>(ctx, predicate != nullptr, ps, fp);

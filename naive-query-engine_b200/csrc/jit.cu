@@ -291,6 +291,8 @@ struct Gen {
     std::vector<TNode> nodes;
     std::vector<char> in_proj; // slot is read by some projection
     std::vector<char> has_valid; // slot has a validity bitmap
+    std::vector<int> via_slot;   // gathered column (DevColumn::via): slot of its position column, else -1
+    bool any_via = false;
     bool parsing_proj = false;
     bool any_nulls = false; // some referenced column is nullable or a literal is NULL
 
@@ -302,8 +304,14 @@ struct Gen {
             col_of_slot.push_back(col);
             in_proj.push_back(0);
             has_valid.push_back(in->cols[col].validity ? 1 : 0);
+            via_slot.push_back(-1);
         }
         if (parsing_proj) in_proj[s] = 1;
+        if (in->cols[col].via >= 0) { // the position column is staged wherever the gathered column is read
+            const int x = slot_of(in->cols[col].via);
+            via_slot[s] = x;
+            any_via = true;
+        }
         return (int)s;
     }
 
@@ -316,7 +324,8 @@ struct Gen {
             n.kind = s.kind; n.op = s.op;
             if (s.kind == NQE_NODE_COLUMN) {
                 const DevColumn &c = in->cols[s.column];
-                if (c.dtype == NQE_UTF8) return -1;
+                if (c.dtype == NQE_UTF8 || c.dtype == NQE_POS32) return -1;
+                if (c.via >= 0 && (c.validity || c.dtype == NQE_BOOL || in->cols[c.via].dtype != NQE_POS32 || in->cols[c.via].via >= 0)) return -1;
                 if (c.validity) any_nulls = true;
                 n.dtype = c.dtype;
                 n.col = slot_of(s.column);
@@ -575,11 +584,12 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
     std::vector<uint32_t> poff(n_slots), woff(n_slots), col_bytes(n_slots), pvoff(n_slots), wvoff(n_slots);
     int sp = SP, sw = SW, tk = TK;
     const bool nulls = g.any_nulls; // NULL-aware code: only the TMA-ring skeleton has it
-    if (nulls && !tma) return NQE_OK;
+    if ((nulls || g.any_via) && !tma) return NQE_OK; // gathered columns too
+    if (g.any_via && nulls) return NQE_OK;
     if (tma) {
         bool any_proj = false;
         for (size_t s = 0; s < n_slots; s++) {
-            if ((uintptr_t)in->cols[g.col_of_slot[s]].values & 15) tma = false;
+            if (g.via_slot[s] < 0 && ((uintptr_t)in->cols[g.col_of_slot[s]].values & 15)) tma = false;
             if ((uintptr_t)in->cols[g.col_of_slot[s]].validity & 15) tma = false;
             if (g.in_proj[s]) any_proj = true;
         }
@@ -589,7 +599,8 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
             const uint32_t tile = (uint32_t)tk * 256;
             pstage = ptx = wstage = wtx = 0;
             for (size_t s = 0; s < n_slots; s++) {
-                col_bytes[s] = in->cols[g.col_of_slot[s]].dtype == NQE_BOOL ? tile / 8 : tile * 8;
+                const int sdt = in->cols[g.col_of_slot[s]].dtype;
+                col_bytes[s] = g.via_slot[s] >= 0 ? 0 : sdt == NQE_BOOL ? tile / 8 : sdt == NQE_POS32 ? tile * 4 : tile * 8;
                 const uint32_t padded = (col_bytes[s] + 127) & ~127u;
                 if (s < n_pred_cols) { poff[s] = pstage; pstage += padded; ptx += col_bytes[s]; }
                 if (g.in_proj[s]) { woff[s] = wstage; wstage += padded; wtx += col_bytes[s]; }
@@ -603,9 +614,9 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         }
         if ((size_t)sp * pstage + (size_t)sw * wstage > 200 * 1024) tma = false;
     }
-    if (nulls && !tma) return NQE_OK;
+    if ((nulls || g.any_via) && !tma) return NQE_OK;
     const int nr = LAG + sw + WALKERS + 2; // ring slots of per-tile state: covers claim .. write of a tile
-    src << "#define NQE_PROF " << (tma ? prof : 0) << "\n#define NULLS " << (nulls ? 1 : 0) << "\n";
+    src << "#define NQE_PROF " << (tma ? prof : 0) << "\n#define NULLS " << (nulls ? 1 : 0) << "\n#define GATHERS " << (g.any_via ? 1 : 0) << "\n";
     if (tma) {
         K = tk;
         src << "#define K " << tk << "\n#define SP " << sp << "\n#define SW " << sw << "\n#define LAG " << LAG << "\n#define NR " << nr
@@ -630,7 +641,7 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         k << tma << ',' << tk << ',' << sp << ',' << sw << ',' << LAG << ',' << WALKERS << ',' << lbw << ',' << prof << ',' << CK << ','
           << D << ',' << HINTS << ',' << (predicate ? 1 : 0) << ',' << n_pred_cols << ',' << pred_root << ',' << nulls << ';';
         for (size_t sl = 0; sl < n_slots; sl++)
-            k << in->cols[g.col_of_slot[sl]].dtype << (g.in_proj[sl] ? 'p' : '-') << (g.has_valid[sl] ? 'v' : '-');
+            k << in->cols[g.col_of_slot[sl]].dtype << (g.in_proj[sl] ? 'p' : '-') << (g.has_valid[sl] ? 'v' : '-') << g.via_slot[sl] << ' ';
         k << ';';
         for (const TNode &t : g.nodes) k << t.kind << '.' << t.op << '.' << t.dtype << '.' << t.col << '.' << t.lit << '.' << t.left << '.' << t.right << '.' << t.is_null << ' ';
         k << ';';
@@ -660,13 +671,23 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
             if (nulls && g.has_valid[s]) o << "u32 v" << s << "m = 0;\n"; // bit j = row j of this thread is valid
         }
     };
+    // gathered columns (DevColumn::via) are loaded after the staged ones: value = base[position of this row]
+    auto emit_gathers = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v) {
+        for (size_t s : slots)
+            if (g.via_slot[s] >= 0)
+                o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) " << v << s << "_[j] = __ldg(p.col[" << s << "] + " << v
+                  << g.via_slot[s] << "_[j]);\n";
+    };
     auto emit_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const char *v, const char *e0, const char *full,
                           bool decl, const char *pol = nullptr) {
         for (size_t s : slots) {
             const int dt = in->cols[g.col_of_slot[s]].dtype;
             if (decl) o << "u64 " << v << s << "_[K];\n";
+            if (g.via_slot[s] >= 0) continue;
             o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; ";
-            if (dt == NQE_BOOL)
+            if (dt == NQE_POS32)
+                o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? (u64)((const u32 *)p.col[" << s << "])[e] : 0ull; }\n";
+            else if (dt == NQE_BOOL)
                 o << v << s << "_[j] = (" << full << " || e < p.n_rows) ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull; }\n";
             else
                 if (pol && HINTS && predicate)
@@ -677,14 +698,18 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                 o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) { const i64 e = " << e0 << " + (i64)j * THREADS; v" << s
                   << "m |= ((" << full << " || e < p.n_rows) ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) : 0u) << j; }\n";
         }
+        emit_gathers(o, slots, v);
     };
     // operands of a staged (full) tile come from shared memory: row j*256+tid of the stage's column block
     auto emit_smem_loads = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off,
                                const std::vector<uint32_t> &voff) {
         for (size_t s : slots) {
             const int dt = in->cols[g.col_of_slot[s]].dtype;
+            if (g.via_slot[s] >= 0) continue;
             o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) ";
-            if (dt == NQE_BOOL)
+            if (dt == NQE_POS32)
+                o << "c" << s << "_[j] = ((const u32 *)(stg + " << off[s] << "))[j * 256 + tid];\n";
+            else if (dt == NQE_BOOL)
                 o << "c" << s << "_[j] = (((const u32 *)(stg + " << off[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
             else
                 o << "c" << s << "_[j] = ((const u64 *)(stg + " << off[s] << "))[j * 256 + tid];\n";
@@ -692,10 +717,12 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
                 o << "_Pragma(\"unroll\") for (int j = 0; j < K; j++) v" << s << "m |= ((((const u32 *)(stg + " << voff[s]
                   << "))[j * 8 + warp] >> lane) & 1u) << j;\n";
         }
+        emit_gathers(o, slots, "c");
     };
     auto emit_copies = [&](std::ostringstream &o, const std::vector<size_t> &slots, const std::vector<uint32_t> &off,
                            const std::vector<uint32_t> &voff, bool pred_ring) {
         for (size_t s : slots) { // a predicate column that a projection reads again is kept in L2 for the write pass
+            if (g.via_slot[s] >= 0) continue; // gathered: nothing contiguous to stage
             const char *pol = pred_ring && g.in_proj[s] ? "pol_keep" : "pol_stream";
             o << "bulk_g2s(dst + " << off[s] << ", (const u8 *)p.col[" << s << "] + (size_t)tile * " << col_bytes[s] << "u, " << col_bytes[s]
               << "u, bar, " << pol << ");\n";
@@ -725,39 +752,54 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         qvalid = "t" + std::to_string(pred_root) + "k";
         qvalue = "t" + std::to_string(pred_root) + "v";
     }
-    if (nulls) {
-        // NULL-aware write pass: rows outermost, so that a row's operands (and their valid flags) are loaded, used by
-        // every output and dead again -- the (value, valid) pairs would otherwise not fit in the 80 registers that two
-        // CTAs per SM allow
+    const bool rows_outer = nulls || g.any_via;
+    if (rows_outer) {
+        // write pass with the ROWS outermost: a row's operands (and their valid flags / gathered values) are loaded, used
+        // by every output and dead again.  The NULL-aware and the gathered variants need this to stay within the 80
+        // registers that two CTAs per SM allow.
         auto row_loads = [&](std::ostringstream &o, bool smem) {
             if (!smem) o << "const i64 e = e0 + (i64)j * THREADS; const bool inr = e < p.n_rows;\n";
-            for (size_t s : proj_slots) {
-                const int dt = in->cols[g.col_of_slot[s]].dtype;
-                if (smem) {
-                    if (dt == NQE_BOOL) o << "c" << s << "_[j] = (((const u32 *)(stg + " << woff[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
-                    else o << "c" << s << "_[j] = ((const u64 *)(stg + " << woff[s] << "))[j * 256 + tid];\n";
-                    if (g.has_valid[s]) o << "v" << s << "m |= ((((const u32 *)(stg + " << wvoff[s] << "))[j * 8 + warp] >> lane) & 1u) << j;\n";
-                } else {
-                    if (dt == NQE_BOOL) o << "c" << s << "_[j] = inr ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull;\n";
-                    else o << "c" << s << "_[j] = inr ? ldg_stream(p.col[" << s << "] + e) : 0ull;\n";
-                    if (g.has_valid[s]) o << "v" << s << "m |= (inr ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) : 0u) << j;\n";
+            for (int pass = 0; pass < 2; pass++) // staged columns first, then the columns gathered through them
+                for (size_t s : proj_slots) {
+                    const int dt = in->cols[g.col_of_slot[s]].dtype;
+                    if ((g.via_slot[s] >= 0) != (pass == 1)) continue;
+                    if (pass == 1) {
+                        o << "c" << s << "_[j] = __ldg(p.col[" << s << "] + c" << g.via_slot[s] << "_[j]);\n";
+                    } else if (smem) {
+                        if (dt == NQE_BOOL) o << "c" << s << "_[j] = (((const u32 *)(stg + " << woff[s] << "))[j * 8 + warp] >> lane) & 1u;\n";
+                        else if (dt == NQE_POS32) o << "c" << s << "_[j] = ((const u32 *)(stg + " << woff[s] << "))[j * 256 + tid];\n";
+                        else o << "c" << s << "_[j] = ((const u64 *)(stg + " << woff[s] << "))[j * 256 + tid];\n";
+                        if (nulls && g.has_valid[s]) o << "v" << s << "m |= ((((const u32 *)(stg + " << wvoff[s] << "))[j * 8 + warp] >> lane) & 1u) << j;\n";
+                    } else {
+                        if (dt == NQE_BOOL) o << "c" << s << "_[j] = inr ? ((((const u32 *)p.col[" << s << "])[e >> 5] >> (e & 31)) & 1u) : 0ull;\n";
+                        else if (dt == NQE_POS32) o << "c" << s << "_[j] = inr ? (u64)((const u32 *)p.col[" << s << "])[e] : 0ull;\n";
+                        else o << "c" << s << "_[j] = inr ? ldg_stream(p.col[" << s << "] + e) : 0ull;\n";
+                        if (nulls && g.has_valid[s]) o << "v" << s << "m |= (inr ? ((p.valid[" << s << "][e >> 5] >> (e & 31)) & 1u) : 0u) << j;\n";
+                    }
                 }
-            }
         };
         std::ostringstream body;
         for (int o = 0; o < n_projs; o++) {
             const TNode &r = g.nodes[roots[o]];
-            const std::string rv = "t" + std::to_string(roots[o]) + "v", rk = "t" + std::to_string(roots[o]) + "k";
-            stores << "u8 *const ov" << o << " = p.out_valid[" << o << "] ? p.out_valid[" << o << "] + tile_excl : (u8 *)0;\n";
+            if (nulls) stores << "u8 *const ov" << o << " = p.out_valid[" << o << "] ? p.out_valid[" << o << "] + tile_excl : (u8 *)0;\n";
             if (r.dtype == NQE_BOOL) stores << "u8 *const out" << o << " = (u8 *)p.out[" << o << "] + tile_excl;\n";
             else stores << "u64 *const out" << o << " = (u64 *)p.out[" << o << "] + tile_excl;\n";
             body << "{\n";
-            g.emit_stmts(roots[o], body, "KEEPJ && !RNJ", "RNJ");
-            body << "if (KEEPJ) { out" << o << "[idx[j]] = " << rk << " ? ";
-            if (r.dtype == NQE_FLOAT64) body << "(u64)__double_as_longlong(" << rv << ")";
-            else if (r.dtype == NQE_BOOL) body << "(u8)" << rv;
-            else body << "(u64)" << rv;
-            body << " : 0; if (ov" << o << ") ov" << o << "[idx[j]] = (u8)" << rk << "; } }\n";
+            if (nulls) {
+                const std::string rv = "t" + std::to_string(roots[o]) + "v", rk = "t" + std::to_string(roots[o]) + "k";
+                g.emit_stmts(roots[o], body, "KEEPJ && !RNJ", "RNJ");
+                body << "if (KEEPJ) { out" << o << "[idx[j]] = " << rk << " ? ";
+                if (r.dtype == NQE_FLOAT64) body << "(u64)__double_as_longlong(" << rv << ")";
+                else if (r.dtype == NQE_BOOL) body << "(u8)" << rv;
+                else body << "(u64)" << rv;
+                body << " : 0; if (ov" << o << ") ov" << o << "[idx[j]] = (u8)" << rk << "; } }\n";
+            } else {
+                body << "const " << Gen::ctype(r.dtype) << " v = " << g.emit(roots[o], "keep[j]") << "; if (keep[j]) out" << o << "[idx[j]] = ";
+                if (r.dtype == NQE_FLOAT64) body << "(u64)__double_as_longlong(v)";
+                else if (r.dtype == NQE_BOOL) body << "(u8)v";
+                else body << "(u64)v";
+                body << "; }\n";
+            }
         }
         stores << "if (full) {\n_Pragma(\"unroll\") for (int j = 0; j < K; j++) {\n";
         row_loads(stores, true);
@@ -767,7 +809,7 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         smem_loads.str("");
         loads.str("");
     }
-    for (int o = 0; !nulls && o < n_projs; o++) {
+    for (int o = 0; !rows_outer && o < n_projs; o++) {
         const TNode &r = g.nodes[roots[o]];
         stores << "{ ";
         if (r.dtype == NQE_BOOL) stores << "u8 *out = (u8 *)p.out[" << o << "] + tile_excl;\n";

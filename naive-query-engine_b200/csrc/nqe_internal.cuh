@@ -23,7 +23,12 @@ struct DevColumn {
     uint8_t *data = nullptr;     // utf8 bytes
     int64_t data_bytes = 0;
     bool owned = true;
+    // library-internal: a GATHERED column.  via >= 0: row r of this column is values[ pos ] where pos is row r of column
+    // `via` of the same table, a column of dtype NQE_POS32 (4-byte unsigned positions).  Only the shape-specialised
+    // filter/project kernel (jit.cu) evaluates such columns; the partitioned join hands it its results this way.
+    int32_t via = -1;
 };
+constexpr int32_t NQE_POS32 = 64; // internal dtype: 4-byte unsigned row positions (never leaves the library)
 
 struct nqe_ctx {
     int device = 0;

@@ -20,10 +20,25 @@ int main() {
     nqe_expr_node a[1] = {{NQE_NODE_COLUMN, 0, 0, 0, 0, 0, {0}}};
     nqe_expr_node b[3] = {{NQE_NODE_COLUMN, 0, 1, 0, 0, 0, {0}}, {NQE_NODE_LITERAL, 0, 0, NQE_INT64, 0, 0, {100}}, {NQE_NODE_BINARY, NQE_OP_PLUS, 0, 0, 0, 0, {0}}};
     nqe_expr projs[2] = {{a, 1, 0}, {b, 3, 0}};
-    void *outs[2] = {nullptr, nullptr};
+    void *outs[4] = {nullptr, nullptr, nullptr, nullptr};
     bool used = false;
     std::string src;
-    int rc = nqe_jit_filter_project(&ctx, &t, &pred, projs, 2, outs, nullptr, nullptr, nullptr, nullptr, nullptr, &used, &src);
+    int rc;
+    if (getenv("WITH_GATHER")) { // the partitioned join's last pass: [k, a (gathered), fk, b, pos, match (gathered)]
+        t.cols.resize(6);
+        for (int i = 0; i < 6; i++) { t.cols[i].dtype = NQE_INT64; t.cols[i].values = (void *)0x10000; t.cols[i].length = t.nrows; }
+        t.cols[3].dtype = NQE_FLOAT64;
+        t.cols[4].dtype = NQE_POS32;
+        t.cols[5].dtype = NQE_UINT64;
+        t.cols[1].via = 4;
+        t.cols[5].via = 4;
+        nqe_expr_node gp[3] = {{NQE_NODE_COLUMN, 0, 5, 0, 0, 0, {0}}, {NQE_NODE_LITERAL, 0, 0, NQE_UINT64, 0, 0, {-1}}, {NQE_NODE_BINARY, NQE_OP_NOT_EQ, 0, 0, 0, 0, {0}}};
+        nqe_expr gpred{gp, 3, 0};
+        nqe_expr_node c[4] = {{NQE_NODE_COLUMN, 0, 2, 0, 0, 0, {0}}, {NQE_NODE_COLUMN, 0, 1, 0, 0, 0, {0}}, {NQE_NODE_COLUMN, 0, 2, 0, 0, 0, {0}}, {NQE_NODE_COLUMN, 0, 3, 0, 0, 0, {0}}};
+        nqe_expr gprojs[4] = {{&c[0], 1, 0}, {&c[1], 1, 0}, {&c[2], 1, 0}, {&c[3], 1, 0}};
+        rc = nqe_jit_filter_project(&ctx, &t, &gpred, gprojs, 4, outs, nullptr, nullptr, nullptr, nullptr, nullptr, &used, &src);
+    } else
+    rc = nqe_jit_filter_project(&ctx, &t, &pred, projs, 2, outs, nullptr, nullptr, nullptr, nullptr, nullptr, &used, &src);
     printf("rc=%d used=%d err=%s\n", rc, (int)used, ctx.last_error.c_str());
     FILE *f = fopen("/tmp/jit_src.cu", "w"); fputs(src.c_str(), f); fclose(f);
     return 0;
