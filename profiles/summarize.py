@@ -14,19 +14,27 @@ import sys
 def launches(src, dst):
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.OrderedDict()
+    dram = collections.defaultdict(float)  # DRAM bytes (read + write) per kernel, when the capture has them
     for x in csv.DictReader(lines):
         v = float(x["Metric Value"].replace(",", ""))
         u = x["Metric Unit"]
+        name = x.get("Metric Name", "gpu__time_duration.sum")
+        if name.startswith("dram__bytes"):
+            dram[x["Kernel Name"]] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            continue
+        if name != "gpu__time_duration.sum":
+            continue
         ms = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v
         agg.setdefault(x["Kernel Name"], []).append(ms)
     tot = sum(sum(v) for v in agg.values())
     with open(dst, "w") as f:
         f.write(f"# ncu launch list ({os.path.basename(src)})\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py`; times are "
-                "cold-cache and serialised (compare shares, not absolutes).\n\n"
-                "| kernel | launches | avg ms | total ms | share |\n|---|---:|---:|---:|---:|\n")
+                "`ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --clock-control none` over "
+                "`bench.py`; times are cold-cache and serialised (compare shares, not absolutes).\n\n"
+                "| kernel | launches | avg ms | total ms | share | avg DRAM GB |\n|---|---:|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v):.4f} | {sum(v):.3f} | {100 * sum(v) / tot:.1f}% |\n")
+            gb = f"{dram[k] / len(v) / 1e9:.3f}" if k in dram else ""
+            f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v):.4f} | {sum(v):.3f} | {100 * sum(v) / tot:.1f}% | {gb} |\n")
     print("wrote", dst)
 
 
