@@ -1032,12 +1032,14 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     ProbeParams pp;
     memset(&pp, 0, sizeof pp);
     static int allow_part = -1, allow_rowpay = 1;
-    static size_t l2_budget = 0;
+    static size_t l2_budget = 0, part_min = 0;
     if (allow_part < 0) {
         const char *e = getenv("NQE_JOIN_PART");
         allow_part = e ? atoi(e) : 1;
         e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
-        l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
+        l2_budget = (size_t)(e ? atoi(e) : 48) << 20; // measured 12 / 24 / 48 / 96 MiB: 3.98 / 3.73 / 3.63 / 3.80 ms (1e8 x 1e7)
+        e = getenv("NQE_JOIN_PART_MIN_MB"); // tables up to this size are probed directly
+        part_min = (size_t)(e ? atoi(e) : 48) << 20;
         e = getenv("NQE_JOIN_ROWPAY");
         allow_rowpay = e ? atoi(e) : 1;
     }
@@ -1045,7 +1047,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     // the partitioned probe (below) will run if the build keys turn out unique; with a single non-key build column its
     // values ride in the slots' row word and the gather pass has nothing left to chase
     const bool part_sizes = allow_part && pp.n_probe >= (1 << 22) && pp.n_probe < (int64_t)1 << 32 &&
-                            ((size_t)((double)left->nrows / 0.5) + 16) * 16 > 2 * l2_budget && nl + nr + 1 <= 16;
+                            ((size_t)((double)left->nrows / 0.5) + 16) * 16 > part_min && nl + nr + 1 <= 16;
     const int rowpay_col = allow_rowpay && part_sizes && nl == 2 && !left->cols[left_key].validity ? 1 - left_key : -1;
     pp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
     // The split of the probe keys depends only on sizes, not on the table: it runs on the auxiliary stream WHILE the

@@ -1,0 +1,31 @@
+"""The kernels behind the tuning knobs stay correct: the knobs are read once per process, so each alternative runs a
+slice of the parity suite in a child process with the knob set.  Covers the interpreter kernels (what runs when NVRTC
+is unavailable), the join table with row numbers instead of payloads, the stable ballot split with the streaming
+gather, gathered columns inside the compaction kernel, and the partitioned fused join -> group-by."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [
+    ({"NQE_JIT": "0"}, "filter_project_random or kleene or null_predicate or every_operator or error_behaviour or deep_expression"),
+    ({"NQE_JIT_IMPL": "ca"}, "filter_project_many_tiles and not nullable"),
+    ({"NQE_JOIN_ROWPAY": "0"}, "partitioned_probe_large or join_aggregate_group_key or join_aggregate_fused"),
+    ({"NQE_JOIN_SPLIT": "1", "NQE_JOIN_GATHER": "1", "NQE_JOIN_OVERLAP": "0"}, "partitioned_probe_large"),
+    ({"NQE_JOIN_FUSE": "1"}, "partitioned_probe_large"),
+    ({"NQE_JOINAGG_PART": "1"}, "join_aggregate_partitioned_large"),
+]
+
+
+@pytest.mark.parametrize("env,select", CASES, ids=["+".join(f"{k}={v}" for k, v in e.items()) for e, _ in CASES])
+def test_alternate_kernels_pass_the_parity_slice(env, select):
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-p", "no:cacheprovider", "-k", select],
+                       cwd=ROOT, env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+    tail = (p.stdout + p.stderr)[-2000:]
+    assert p.returncode == 0, tail
+    assert " passed" in p.stdout and "failed" not in p.stdout, tail
