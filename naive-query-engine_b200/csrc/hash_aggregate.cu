@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "agg_device.cuh"
 
@@ -84,6 +85,223 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
 #pragma unroll
         for (int j = 0; j < AGK; j++)
             if (rec[j]) update_states(ap, rec[j], s0[j], RowSource<SIMPLE>{ps, e0 + (int64_t)j * AG_THREADS});
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Partitioned shared-memory group-by (knob NQE_AGG_PART; EXPERIMENTAL until measured on the GPU).
+//
+// The table path above costs one `red` per row per additive state and the L2 retires ~1.5e11 of those per second
+// (profiles/README_r01.md §2).  Here the (key, value) rows are first split into up to 32 partitions by the top bits of
+// the key's hash -- shared-memory-atomic histograms, runs claimed with one global atomic per (tile, partition), rows
+// staged in shared memory and written as contiguous runs; no order is kept, aggregation does not care -- and every
+// partition is then aggregated in SHARED memory (6144-slot open-addressing table per CTA, one CTA per SM): the
+// per-row updates become shared-memory atomics, and only the per-CTA partial states go to the global table (one
+// probe + one `red` per state per GROUP per chunk instead of per ROW).  Rows that do not fit the shared table
+// (a partition with more groups than expected) fall back to the global table one by one, so any key distribution
+// stays correct.  Eligible: bare NULL-free key column, all aggregates over ONE NULL-free 8-byte column.
+constexpr int GP_MAX_PARTS = 32;
+constexpr int GP_K = 8, GP_THREADS = 256, GP_TILE = GP_K * GP_THREADS;
+constexpr int GP_SLOTS = 6144;        // 6144 x 36 bytes = 216 KB of shared memory
+constexpr int GP_AGG_THREADS = 1024;
+constexpr int GP_MAX_PROBE = 48;
+
+struct GroupPart {
+    const unsigned long long *keys, *vals; // input columns
+    int64_t n;
+    int32_t log2p, num_tiles;
+    unsigned long long *pkeys, *pvals;     // rows in partition order
+    unsigned long long *totals;            // [P] rows per partition, then [P] claim cursors
+};
+
+__device__ __forceinline__ int gp_part(uint64_t h, int log2p) { return (int)(h >> (64 - log2p)); }
+
+__global__ void __launch_bounds__(GP_THREADS) gp_count_kernel(GroupPart gp) {
+    __shared__ unsigned int s_hist[GP_MAX_PARTS];
+    const int tid = threadIdx.x, P = 1 << gp.log2p;
+    if (tid < GP_MAX_PARTS) s_hist[tid] = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * GP_TILE + tid;
+        unsigned long long key[GP_K];
+#pragma unroll
+        for (int j = 0; j < GP_K; j++) {
+            const int64_t e = e0 + (int64_t)j * GP_THREADS;
+            key[j] = e < gp.n ? ld_stream_u64(gp.keys + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < GP_K; j++)
+            if (e0 + (int64_t)j * GP_THREADS < gp.n) atomicAdd(&s_hist[gp_part(nqe_mix64(key[j]), gp.log2p)], 1u);
+    }
+    __syncthreads();
+    if (tid < P && s_hist[tid]) atomicAdd(gp.totals + tid, (unsigned long long)s_hist[tid]);
+}
+
+__global__ void __launch_bounds__(GP_THREADS) gp_scatter_kernel(GroupPart gp) {
+    __shared__ unsigned long long s_keys[GP_TILE], s_vals[GP_TILE];
+    __shared__ unsigned char s_pid[GP_TILE];
+    __shared__ unsigned int s_cnt[GP_MAX_PARTS], s_start[GP_MAX_PARTS + 1];
+    __shared__ unsigned long long s_gbase[GP_MAX_PARTS], s_pbase[GP_MAX_PARTS];
+    const int tid = threadIdx.x, lane = tid & 31, P = 1 << gp.log2p;
+    unsigned long long *cursors = gp.totals + P;
+    if (tid < 32) { // partition bases: exclusive scan of the totals (P <= 32: one warp)
+        const unsigned long long t = tid < P ? gp.totals[tid] : 0ull;
+        unsigned long long incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        s_pbase[tid] = incl - t;
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * GP_TILE + tid;
+        unsigned long long key[GP_K], val[GP_K];
+        int pid[GP_K];
+        unsigned rank[GP_K];
+#pragma unroll
+        for (int j = 0; j < GP_K; j++) {
+            const int64_t e = e0 + (int64_t)j * GP_THREADS;
+            key[j] = e < gp.n ? ld_stream_u64(gp.keys + e) : 0ull;
+            val[j] = e < gp.n ? ld_stream_u64(gp.vals + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < GP_K; j++) {
+            pid[j] = gp_part(nqe_mix64(key[j]), gp.log2p);
+            rank[j] = 0;
+            if (e0 + (int64_t)j * GP_THREADS < gp.n) rank[j] = atomicAdd(&s_cnt[pid[j]], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) { // claim this tile's run in every partition; local starts for the staging order
+            const unsigned c = tid < P ? s_cnt[tid] : 0u;
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            s_start[tid] = incl - c;
+            if (tid == 31) s_start[32] = incl;
+            if (tid < P && c) s_gbase[tid] = s_pbase[tid] + atomicAdd(cursors + tid, (unsigned long long)c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < GP_K; j++)
+            if (e0 + (int64_t)j * GP_THREADS < gp.n) {
+                const unsigned local = s_start[pid[j]] + rank[j];
+                s_keys[local] = key[j];
+                s_vals[local] = val[j];
+                s_pid[local] = (unsigned char)pid[j];
+            }
+        __syncthreads();
+        const unsigned total = s_start[32];
+#pragma unroll
+        for (int j = 0; j < GP_K; j++) {
+            const unsigned idx = tid + j * GP_THREADS;
+            if (idx < total) {
+                const int p = s_pid[idx];
+                const unsigned long long pos = s_gbase[p] + (idx - s_start[p]);
+                gp.pkeys[pos] = s_keys[idx];
+                gp.pvals[pos] = s_vals[idx];
+            }
+        }
+        if (tid < 32) s_cnt[tid] = 0;
+        __syncthreads(); // staging buffers and counters are reused by the next tile
+    }
+}
+
+// one row straight into the global table (keys that cannot live in the shared table)
+struct OneValueSource {
+    int dtype;
+    uint64_t bits;
+    __device__ __forceinline__ bool operator()(int, int *dt, uint64_t *b) const { *dt = dtype; *b = bits; return true; }
+};
+__device__ __forceinline__ void gp_global_row(const AggParams &ap, uint64_t key, int dtype, uint64_t bits) {
+    Sector0 s0;
+    unsigned long long *rec = find_slot(ap, key, &s0);
+    if (rec) update_states(ap, rec, s0, OneValueSource{dtype, bits});
+}
+
+// need: bit ST_CNT / ST_SUM / ST_MIN / ST_MAX set when the plan has such a state
+__global__ void __launch_bounds__(GP_AGG_THREADS, 1)
+gp_aggregate_kernel(GroupPart gp, const __grid_constant__ AggParams ap, int val_dtype, int chunks, int need) {
+    extern __shared__ __align__(16) unsigned char gp_smem[];
+    unsigned long long *s_key = (unsigned long long *)gp_smem;
+    double *s_sum = (double *)(s_key + GP_SLOTS);
+    unsigned long long *s_min = (unsigned long long *)(s_sum + GP_SLOTS);
+    unsigned long long *s_max = s_min + GP_SLOTS;
+    unsigned int *s_cnt = (unsigned int *)(s_max + GP_SLOTS);
+    const int tid = threadIdx.x, P = 1 << gp.log2p, items = P * chunks;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int p = item / chunks, c = item % chunks;
+        unsigned long long base = 0;
+        for (int q = 0; q < p; q++) base += gp.totals[q];
+        const unsigned long long len = gp.totals[p];
+        const unsigned long long r0 = base + len * (unsigned long long)c / (unsigned long long)chunks;
+        const unsigned long long r1 = base + len * (unsigned long long)(c + 1) / (unsigned long long)chunks;
+        for (int i = tid; i < GP_SLOTS; i += GP_AGG_THREADS) {
+            s_key[i] = EMPTY_KEY;
+            s_sum[i] = 0.0;
+            s_min[i] = ~0ull;
+            s_max[i] = 0ull;
+            s_cnt[i] = 0u;
+        }
+        __syncthreads();
+        for (unsigned long long rb = r0; rb < r1; rb += 4ull * GP_AGG_THREADS) {
+            unsigned long long key[4], bits[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned long long r = rb + (unsigned long long)j * GP_AGG_THREADS + tid;
+                key[j] = r < r1 ? ld_stream_u64(gp.pkeys + r) : 0ull;
+                bits[j] = r < r1 ? ld_stream_u64(gp.pvals + r) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (rb + (unsigned long long)j * GP_AGG_THREADS + tid >= r1) continue;
+                if (key[j] == EMPTY_KEY) { gp_global_row(ap, key[j], val_dtype, bits[j]); continue; }
+                unsigned slot = __umulhi((unsigned)nqe_mix64(key[j]), (unsigned)GP_SLOTS);
+                int found = -1;
+                for (int probe = 0; probe < GP_MAX_PROBE; probe++) {
+                    const unsigned long long k = *(volatile unsigned long long *)&s_key[slot];
+                    if (k == key[j]) { found = (int)slot; break; }
+                    if (k == EMPTY_KEY) {
+                        const unsigned long long old = atomicCAS(&s_key[slot], (unsigned long long)EMPTY_KEY, key[j]);
+                        if (old == EMPTY_KEY || old == key[j]) { found = (int)slot; break; }
+                    }
+                    slot = slot + 1 == GP_SLOTS ? 0 : slot + 1;
+                }
+                if (found < 0) { gp_global_row(ap, key[j], val_dtype, bits[j]); continue; }
+                const double v = value_as_f64(val_dtype, bits[j]);
+                if (need & (1 << ST_CNT)) atomicAdd(&s_cnt[found], 1u);
+                if (need & (1 << ST_SUM)) atomicAdd(&s_sum[found], v);
+                if (need & ((1 << ST_MIN) | (1 << ST_MAX))) {
+                    const unsigned long long o = nqe_f64_to_ord(v);
+                    if ((need & (1 << ST_MAX)) && o > *(volatile unsigned long long *)&s_max[found]) atomicMax(&s_max[found], o);
+                    if ((need & (1 << ST_MIN)) && v == v && o < *(volatile unsigned long long *)&s_min[found]) atomicMin(&s_min[found], o);
+                }
+            }
+        }
+        __syncthreads();
+        // partial states of this chunk -> global table
+        for (int i = tid; i < GP_SLOTS; i += GP_AGG_THREADS) {
+            const unsigned long long key = s_key[i];
+            if (key == EMPTY_KEY) continue;
+            Sector0 s0;
+            unsigned long long *rec = find_slot(ap, key, &s0);
+            if (!rec) continue; // table full: flagged, the host grows the table and repeats the pass
+            for (int s = 0; s < ap.n_states; s++) {
+                unsigned long long *w = rec + ap.st_off[s];
+                switch (ap.st_kind[s]) {
+                case ST_CNT: red_add_u64(w, (unsigned long long)s_cnt[i]); break;
+                case ST_SUM: red_add_f64(w, s_sum[i]); break;
+                case ST_MIN: red_min_u64(w, s_min[i]); break;
+                default: red_max_u64(w, s_max[i]); break;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -416,6 +634,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         }
         // --- size the table from a sampled cardinality estimate, grow on overflow
         uint64_t capacity = 1024;
+        double est_groups = 1e18;
         if (n > 0) {
             const int64_t n_sample = n < (1 << 20) ? n : (1 << 20);
             const int64_t stride = n / n_sample;
@@ -439,6 +658,61 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 if (distinct > 0.5 * (double)n_sample) est = distinct * ((double)n / (double)n_sample); // still growing
                 if (est > (double)n) est = (double)n;
                 capacity = nqe_agg_capacity(est);
+                est_groups = est;
+            }
+        }
+        // --- partitioned shared-memory path (see gp_* kernels): split once, aggregate inside the retry loop
+        static int agg_part = -1;
+        static int64_t agg_part_min_rows = 0;
+        if (agg_part < 0) {
+            const char *e = getenv("NQE_AGG_PART");
+            agg_part = e ? atoi(e) : 0;
+            e = getenv("NQE_AGG_PART_MIN_ROWS");
+            agg_part_min_rows = e ? atoll(e) : ((int64_t)1 << 24);
+        }
+        bool use_part = false;
+        GroupPart gp;
+        memset(&gp, 0, sizeof gp);
+        std::vector<void *> gp_bufs;
+        int gp_need = 0, gp_chunks = 1, gp_dtype = 0;
+        if (rc == NQE_OK && agg_part && simple && n >= agg_part_min_rows && ap.n_states > 0 &&
+            est_groups <= 32.0 * GP_SLOTS * 0.6) {
+            bool one_src = true;
+            for (int q = 0; q < ap.n_states; q++) {
+                if (ap.st_src[q] != ap.st_src[0]) one_src = false;
+                gp_need |= 1 << ap.st_kind[q];
+            }
+            const DevColRef &vc = ps.cols[ap.st_src[0]];
+            if (one_src && (vc.dtype == NQE_INT64 || vc.dtype == NQE_UINT64 || vc.dtype == NQE_FLOAT64)) {
+                int log2p = 1;
+                while (log2p < 5 && est_groups / (double)(1 << log2p) > 0.55 * GP_SLOTS) log2p++;
+                const size_t P = (size_t)1 << log2p;
+                gp.keys = (const unsigned long long *)ps.cols[key_slot].values;
+                gp.vals = (const unsigned long long *)vc.values;
+                gp.n = n;
+                gp.log2p = log2p;
+                gp.num_tiles = (int32_t)((n + GP_TILE - 1) / GP_TILE);
+                gp_dtype = vc.dtype;
+                gp_chunks = (int)((ctx->sm_count * 8 + P - 1) / P);
+                auto alloc = [&](void **p, size_t bytes) {
+                    if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
+                    if (rc == NQE_OK) gp_bufs.push_back(*p);
+                };
+                alloc((void **)&gp.pkeys, (size_t)n * 8);
+                alloc((void **)&gp.pvals, (size_t)n * 8);
+                alloc((void **)&gp.totals, 2 * P * 8);
+                if (rc == NQE_OK &&
+                    cudaFuncSetAttribute(gp_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SLOTS * 36) != cudaSuccess) {
+                    cudaGetLastError();
+                } else if (rc == NQE_OK) {
+                    cudaMemsetAsync(gp.totals, 0, 2 * P * 8, ctx->stream);
+                    int grid = ctx->sm_count * 6;
+                    if (grid > gp.num_tiles) grid = gp.num_tiles;
+                    gp_count_kernel<<<grid, GP_THREADS, 0, ctx->stream>>>(gp);
+                    gp_scatter_kernel<<<grid, GP_THREADS, 0, ctx->stream>>>(gp);
+                    ctx->launches += 2;
+                    use_part = cudaGetLastError() == cudaSuccess;
+                }
             }
         }
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
@@ -456,7 +730,9 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 const int64_t tiles = (n + kk * AG_THREADS - 1) / (kk * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
+                if (use_part)
+                    gp_aggregate_kernel<<<ctx->sm_count, GP_AGG_THREADS, GP_SLOTS * 36, ctx->stream>>>(gp, ap, gp_dtype, gp_chunks, gp_need);
+                else if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple && agk == 8) group_aggregate_kernel<true, 8><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple) group_aggregate_kernel<true, 4><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else group_aggregate_kernel<false, AG_K><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, 0);
@@ -473,6 +749,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             capacity *= 8;
             if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
         }
+        for (void *p : gp_bufs) nqe_dev_free(ctx, p);
     }
     if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, group_expr == nullptr, n, t);
     timer.stop();

@@ -18,6 +18,7 @@ CASES = [
     ({"NQE_JOIN_SPLIT": "1", "NQE_JOIN_GATHER": "1", "NQE_JOIN_OVERLAP": "0"}, "partitioned_probe_large"),
     ({"NQE_JOIN_FUSE": "1"}, "partitioned_probe_large"),
     ({"NQE_JOINAGG_PART": "1"}, "join_aggregate_partitioned_large"),
+    ({"NQE_AGG_PART": "1", "NQE_AGG_PART_MIN_ROWS": "1000"}, "group_by"),
 ]
 
 

@@ -501,6 +501,68 @@ def test_group_by_random(n, groups, vtype):
         assert a[0] == w[0] and a[3] == w[3] and a[4] == w[4]
 
 
+@pytest.mark.parametrize("n,groups", [(300_000, 5000), (300_000, 110_000), (20_000_000, 100_000)])
+@pytest.mark.parametrize("vtype", ["f64", "i64"])
+def test_group_by_one_value_column(n, groups, vtype):
+    """Bare NULL-free key, every aggregate over ONE NULL-free column -- the BASELINE configs[2] shape and the shape the
+    partitioned shared-memory path (NQE_AGG_PART=1) takes.  No key aggregate here, so groups are matched through their
+    (count, min, max) triples; includes NaN / +-inf values and the key i64::MIN (the table's free-slot marker)."""
+    import pyarrow as pa
+    rng = np.random.default_rng(n // 1000 + groups)
+    k = rng.integers(0, groups, n).astype(np.int64) * 7919 - 12345
+    k[rng.integers(0, n, 50)] = np.iinfo(np.int64).min
+    if vtype == "f64":
+        v = np.round(rng.normal(0, 1000, n), 6)
+        v[rng.integers(0, n, 20)] = np.nan
+        v[rng.integers(0, n, 20)] = np.inf
+        v[rng.integers(0, n, 20)] = -np.inf
+    else:
+        v = rng.integers(-10**9, 10**9, n).astype(np.int64)
+    rb = pa.RecordBatch.from_arrays([pa.array(k), pa.array(v)], names=["k", "v"])
+    nq = G.nq
+    col = nq.ColumnExpr.try_create
+    plan = nq.PhysicalAggregatePlan.create([col(None, 0)], [nq.Count.create(col(None, 1)), nq.Sum.create(col(None, 1)),
+                                                          nq.Avg.create(col(None, 1)), nq.Min.create(col(None, 1)),
+                                                          nq.Max.create(col(None, 1))],
+                                           nq.ScanPlan.create(nq.MemTable.try_create(rb.schema, [rb]), None))
+    out = plan.execute()[0]
+    # expectation with numpy: group ids by sorting the keys
+    uk, inv = np.unique(k, return_inverse=True)
+    g = len(uk)
+    assert out.num_rows == g
+    vf = v.astype(np.float64)
+    cnt = np.bincount(inv, minlength=g)
+    order = np.argsort(inv, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    vs = vf[order]
+    # reference semantics: max is NaN if any NaN (OrderedFloat: NaN greatest), min ignores NaN, identities f64::MAX / f64::MIN
+    has_nan = np.bincount(inv, weights=np.isnan(vf), minlength=g) > 0
+    mx = np.maximum.reduceat(np.where(np.isnan(vs), -np.inf, vs), starts)
+    mx = np.maximum(mx, -np.finfo(np.float64).max)
+    mx = np.where(has_nan, np.nan, mx)
+    mn = np.minimum.reduceat(np.where(np.isnan(vs), np.inf, vs), starts)
+    mn = np.minimum(mn, np.finfo(np.float64).max)
+    with np.errstate(invalid="ignore"):
+        sm = np.add.reduceat(vs, starts)
+
+    def canon(c, lo, hi):  # sortable (count, min, max) with NaN mapped to a sentinel
+        return sorted(zip(c.tolist(), np.nan_to_num(lo, nan=1e308).tolist(), np.nan_to_num(hi, nan=1e308).tolist(), range(len(c))))
+    got = [out.column(i).to_numpy(zero_copy_only=False) for i in range(5)]
+    gs, ws = canon(got[0].astype(np.int64), got[3], got[4]), canon(cnt, mn, mx)
+    assert [r[:3] for r in gs] == [r[:3] for r in ws]  # count, min, max exact
+    gi, wi = np.array([r[3] for r in gs]), np.array([r[3] for r in ws])
+    # groups that share a (count, min, max) triple cannot be told apart: compare sums only where the triple is unique
+    trip = [r[:3] for r in ws]
+    uniq = np.array([i == 0 or trip[i] != trip[i - 1] for i in range(g)]) & np.array([i == g - 1 or trip[i] != trip[i + 1] for i in range(g)])
+    gsum, wsum = got[1][gi][uniq], sm[wi][uniq]
+    fin = np.isfinite(wsum)
+    assert np.array_equal(np.isnan(gsum), np.isnan(wsum)) and np.array_equal(gsum[~fin & ~np.isnan(wsum)], wsum[~fin & ~np.isnan(wsum)])
+    scale = np.add.reduceat(np.abs(np.where(np.isfinite(vs), vs, 0.0)), starts)[wi][uniq]
+    assert np.all(np.abs(gsum[fin] - wsum[fin]) <= SUM_REL * np.maximum(scale[fin], 1.0))
+    gavg = got[2][gi][uniq]
+    assert np.all(np.abs(gavg[fin] - (wsum / cnt[wi][uniq])[fin]) <= SUM_REL * np.maximum(scale[fin] / cnt[wi][uniq][fin], 1.0))
+
+
 def test_group_by_expression_key_and_special_values():
     nan, inf = float("nan"), float("inf")
     b = O.Batch(["k", "v"], [O.col("i64", [1, 1, None, 2, 3, 3, -2**63, -2**63, 4]),
