@@ -168,3 +168,8 @@ int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const 
 int32_t nqe_agg_table_create(nqe_ctx *ctx, AggParams *ap, uint64_t capacity);
 int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64_t max_groups, nqe_table *t);
 uint64_t nqe_agg_capacity(double est);
+// partitioned shared-memory group-by over paged streams (hash_aggregate.cu; paged_split.cuh)
+struct PagedStreams;
+int32_t nqe_estimate_distinct_u64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, double *est);
+bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m);
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int val_dtype, int need);

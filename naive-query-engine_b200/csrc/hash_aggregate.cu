@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "agg_device.cuh"
+#include "paged_split.cuh"
 
 int32_t nqe_utf8_key_ids(nqe_ctx *ctx, const DevColumn &dict, const DevColumn *probe, DevColumn *dict_ids, DevColumn *probe_ids);
 static const char *agg_fn_name(int op);
@@ -89,128 +90,28 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
 }
 
 // ---------------------------------------------------------------------------
-// Partitioned shared-memory group-by (knob NQE_AGG_PART; EXPERIMENTAL until measured on the GPU).
+// Partitioned shared-memory group-by.
 //
-// The table path above costs one `red` per row per additive state and the L2 retires ~1.5e11 of those per second
-// (profiles/README_r01.md §2).  Here the (key, value) rows are first split into up to 32 partitions by the top bits of
-// the key's hash -- shared-memory-atomic histograms, runs claimed with one global atomic per (tile, partition), rows
-// staged in shared memory and written as contiguous runs; no order is kept, aggregation does not care -- and every
-// partition is then aggregated in SHARED memory (6144-slot open-addressing table per CTA, one CTA per SM): the
-// per-row updates become shared-memory atomics, and only the per-CTA partial states go to the global table (one
-// probe + one `red` per state per GROUP per chunk instead of per ROW).  Rows that do not fit the shared table
-// (a partition with more groups than expected) fall back to the global table one by one, so any key distribution
-// stays correct.  Eligible: bare NULL-free key column, all aggregates over ONE NULL-free 8-byte column.
-constexpr int GP_MAX_PARTS = 32;
-constexpr int GP_K = 8, GP_THREADS = 256, GP_TILE = GP_K * GP_THREADS;
-constexpr int GP_SLOTS = 6144;        // 6144 x 36 bytes = 216 KB of shared memory
-constexpr int GP_AGG_THREADS = 1024;
-constexpr int GP_MAX_PROBE = 48;
-
-struct GroupPart {
-    const unsigned long long *keys, *vals; // input columns
-    int64_t n;
-    int32_t log2p, num_tiles;
-    unsigned long long *pkeys, *pvals;     // rows in partition order
-    unsigned long long *totals;            // [P] rows per partition, then [P] claim cursors
-};
-
-__device__ __forceinline__ int gp_part(uint64_t h, int log2p) { return (int)(h >> (64 - log2p)); }
-
-__global__ void __launch_bounds__(GP_THREADS) gp_count_kernel(GroupPart gp) {
-    __shared__ unsigned int s_hist[GP_MAX_PARTS];
-    const int tid = threadIdx.x, P = 1 << gp.log2p;
-    if (tid < GP_MAX_PARTS) s_hist[tid] = 0;
-    __syncthreads();
-    for (int tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
-        const int64_t e0 = (int64_t)tile * GP_TILE + tid;
-        unsigned long long key[GP_K];
-#pragma unroll
-        for (int j = 0; j < GP_K; j++) {
-            const int64_t e = e0 + (int64_t)j * GP_THREADS;
-            key[j] = e < gp.n ? ld_stream_u64(gp.keys + e) : 0ull;
-        }
-#pragma unroll
-        for (int j = 0; j < GP_K; j++)
-            if (e0 + (int64_t)j * GP_THREADS < gp.n) atomicAdd(&s_hist[gp_part(nqe_mix64(key[j]), gp.log2p)], 1u);
-    }
-    __syncthreads();
-    if (tid < P && s_hist[tid]) atomicAdd(gp.totals + tid, (unsigned long long)s_hist[tid]);
-}
-
-__global__ void __launch_bounds__(GP_THREADS) gp_scatter_kernel(GroupPart gp) {
-    __shared__ unsigned long long s_keys[GP_TILE], s_vals[GP_TILE];
-    __shared__ unsigned char s_pid[GP_TILE];
-    __shared__ unsigned int s_cnt[GP_MAX_PARTS], s_start[GP_MAX_PARTS + 1];
-    __shared__ unsigned long long s_gbase[GP_MAX_PARTS], s_pbase[GP_MAX_PARTS];
-    const int tid = threadIdx.x, lane = tid & 31, P = 1 << gp.log2p;
-    unsigned long long *cursors = gp.totals + P;
-    if (tid < 32) { // partition bases: exclusive scan of the totals (P <= 32: one warp)
-        const unsigned long long t = tid < P ? gp.totals[tid] : 0ull;
-        unsigned long long incl = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += x;
-        }
-        s_pbase[tid] = incl - t;
-        s_cnt[tid] = 0;
-    }
-    __syncthreads();
-    for (int tile = blockIdx.x; tile < gp.num_tiles; tile += gridDim.x) {
-        const int64_t e0 = (int64_t)tile * GP_TILE + tid;
-        unsigned long long key[GP_K], val[GP_K];
-        int pid[GP_K];
-        unsigned rank[GP_K];
-#pragma unroll
-        for (int j = 0; j < GP_K; j++) {
-            const int64_t e = e0 + (int64_t)j * GP_THREADS;
-            key[j] = e < gp.n ? ld_stream_u64(gp.keys + e) : 0ull;
-            val[j] = e < gp.n ? ld_stream_u64(gp.vals + e) : 0ull;
-        }
-#pragma unroll
-        for (int j = 0; j < GP_K; j++) {
-            pid[j] = gp_part(nqe_mix64(key[j]), gp.log2p);
-            rank[j] = 0;
-            if (e0 + (int64_t)j * GP_THREADS < gp.n) rank[j] = atomicAdd(&s_cnt[pid[j]], 1u);
-        }
-        __syncthreads();
-        if (tid < 32) { // claim this tile's run in every partition; local starts for the staging order
-            const unsigned c = tid < P ? s_cnt[tid] : 0u;
-            unsigned incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += x;
-            }
-            s_start[tid] = incl - c;
-            if (tid == 31) s_start[32] = incl;
-            if (tid < P && c) s_gbase[tid] = s_pbase[tid] + atomicAdd(cursors + tid, (unsigned long long)c);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < GP_K; j++)
-            if (e0 + (int64_t)j * GP_THREADS < gp.n) {
-                const unsigned local = s_start[pid[j]] + rank[j];
-                s_keys[local] = key[j];
-                s_vals[local] = val[j];
-                s_pid[local] = (unsigned char)pid[j];
-            }
-        __syncthreads();
-        const unsigned total = s_start[32];
-#pragma unroll
-        for (int j = 0; j < GP_K; j++) {
-            const unsigned idx = tid + j * GP_THREADS;
-            if (idx < total) {
-                const int p = s_pid[idx];
-                const unsigned long long pos = s_gbase[p] + (idx - s_start[p]);
-                gp.pkeys[pos] = s_keys[idx];
-                gp.pvals[pos] = s_vals[idx];
-            }
-        }
-        if (tid < 32) s_cnt[tid] = 0;
-        __syncthreads(); // staging buffers and counters are reused by the next tile
-    }
-}
+// The table path above costs one L2 sector read plus one `red` per additive state per ROW, and the L2 retires only
+// ~1.5e11 of those per second (profiles/README_r01.md 2): 2.25 ms per 1e8 rows whatever the kernel does.  Shared
+// memory takes ~20x that rate, but holds only a few thousand groups per SM.  So the (key, value) rows are first split
+// by key hash into P partitions of ~1400 groups (paged_split.cuh: one pass, no count pass), and every partition is
+// then aggregated by sm_count / P CTAs, each in its own 4096-slot open-addressing table in SHARED memory
+//      ks[slot] = {key, f64 sum bits}   mm[slot] = {min, max} (OrderedFloat encoding)   cnt[slot]
+// Pages (4096 rows, 64 KB) arrive through one cp.async.bulk-filled buffer: a thread copies its four rows into
+// registers, the buffer is handed back at once and the next page flies while the CTA updates its table.  Per row:
+// one 16-byte probe read (key + current sum), a native 32-bit shared atomic for the count, one 64-bit CAS for the sum
+// (seeded with the sum the probe saw; shared memory has no f64 add), one 16-byte read of {min, max} and a CAS only
+// when the value improves one of them.  The four rows of a thread are kept in lock step so that their shared-memory
+// round trips overlap.  At the end every CTA folds its partial states into the global table (one probe + one `red`
+// per state per GROUP).  Rows that do not fit (a partition with more groups than estimated, probe sequence too long)
+// go to the global table one by one, so any key distribution stays correct.
+// Eligible: all aggregates over ONE NULL-free 8-byte column; the key may be any Int64/UInt64 expression.
+constexpr int GA_THREADS = 1024, GA_K = 4;
+constexpr int GA_SLOTS = 4096;
+constexpr int GA_MAX_PROBE = 32;
+static_assert(GA_THREADS * GA_K == PS_PAGE_ROWS, "one page per step");
+constexpr size_t GA_SMEM = (size_t)PS_PAGE_ROWS * 16 + (size_t)GA_SLOTS * 36 + sizeof(PsPageBuf);
 
 // one row straight into the global table (keys that cannot live in the shared table)
 struct OneValueSource {
@@ -224,86 +125,147 @@ __device__ __forceinline__ void gp_global_row(const AggParams &ap, uint64_t key,
     if (rec) update_states(ap, rec, s0, OneValueSource{dtype, bits});
 }
 
+__device__ __forceinline__ unsigned long long ga_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long val) {
+    return atomicCAS(p, cmp, val);
+}
+
 // need: bit ST_CNT / ST_SUM / ST_MIN / ST_MAX set when the plan has such a state
-__global__ void __launch_bounds__(GP_AGG_THREADS, 1)
-gp_aggregate_kernel(GroupPart gp, const __grid_constant__ AggParams ap, int val_dtype, int chunks, int need) {
-    extern __shared__ __align__(16) unsigned char gp_smem[];
-    unsigned long long *s_key = (unsigned long long *)gp_smem;
-    double *s_sum = (double *)(s_key + GP_SLOTS);
-    unsigned long long *s_min = (unsigned long long *)(s_sum + GP_SLOTS);
-    unsigned long long *s_max = s_min + GP_SLOTS;
-    unsigned int *s_cnt = (unsigned int *)(s_max + GP_SLOTS);
-    const int tid = threadIdx.x, P = 1 << gp.log2p, items = P * chunks;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int p = item / chunks, c = item % chunks;
-        unsigned long long base = 0;
-        for (int q = 0; q < p; q++) base += gp.totals[q];
-        const unsigned long long len = gp.totals[p];
-        const unsigned long long r0 = base + len * (unsigned long long)c / (unsigned long long)chunks;
-        const unsigned long long r1 = base + len * (unsigned long long)(c + 1) / (unsigned long long)chunks;
-        for (int i = tid; i < GP_SLOTS; i += GP_AGG_THREADS) {
-            s_key[i] = EMPTY_KEY;
-            s_sum[i] = 0.0;
-            s_min[i] = ~0ull;
-            s_max[i] = 0ull;
-            s_cnt[i] = 0u;
-        }
-        __syncthreads();
-        for (unsigned long long rb = r0; rb < r1; rb += 4ull * GP_AGG_THREADS) {
-            unsigned long long key[4], bits[4];
+__global__ void __launch_bounds__(GA_THREADS, 1)
+gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_constant__ AggParams ap, int m, int val_dtype, int need) {
+    extern __shared__ __align__(128) unsigned char ga_smem[];
+    ulonglong2 *s_page = (ulonglong2 *)ga_smem;
+    ulonglong2 *s_ks = s_page + PS_PAGE_ROWS;
+    ulonglong2 *s_mm = s_ks + GA_SLOTS;
+    unsigned int *s_cnt = (unsigned int *)(s_mm + GA_SLOTS);
+    PsPageBuf &buf = *(PsPageBuf *)(s_cnt + GA_SLOTS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int p = blockIdx.x / m, sub = blockIdx.x % m;
+    const unsigned long long rows_p = st.cursor[p];
+    const unsigned npg = (unsigned)((rows_p + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
+    for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
+        s_ks[i] = make_ulonglong2(EMPTY_KEY, 0ull);  // sum = +0.0
+        s_mm[i] = make_ulonglong2(~0ull, 0ull);      // identities of min / max in the ordered encoding
+        s_cnt[i] = 0u;
+    }
+    ps_pagebuf_init(buf, GA_THREADS / 32);
+    __syncthreads();
+    const unsigned int *pt = st.pt + (size_t)p * st.pt_stride;
+    unsigned long long pol = 0;
+    unsigned next_phys = 0; // thread 0: pool page of the page after the one in flight
+    if (tid == 0) {
+        pol = nqe_policy_evict_first();
+        if ((unsigned)sub < npg) ps_issue_page(st, buf, s_page, pt[sub] - 1u, ps_page_rows(st, p, sub), pol);
+        if ((unsigned)(sub + m) < npg) next_phys = pt[sub + m] - 1u;
+    }
+    uint32_t it = 0;
+    for (unsigned q = sub; q < npg; q += m, it++) {
+        const unsigned fill = ps_page_rows(st, p, q);
+        nqe_mbar_wait(&buf.full, it & 1u);
+        unsigned long long key[GA_K], bits[GA_K];
+        uint32_t live = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned long long r = rb + (unsigned long long)j * GP_AGG_THREADS + tid;
-                key[j] = r < r1 ? ld_stream_u64(gp.pkeys + r) : 0ull;
-                bits[j] = r < r1 ? ld_stream_u64(gp.pvals + r) : 0ull;
+        for (int j = 0; j < GA_K; j++) {
+            const unsigned idx = j * GA_THREADS + tid;
+            ulonglong2 r = make_ulonglong2(0ull, 0ull);
+            if (idx < fill) { r = s_page[idx]; live |= 1u << j; }
+            key[j] = r.x;
+            bits[j] = r.y;
+        }
+        __syncwarp();
+        if (lane == 0) nqe_mbar_arrive(&buf.empty);
+        if (tid == 0 && q + m < npg) { // the producer: refill the buffer as soon as every warp has let go of it
+            nqe_mbar_wait(&buf.empty, it & 1u);
+            ps_issue_page(st, buf, s_page, next_phys, ps_page_rows(st, p, q + m), pol);
+            if (q + 2 * m < npg) next_phys = pt[q + 2 * m] - 1u;
+        }
+        // ---- find or claim the slots: first probes of the four rows together, collisions walked one row at a time
+        unsigned slot[GA_K];
+        ulonglong2 ks[GA_K];
+#pragma unroll
+        for (int j = 0; j < GA_K; j++) {
+            slot[j] = __umulhi((unsigned)nqe_mix64(key[j]), (unsigned)GA_SLOTS);
+            ks[j] = s_ks[slot[j]];
+        }
+        uint32_t found = 0;
+#pragma unroll
+        for (int j = 0; j < GA_K; j++) {
+            if (!((live >> j) & 1u)) continue;
+            if (key[j] == EMPTY_KEY) continue; // i64::MIN marks free slots: that key lives in the global table only
+            for (int probe = 0; probe < GA_MAX_PROBE; probe++) {
+                unsigned long long k = ks[j].x;
+                if (k == EMPTY_KEY) {
+                    k = ga_cas64(&s_ks[slot[j]].x, (unsigned long long)EMPTY_KEY, key[j]);
+                    if (k == EMPTY_KEY) k = key[j];
+                }
+                if (k == key[j]) { found |= 1u << j; break; }
+                slot[j] = slot[j] + 1 == GA_SLOTS ? 0 : slot[j] + 1;
+                ks[j] = s_ks[slot[j]];
+            }
+        }
+        const uint32_t lost = live & ~found; // shared table full / i64::MIN key: straight to the global table
+        if (lost) {
+#pragma unroll
+            for (int j = 0; j < GA_K; j++)
+                if ((lost >> j) & 1u) gp_global_row(ap, key[j], val_dtype, bits[j]);
+        }
+        // ---- updates, the four rows in lock step (bits[j] becomes the value as f64)
+        unsigned long long seen[GA_K], old[GA_K];
+#pragma unroll
+        for (int j = 0; j < GA_K; j++) {
+            seen[j] = ks[j].y;
+            bits[j] = (unsigned long long)__double_as_longlong(value_as_f64(val_dtype, bits[j]));
+            if (((found >> j) & 1u) && (need & (1 << ST_CNT))) atomicAdd(&s_cnt[slot[j]], 1u);
+        }
+        if (need & (1 << ST_SUM)) {
+#pragma unroll
+            for (int j = 0; j < GA_K; j++) {
+                old[j] = seen[j];
+                if ((found >> j) & 1u)
+                    old[j] = ga_cas64(&s_ks[slot[j]].y, seen[j],
+                                      (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
+                                                                               __longlong_as_double((long long)bits[j])));
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (rb + (unsigned long long)j * GP_AGG_THREADS + tid >= r1) continue;
-                if (key[j] == EMPTY_KEY) { gp_global_row(ap, key[j], val_dtype, bits[j]); continue; }
-                unsigned slot = __umulhi((unsigned)nqe_mix64(key[j]), (unsigned)GP_SLOTS);
-                int found = -1;
-                // left to the compiler's full unrolling on purpose: `#pragma unroll 1` here was measured 3x SLOWER (2.2 -> 7.0 ms):
-                // the kernel is latency-bound (32 warps per SM) and the unrolled form lets the 4 rows' probe chains overlap
-                for (int probe = 0; probe < GP_MAX_PROBE; probe++) {
-                    const unsigned long long k = *(volatile unsigned long long *)&s_key[slot];
-                    if (k == key[j]) { found = (int)slot; break; }
-                    if (k == EMPTY_KEY) {
-                        const unsigned long long old = atomicCAS(&s_key[slot], (unsigned long long)EMPTY_KEY, key[j]);
-                        if (old == EMPTY_KEY || old == key[j]) { found = (int)slot; break; }
-                    }
-                    slot = slot + 1 == GP_SLOTS ? 0 : slot + 1;
-                }
-                if (found < 0) { gp_global_row(ap, key[j], val_dtype, bits[j]); continue; }
-                const double v = value_as_f64(val_dtype, bits[j]);
-                if (need & (1 << ST_CNT)) atomicAdd(&s_cnt[found], 1u);
-                if (need & (1 << ST_SUM)) atomicAdd(&s_sum[found], v);
-                if (need & ((1 << ST_MIN) | (1 << ST_MAX))) {
-                    const unsigned long long o = nqe_f64_to_ord(v);
-                    if ((need & (1 << ST_MAX)) && o > *(volatile unsigned long long *)&s_max[found]) atomicMax(&s_max[found], o);
-                    if ((need & (1 << ST_MIN)) && v == v && o < *(volatile unsigned long long *)&s_min[found]) atomicMin(&s_min[found], o);
+            for (int j = 0; j < GA_K; j++) {
+                if (!((found >> j) & 1u)) continue;
+                while (old[j] != seen[j]) { // another row of this group got in between: retry on the value it left
+                    seen[j] = old[j];
+                    old[j] = ga_cas64(&s_ks[slot[j]].y, seen[j],
+                                      (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
+                                                                               __longlong_as_double((long long)bits[j])));
                 }
             }
         }
-        __syncthreads();
-        // partial states of this chunk -> global table
-        for (int i = tid; i < GP_SLOTS; i += GP_AGG_THREADS) {
-            const unsigned long long key = s_key[i];
-            if (key == EMPTY_KEY) continue;
-            Sector0 s0;
-            unsigned long long *rec = find_slot(ap, key, &s0);
-            if (!rec) continue; // table full: flagged, the host grows the table and repeats the pass
-            for (int s = 0; s < ap.n_states; s++) {
-                unsigned long long *w = rec + ap.st_off[s];
-                switch (ap.st_kind[s]) {
-                case ST_CNT: red_add_u64(w, (unsigned long long)s_cnt[i]); break;
-                case ST_SUM: red_add_f64(w, s_sum[i]); break;
-                case ST_MIN: red_min_u64(w, s_min[i]); break;
-                default: red_max_u64(w, s_max[i]); break;
-                }
+        if (need & ((1 << ST_MIN) | (1 << ST_MAX))) {
+#pragma unroll
+            for (int j = 0; j < GA_K; j++) {
+                if (!((found >> j) & 1u)) continue;
+                const ulonglong2 mm = s_mm[slot[j]];
+                const double v = __longlong_as_double((long long)bits[j]);
+                const unsigned long long o = nqe_f64_to_ord(v);
+                if ((need & (1 << ST_MAX)) && o > mm.y) atomicMax(&s_mm[slot[j]].y, o);
+                if ((need & (1 << ST_MIN)) && v == v && o < mm.x) atomicMin(&s_mm[slot[j]].x, o); // min never picks NaN (min.rs:49)
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    // partial states of this CTA -> global table
+    for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
+        const ulonglong2 e = s_ks[i];
+        if (e.x == EMPTY_KEY) continue;
+        Sector0 s0;
+        unsigned long long *rec = find_slot(ap, e.x, &s0);
+        if (!rec) continue; // table full: flagged, the host grows the table and repeats this kernel
+        const ulonglong2 x = s_mm[i];
+        for (int s = 0; s < ap.n_states; s++) {
+            unsigned long long *w = rec + ap.st_off[s];
+            switch (ap.st_kind[s]) {
+            case ST_CNT: red_add_u64(w, (unsigned long long)s_cnt[i]); break;
+            case ST_SUM: red_add_f64(w, __longlong_as_double((long long)e.y)); break;
+            case ST_MIN: red_min_u64(w, x.x); break;
+            default: red_max_u64(w, x.y); break;
+            }
+        }
     }
 }
 
@@ -407,7 +369,61 @@ __global__ void popcount_kernel(const uint32_t *bitmap, int n_words, unsigned lo
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
+// distinct values of an 8-byte column, estimated by linear counting over a strided sample
+__global__ void distinct_sample_kernel(const unsigned long long *col, int64_t stride, int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sample) return;
+    const uint32_t h = (uint32_t)(nqe_mix64(col[i * stride]) >> 32) & bits_mask;
+    atomicOr(bitmap + (h >> 5), 1u << (h & 31));
+}
+
 } // namespace
+
+static double linear_count(uint64_t ones, uint32_t bits, int64_t n, int64_t n_sample) {
+    const double m = (double)bits, z = m - (double)ones;
+    const double distinct = z > 0 ? -m * log(z / m) : m * 16;
+    double est = distinct;
+    if (distinct > 0.5 * (double)n_sample) est = distinct * ((double)n / (double)n_sample); // still growing
+    return est > (double)n ? (double)n : est;
+}
+
+int32_t nqe_estimate_distinct_u64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, double *est) {
+    *est = 0;
+    if (n <= 0) return NQE_OK;
+    const int64_t n_sample = n < (1 << 20) ? n : (1 << 20), stride = n / n_sample;
+    const uint32_t bits = 1u << 23;
+    void *bm = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &bm, bits / 8));
+    cudaMemsetAsync(bm, 0, bits / 8, ctx->stream);
+    cudaMemsetAsync(ctx->d_scratch + 8, 0, sizeof(uint64_t), ctx->stream);
+    distinct_sample_kernel<<<(unsigned)((n_sample + 255) / 256), 256, 0, ctx->stream>>>(col, stride, n_sample, (uint32_t *)bm, bits - 1);
+    popcount_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t *)bm, bits / 32, (unsigned long long *)(ctx->d_scratch + 8));
+    ctx->launches += 2;
+    cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    nqe_dev_free(ctx, bm);
+    if (e != cudaSuccess) return nqe_fail(ctx, NQE_ERR_CUDA, "distinct estimate failed: %s", cudaGetErrorString(e));
+    *est = linear_count(ctx->h_scratch[8], bits, n, n_sample);
+    return NQE_OK;
+}
+
+// partitions for the shared-memory group-by: <= 0.45 * GA_SLOTS expected groups per partition, P * m CTAs, one per SM
+bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m) {
+    const int want = (int)(est_groups * 1.15 / (0.45 * GA_SLOTS)) + 1;
+    if (want > ctx->sm_count || want > PS_MAX_PARTS) return false;
+    *m = ctx->sm_count / want;
+    *P = ctx->sm_count / *m;
+    if (*P > PS_MAX_PARTS) *P = PS_MAX_PARTS;
+    return true;
+}
+
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int val_dtype, int need) {
+    NQE_CUDA(ctx, cudaFuncSetAttribute(gp2_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
+    gp2_aggregate_kernel<<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, val_dtype, need);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
 
 static const char *agg_fn_name(int op) {
     static const char *n[] = {"Count", "Sum", "Avg", "min", "Max"};
@@ -663,57 +679,53 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 est_groups = est;
             }
         }
-        // --- partitioned shared-memory path (see gp_* kernels): split once, aggregate inside the retry loop
+        // --- partitioned shared-memory path (gp2_aggregate_kernel): split once, aggregate inside the retry loop
         static int agg_part = -1;
         static int64_t agg_part_min_rows = 0;
         if (agg_part < 0) {
             const char *e = getenv("NQE_AGG_PART");
-            agg_part = e ? atoi(e) : 0;
+            agg_part = e ? atoi(e) : 1;
             e = getenv("NQE_AGG_PART_MIN_ROWS");
-            agg_part_min_rows = e ? atoll(e) : ((int64_t)1 << 24);
+            agg_part_min_rows = e ? atoll(e) : ((int64_t)1 << 22);
         }
         bool use_part = false;
-        GroupPart gp;
-        memset(&gp, 0, sizeof gp);
-        std::vector<void *> gp_bufs;
-        int gp_need = 0, gp_chunks = 1, gp_dtype = 0;
-        if (rc == NQE_OK && agg_part && simple && n >= agg_part_min_rows && ap.n_states > 0 &&
-            est_groups <= 32.0 * GP_SLOTS * 0.6) {
+        PagedStreams streams;
+        memset(&streams, 0, sizeof streams);
+        int gp_need = 0, gp_m = 1, gp_dtype = 0;
+        if (rc == NQE_OK && agg_part && n >= agg_part_min_rows && ap.n_states > 0 && est_groups >= 2048.0) {
             bool one_src = true;
             for (int q = 0; q < ap.n_states; q++) {
                 if (ap.st_src[q] != ap.st_src[0]) one_src = false;
                 gp_need |= 1 << ap.st_kind[q];
             }
             const DevColRef &vc = ps.cols[ap.st_src[0]];
-            if (one_src && (vc.dtype == NQE_INT64 || vc.dtype == NQE_UINT64 || vc.dtype == NQE_FLOAT64)) {
-                int log2p = 1;
-                while (log2p < 5 && est_groups / (double)(1 << log2p) > 0.55 * GP_SLOTS) log2p++;
-                const size_t P = (size_t)1 << log2p;
-                gp.keys = (const unsigned long long *)ps.cols[key_slot].values;
-                gp.vals = (const unsigned long long *)vc.values;
-                gp.n = n;
-                gp.log2p = log2p;
-                gp.num_tiles = (int32_t)((n + GP_TILE - 1) / GP_TILE);
+            int P = 0;
+            if (!nqe_gp2_plan(ctx, est_groups, &P, &gp_m)) P = 0;
+            if (P > 0 && one_src && !vc.validity && (vc.dtype == NQE_INT64 || vc.dtype == NQE_UINT64 || vc.dtype == NQE_FLOAT64)) {
                 gp_dtype = vc.dtype;
-                gp_chunks = (int)((ctx->sm_count * 8 + P - 1) / P);
-                auto alloc = [&](void **p, size_t bytes) {
-                    if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
-                    if (rc == NQE_OK) gp_bufs.push_back(*p);
-                };
-                alloc((void **)&gp.pkeys, (size_t)n * 8);
-                alloc((void **)&gp.pvals, (size_t)n * 8);
-                alloc((void **)&gp.totals, 2 * P * 8);
-                if (rc == NQE_OK &&
-                    cudaFuncSetAttribute(gp_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SLOTS * 36) != cudaSuccess) {
-                    cudaGetLastError();
-                } else if (rc == NQE_OK) {
-                    cudaMemsetAsync(gp.totals, 0, 2 * P * 8, ctx->stream);
-                    int grid = ctx->sm_count * 6;
-                    if (grid > gp.num_tiles) grid = gp.num_tiles;
-                    gp_count_kernel<<<grid, GP_THREADS, 0, ctx->stream>>>(gp);
-                    gp_scatter_kernel<<<grid, GP_THREADS, 0, ctx->stream>>>(gp);
-                    ctx->launches += 2;
-                    use_part = cudaGetLastError() == cudaSuccess;
+                rc = nqe_ps_create(ctx, n, P, &streams);
+                if (rc == NQE_OK) {
+                    const size_t smem = nqe_ps_split_smem();
+                    PsSplitArgs sa{simple ? (const unsigned long long *)ps.cols[key_slot].values : nullptr,
+                                   (const unsigned long long *)vc.values, n};
+                    const int64_t tiles = (n + PS_SPLIT_THREADS * PS_SPLIT_K - 1) / (PS_SPLIT_THREADS * PS_SPLIT_K);
+                    int grid = ctx->sm_count * 2;
+                    if (grid > tiles) grid = (int)tiles;
+                    const PartByHash part{(uint32_t)P};
+                    cudaError_t e1, e2 = cudaSuccess;
+                    if (simple) {
+                        e1 = cudaFuncSetAttribute(ps_split_kernel<false, PartByHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e1 == cudaSuccess && e2 == cudaSuccess)
+                            ps_split_kernel<false, PartByHash><<<grid, PS_SPLIT_THREADS, smem, ctx->stream>>>(streams, sa, part, ps, ap.status);
+                    } else {
+                        e1 = cudaFuncSetAttribute(ps_split_kernel<true, PartByHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e1 == cudaSuccess && e2 == cudaSuccess)
+                            ps_split_kernel<true, PartByHash><<<grid, PS_SPLIT_THREADS, smem, ctx->stream>>>(streams, sa, part, ps, ap.status);
+                    }
+                    ctx->launches++;
+                    if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                        rc = nqe_fail(ctx, NQE_ERR_CUDA, "group-by split launch failed");
+                    use_part = rc == NQE_OK;
                 }
             }
         }
@@ -732,26 +744,27 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 const int64_t tiles = (n + kk * AG_THREADS - 1) / (kk * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                if (use_part)
-                    gp_aggregate_kernel<<<ctx->sm_count, GP_AGG_THREADS, GP_SLOTS * 36, ctx->stream>>>(gp, ap, gp_dtype, gp_chunks, gp_need);
+                if (use_part) rc = nqe_gp2_aggregate(ctx, streams, ap, gp_m, gp_dtype, gp_need);
                 else if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple && agk == 8) group_aggregate_kernel<true, 8><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple) group_aggregate_kernel<true, 4><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else group_aggregate_kernel<false, AG_K><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, 0);
-                ctx->launches++;
+                if (!use_part) ctx->launches++;
+                if (rc != NQE_OK) break;
             }
             rc = read_scratch(ctx, 2);
             if (rc != NQE_OK) break;
             const uint32_t st = (uint32_t)ctx->h_scratch[1];
             if (st & DEV_ERR_DIV0) { rc = nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error"); break; }
             if (st & DEV_ERR_OVERFLOW) { rc = nqe_fail(ctx, NQE_ERR_PANIC, "attempt to divide with overflow"); break; }
+            if (st & DEV_ERR_CAPACITY) { rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: paged stream pool exhausted"); break; }
             if (!(st & DEV_ERR_TABLE_FULL)) break;
             nqe_dev_free(ctx, ap.table);
             ap.table = nullptr;
             capacity *= 8;
             if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
         }
-        for (void *p : gp_bufs) nqe_dev_free(ctx, p);
+        nqe_ps_destroy(ctx, &streams);
     }
     if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, group_expr == nullptr, n, t);
     timer.stop();

@@ -3,14 +3,9 @@
 //
 // Build (hash_join.rs:58-78): the build side's raw key words (validity is ignored,
 // :67) go into one open-addressing multimap; a slot is claimed with a CAS on its row
-// word.  Two slot formats:
-//   thin  16 B  {key, build row}                      any build table
-//   fat   32 B  {key, build row, payload0, payload1}  build tables whose non-key columns
-//               are at most two NULL-free 8-byte columns (the PK-FK dimension-table
-//               shape): one 32-byte sector then holds everything the probe needs, so the
-//               dependent payload gather -- a second random HBM access -- disappears
-// Slots are inserted with one 128-bit CAS, which also tells the build whether any key
-// repeats, so unique-key probes stop at the first match.
+// word.  Slots are 16 bytes {key, build row} -- or {key, payload} when the plan needs exactly one
+// build-side value per match (JoinTable::rowpay) -- and are inserted with one 128-bit CAS, which
+// also tells the build whether any key repeats, so unique-key probes stop at the first match.
 //
 // Probe (hash_join.rs:80-103, 236-246): one pass over the probe side.  Every tile looks
 // its rows up (the first table probe of a thread's K rows is issued together, collisions
@@ -24,6 +19,7 @@
 #include "agg_device.cuh"
 #include "hash_common.cuh"
 #include "nqe_internal.cuh"
+#include "paged_split.cuh"
 
 int32_t nqe_pack_bytes(nqe_ctx *ctx, const uint8_t *bytes, int64_t n, uint32_t *words, unsigned long long *zeros);
 
@@ -44,14 +40,10 @@ struct Slot {
 };
 
 struct JoinTable {
-    unsigned long long *words; // slot s starts at words + (s << shift)
+    unsigned long long *words; // slot s = words[2 s], words[2 s + 1]
     uint64_t cap;     // number of slots (any size: slots are chosen by multiply-high)
-    int32_t shift;    // 1: thin (2 words), 2: fat (4 words)
     int32_t has_dups;
     int32_t key_col;  // build-side key column
-    int32_t n_pay;    // fat: number of payload columns (<= 2)
-    int32_t pay_col[2];
-    const unsigned long long *pay_src[2];
     // "payload in the row word": when the plan needs exactly ONE build-side value per match (the only non-key
     // build column of a join, or the group key of a fused join -> group-by) the slot's second word holds that
     // value instead of the build row number, so a match costs one random access, not two (slot, then column[row]).
@@ -68,7 +60,7 @@ struct ColSrc {
     int32_t pad;
 };
 
-__device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uint64_t s) { return jt.words + (s << jt.shift); }
+__device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uint64_t s) { return jt.words + (s << 1); }
 // Random accesses.  Measured on B200 (scratch/l2gran.cu, profiles/join_groupby_r01.md): an L2 sector miss
 // reads 128 bytes from DRAM (the whole line is installed) whatever the load flavour (.nc, .cg,
 // .L1::no_allocate) and whatever cudaLimitMaxL2FetchGranularity says; the .L2::64B prefetch-size
@@ -76,11 +68,6 @@ __device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uin
 // (~1.7e10 /s), not by bytes -- so the plain read-only path is kept.
 __device__ __forceinline__ ulonglong2 ld_cg_v2(const unsigned long long *p) { return __ldg((const ulonglong2 *)p); }
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldg(p); }
-__device__ __forceinline__ ulonglong4 ld_v4(const unsigned long long *p) {
-    ulonglong4 v;
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.x), "=l"(v.y), "=l"(v.z), "=l"(v.w) : "l"(p));
-    return v;
-}
 // slot of a key: multiply-high range reduction, so the capacity need not be a power of two
 __device__ __forceinline__ uint64_t join_slot_of(const JoinTable &jt, unsigned long long key) {
     return __umul64hi(nqe_mix64(key), jt.cap);
@@ -89,7 +76,6 @@ __device__ __forceinline__ Slot ld_slot(const JoinTable &jt, uint64_t s) {
     const ulonglong2 v = ld_cg_v2(slot_ptr(jt, s));
     return Slot{v.x, v.y};
 }
-__device__ __forceinline__ ulonglong2 ld_payload(const JoinTable &jt, uint64_t s) { return ld_cg_v2(slot_ptr(jt, s) + 2); }
 
 __global__ void join_clear_kernel(JoinTable jt, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,10 +117,6 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
         unsigned long long *p = slot_ptr(jt, s);
         const ulonglong2 old = cas128(p, make_ulonglong2(0ull, EMPTY_ROW), make_ulonglong2(key, rowword));
         if (old.y == EMPTY_ROW) {
-            if (jt.shift == 2) {
-                p[2] = jt.n_pay > 0 ? jt.pay_src[0][i] : 0ull;
-                p[3] = jt.n_pay > 1 ? jt.pay_src[1][i] : 0ull;
-            }
             if (dup) *dupflag = 1u;
             return;
         }
@@ -146,25 +128,15 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
 // K rows is issued together (K independent loads in flight; at load factor <= 0.6 most rows
-// resolve there), collisions are then walked one row at a time.  FAT: the whole 32-byte slot
-// (key, row, two payload words) comes with ONE 256-bit load -- one random sector per probe row.
-template <int K, bool FAT>
+// resolve there), collisions are then walked one row at a time.
+template <int K>
 __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
-                                            unsigned long long (&brow)[K], uint64_t (&slot)[K], ulonglong2 (&pay)[K]) {
+                                            unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
     Slot first[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
         slot[j] = join_slot_of(jt, key[j]);
-        pay[j] = make_ulonglong2(0, 0);
-        if ((want >> j) & 1u) {
-            if (FAT) {
-                const ulonglong4 v = ld_v4(slot_ptr(jt, slot[j]));
-                first[j] = Slot{v.x, v.y};
-                pay[j] = make_ulonglong2(v.z, v.w);
-            } else {
-                first[j] = ld_slot(jt, slot[j]);
-            }
-        }
+        if ((want >> j) & 1u) first[j] = ld_slot(jt, slot[j]);
     }
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -174,13 +146,7 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
         while (sl.row != EMPTY_ROW) {
             if (sl.key == key[j]) { brow[j] = sl.row; break; }
             slot[j] = slot[j] + 1 == jt.cap ? 0 : slot[j] + 1;
-            if (FAT) {
-                const ulonglong4 v = ld_v4(slot_ptr(jt, slot[j]));
-                sl = Slot{v.x, v.y};
-                pay[j] = make_ulonglong2(v.z, v.w);
-            } else {
-                sl = ld_slot(jt, slot[j]);
-            }
+            sl = ld_slot(jt, slot[j]);
         }
     }
 }
@@ -245,12 +211,7 @@ struct PartJoin {
     unsigned long long *part_base;  // [P + 1]: first position of the partition in the partitioned order
     unsigned long long *pkeys;      // keys in partitioned order
     unsigned int *ppos32;           // per probe row (original order): its position in the partitioned order
-    unsigned long long *res0;       // per position: thin = build row (EMPTY_ROW: no match), fat = payload word 0
-    unsigned long long *res1;       // fat, two payload columns: payload word 1
-    unsigned int *mbits;            // fat: match bit per position
-    int32_t n_carry, pad;           // probe-side columns that travel with the keys (fused join -> aggregate)
-    const unsigned long long *carry_src[8];
-    unsigned long long *carry_dst[8];
+    unsigned long long *res0;       // per position: build row or payload (EMPTY_ROW: no match)
 };
 
 // streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
@@ -297,41 +258,6 @@ __device__ __forceinline__ void pj_warp_hist(const unsigned long long (&key)[K],
         rank[j] = __popc(own & ltmask);
         cnt[j] = __popc(bucket);
     }
-}
-
-// pass 1: per-tile partition counts (+ partition totals).  tile_cnt is partition-major: [p][tile].
-__global__ void __launch_bounds__(HJ_THREADS) pj_count_kernel(PartJoin pj, unsigned long long *totals) {
-    constexpr int K = PJ_K, TILE = K * HJ_THREADS;
-    __shared__ unsigned int s_w[HJ_WARPS][PJ_MAX_PARTS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, P = 1 << pj.log2p;
-    unsigned long long mine = 0;
-    for (int tile = blockIdx.x; tile < pj.num_tiles; tile += gridDim.x) {
-        const int64_t e0 = (int64_t)tile * TILE + tid;
-        unsigned long long key[K];
-        uint32_t inrange = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            key[j] = e < pj.n ? ld_stream_u64(pj.keys + e) : 0ull;
-            if (e < pj.n) inrange |= 1u << j;
-        }
-        int pid[K];
-        unsigned rank[K], cnt[K], c = 0;
-        pj_warp_hist<K>(key, inrange, pj.log2p, pid, rank, cnt);
-#pragma unroll
-        for (int j = 0; j < K; j++) c += cnt[j];
-        s_w[warp][lane] = c;
-        __syncthreads();
-        if (tid < P) {
-            unsigned t = 0;
-#pragma unroll
-            for (int w = 0; w < HJ_WARPS; w++) t += s_w[w][tid];
-            pj.tile_cnt[(size_t)tid * pj.num_tiles + tile] = t;
-            mine += t;
-        }
-        __syncthreads();
-    }
-    if (tid < P && mine) atomicAdd(totals + tid, mine);
 }
 
 // pass 2: one CTA per partition: exclusive scan of its per-tile counts (contiguous); partition bases
@@ -418,15 +344,13 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_scatter_kernel(PartJoin pj) {
             if ((inrange >> j) & 1u) {
                 const unsigned long long ppos = s_base[pid[j]] + s_c[j * HJ_WARPS + warp][pid[j]] + rank[j];
                 st_ef(pj.pkeys + ppos, key[j], pol);
-                if (pj.ppos32) pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos;
-                for (int c = 0; c < pj.n_carry; c++)
-                    st_ef(pj.carry_dst[c] + ppos, ld_ef(pj.carry_src[c] + e0 + (int64_t)j * HJ_THREADS, pol), pol);
+                pj.ppos32[e0 + (int64_t)j * HJ_THREADS] = (unsigned int)ppos;
             }
         __syncthreads(); // s_c / s_base are reused by the next tile
     }
 }
 
-// ---- split, second generation (knob NQE_JOIN_SPLIT=2; 1 = the kernels above).  Same three passes and the same
+// ---- split, second generation (knob NQE_JOIN_SPLIT=2; 3 = atomic count + the stable scatter above).  Same three passes and the same
 // tile-major order of every partition's stream (an order that follows the probe rows keeps the gather pass's reads
 // nearly sequential -- claiming runs with a global atomic instead of scanning tile counts was measured: the
 // scatter got faster but the gather's DRAM reads went from 1.3 to 3.5 GB), but
@@ -531,7 +455,7 @@ __global__ void __launch_bounds__(HJ_THREADS) pj2_scatter_kernel(PartJoin pj) {
 }
 
 // pass 4: probe in partitioned order (partition after partition, so one slot range of the table is hot in L2)
-template <bool FAT, int K>
+template <int K>
 __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinTable jt) {
     constexpr int TILE = K * HJ_THREADS;
     const int tid = threadIdx.x;
@@ -541,7 +465,6 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
         const int64_t e0 = (int64_t)tile * TILE + tid;
         unsigned long long key[K], brow[K];
         uint64_t slot[K];
-        ulonglong2 pay[K];
         uint32_t inrange = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
@@ -549,21 +472,11 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
             key[j] = e < pj.n ? ld_ef(pj.pkeys + e, pol) : 0ull;
             if (e < pj.n) inrange |= 1u << j;
         }
-        probe_first<K, FAT>(jt, key, inrange, brow, slot, pay);
+        probe_first<K>(jt, key, inrange, brow, slot);
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            const bool live = (inrange >> j) & 1u;
-            if (FAT) {
-                const unsigned m = __ballot_sync(0xffffffffu, live && brow[j] != EMPTY_ROW);
-                if (live) {
-                    st_ef(pj.res0 + e, pay[j].x, pol);
-                    if (pj.res1) st_ef(pj.res1 + e, pay[j].y, pol);
-                    if ((tid & 31) == 0) pj.mbits[e >> 5] = m;
-                }
-            } else if (live) {
-                st_ef(pj.res0 + e, brow[j], pol);
-            }
+            if ((inrange >> j) & 1u) st_ef(pj.res0 + e, brow[j], pol);
         }
     }
 }
@@ -573,10 +486,10 @@ __global__ void __launch_bounds__(HJ_THREADS) pj_probe_kernel(PartJoin pj, JoinT
 // the joined rows are then compacted by the filter/project kernel (predicate = the match bitmap).
 struct GatherParams {
     PartJoin pj;
-    int32_t fat, n_gather;
-    int32_t row_is_payload, pad; // thin: the probe results ARE the one gathered column's values (JoinTable::rowpay)
-    const unsigned long long *src[HJ_MAX_COLS]; // thin: build column to gather by build row
-    unsigned long long *dst[HJ_MAX_COLS];       // thin: gathered column; fat: dst[0], dst[1] = payload words
+    int32_t n_gather;
+    int32_t row_is_payload;      // the probe results ARE the one gathered column's values (JoinTable::rowpay)
+    const unsigned long long *src[HJ_MAX_COLS]; // build column to gather by build row
+    unsigned long long *dst[HJ_MAX_COLS];       // gathered column
     unsigned int *match;                        // match bitmap in probe-row order
 };
 // Tile-aligned variant for the second-generation split: inside a tile's run the positions are in arrival order, so the
@@ -620,19 +533,13 @@ __global__ void __launch_bounds__(256) pj_gather_kernel(const __grid_constant__ 
         bool m = false;
         if (live) {
             const unsigned int p = gp.pj.ppos32[i];
-            if (gp.fat) {
-                m = (__ldg(gp.pj.mbits + (p >> 5)) >> (p & 31)) & 1u;
-                st_ef(gp.dst[0] + i, ld_ef(gp.pj.res0 + p, pol), pol);
-                if (gp.pj.res1) st_ef(gp.dst[1] + i, ld_ef(gp.pj.res1 + p, pol), pol);
-            } else {
-                const unsigned long long brow = ld_ef(gp.pj.res0 + p, pol);
-                m = brow != EMPTY_ROW;
-                if (gp.row_is_payload) st_ef(gp.dst[0] + i, m ? brow : 0ull, pol);
-                else for (int c = 0; c < gp.n_gather; c++) {
-                    unsigned long long v = 0;
-                    if (m) v = ld_cg_u64(gp.src[c] + brow);
-                    st_ef(gp.dst[c] + i, v, pol);
-                }
+            const unsigned long long brow = ld_ef(gp.pj.res0 + p, pol);
+            m = brow != EMPTY_ROW;
+            if (gp.row_is_payload) st_ef(gp.dst[0] + i, m ? brow : 0ull, pol);
+            else for (int c = 0; c < gp.n_gather; c++) {
+                unsigned long long v = 0;
+                if (m) v = ld_cg_u64(gp.src[c] + brow);
+                st_ef(gp.dst[c] + i, v, pol);
             }
         }
         const unsigned b = __ballot_sync(0xffffffffu, m);
@@ -681,7 +588,6 @@ __device__ __forceinline__ void emit_row(const ProbeParams &pp, int64_t brow, in
     }
 }
 
-template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
@@ -705,9 +611,8 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
             if (e < pp.n_probe) inrange |= 1u << j;
         }
-        ulonglong2 pay[K];
         if (!pp.jt.has_dups) {
-            probe_first<K, FAT>(pp.jt, key, inrange, first, slot, pay);
+            probe_first<K>(pp.jt, key, inrange, first, slot);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
         } else {
@@ -716,14 +621,6 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
                 slot[j] = 0;
                 first[j] = EMPTY_ROW;
                 cnt[j] = ((inrange >> j) & 1u) ? probe_count(pp.jt, key[j], &first[j], &slot[j]) : 0u;
-            }
-        }
-        // fat slots, duplicate keys: the payload of the first match sits next to its key
-        if (FAT && pp.jt.has_dups) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                pay[j] = make_ulonglong2(0, 0);
-                if (cnt[j]) pay[j] = ld_payload(pp.jt, slot[j]);
             }
         }
         // ranks: warp inclusive scan of counts per j, then scan of the K*WARPS warp totals
@@ -774,11 +671,6 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
 #pragma unroll
                 for (int j = 0; j < K; j++)
                     if ((emit >> j) & 1u) out[pos[j]] = key[j];
-            } else if (FAT) {
-                const bool second = pp.jt.n_pay > 1 && c == pp.jt.pay_col[1];
-#pragma unroll
-                for (int j = 0; j < K; j++)
-                    if ((emit >> j) & 1u) out[pos[j]] = second ? pay[j].y : pay[j].x;
             } else {
 #pragma unroll
                 for (int j = 0; j < K; j++)
@@ -829,10 +721,9 @@ struct JoinAggParams {
     int64_t n_probe;
     ColSrc group;          // group key column
     int32_t group_left;    // 1: taken from the build row, 0: from the probe row
-    int32_t group_pay;     // fat table: 0/1 = group key is payload word 0/1; 2 = the slot's row word; -1 = not in the slot
+    int32_t group_in_slot; // the slot's row word IS the group key (JoinTable::rowpay)
     ColSrc val[AG_MAX];
     int32_t val_left[AG_MAX];
-    int32_t val_pay[AG_MAX]; // fat table: payload word holding this build-side argument, or -1
 };
 
 __device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
@@ -842,14 +733,9 @@ __device__ __forceinline__ bool col_valid(const ColSrc &c, int64_t r) {
 struct JoinRowSource {
     const JoinAggParams &jp;
     int64_t brow, prow;
-    ulonglong2 pay;
     __device__ __forceinline__ bool operator()(int id, int *dtype, uint64_t *bits) const {
         const ColSrc &c = jp.val[id];
         *dtype = c.dtype;
-        if (jp.val_left[id] && jp.val_pay[id] >= 0) { // build-side argument stored in the fat slot
-            *bits = jp.val_pay[id] ? pay.y : pay.x;
-            return true;
-        }
         const int64_t r = jp.val_left[id] ? brow : prow;
         if (!col_valid(c, r)) return false;
         *bits = (c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) ? 0ull : ld_cg_u64((const unsigned long long *)c.values + r);
@@ -857,13 +743,9 @@ struct JoinRowSource {
     }
 };
 
-__device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggParams &ap, int64_t brow, int64_t prow,
-                                             uint64_t slot) {
-    ulonglong2 pay = make_ulonglong2(0, 0);
-    if (jp.jt.shift == 2) pay = ld_payload(jp.jt, slot);
+__device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggParams &ap, int64_t brow, int64_t prow) {
     uint64_t gkey;
-    if (jp.group_pay == 2) gkey = (uint64_t)brow; // the slot's row word is the group key (JoinTable::rowpay)
-    else if (jp.group_left && jp.group_pay >= 0) gkey = jp.group_pay ? pay.y : pay.x;
+    if (jp.group_in_slot) gkey = (uint64_t)brow;
     else {
         const int64_t grow = jp.group_left ? brow : prow;
         if (!col_valid(jp.group, grow)) return; // NULL group keys are dropped (aggregate/mod.rs:63-71)
@@ -871,10 +753,9 @@ __device__ __forceinline__ void join_agg_one(const JoinAggParams &jp, const AggP
     }
     Sector0 s0;
     unsigned long long *r = find_slot(ap, gkey, &s0);
-    if (r) update_states(ap, r, s0, JoinRowSource{jp, brow, prow, pay});
+    if (r) update_states(ap, r, s0, JoinRowSource{jp, brow, prow});
 }
 
-template <bool FAT>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_constant__ AggParams ap) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
@@ -890,8 +771,7 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
             key[j] = e < jp.n_probe ? ld_stream_u64(jp.probe_keys + e) : 0ull;
             if (e < jp.n_probe) inrange |= 1u << j;
         }
-        ulonglong2 pay[K];
-        probe_first<K, FAT>(jp.jt, key, inrange, brow, slot, pay);
+        probe_first<K>(jp.jt, key, inrange, brow, slot);
         // group keys of the (first) matches: K independent loads
         uint64_t gkey[K];
         uint32_t have = 0;
@@ -899,10 +779,8 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
         for (int j = 0; j < K; j++) {
             gkey[j] = 0;
             if (brow[j] == EMPTY_ROW) continue;
-            if (jp.group_pay == 2) {
+            if (jp.group_in_slot) {
                 gkey[j] = brow[j];
-            } else if (jp.group_left && jp.group_pay >= 0) {
-                gkey[j] = jp.group_pay ? pay[j].y : pay[j].x;
             } else {
                 const int64_t grow = jp.group_left ? (int64_t)brow[j] : e0 + (int64_t)j * HJ_THREADS;
                 if (!col_valid(jp.group, grow)) continue; // NULL group keys are dropped
@@ -915,7 +793,7 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
         find_slots<K>(ap, gkey, have, rec, s0);
 #pragma unroll
         for (int j = 0; j < K; j++)
-            if (rec[j]) update_states(ap, rec[j], s0[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS, pay[j]});
+            if (rec[j]) update_states(ap, rec[j], s0[j], JoinRowSource{jp, (int64_t)brow[j], e0 + (int64_t)j * HJ_THREADS});
         if (jp.jt.has_dups) {
             // duplicate build keys: walk on from the first match for the remaining ones
 #pragma unroll
@@ -925,11 +803,119 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
                 while (true) {
                     const Slot sl = ld_slot(jp.jt, s);
                     if (sl.row == EMPTY_ROW) break;
-                    if (sl.key == key[j]) join_agg_one(jp, ap, (int64_t)sl.row, e0 + (int64_t)j * HJ_THREADS, s);
+                    if (sl.key == key[j]) join_agg_one(jp, ap, (int64_t)sl.row, e0 + (int64_t)j * HJ_THREADS);
                     s = s + 1 == jp.jt.cap ? 0 : s + 1;
                 }
             }
         }
+    }
+}
+
+// ---- Fused join -> group-by over paged streams ------------------------------------------------------------------
+// The direct kernel above makes one DRAM-random slot access per probe row into a table far larger than the L2
+// (11.6 GB of DRAM traffic per 1e8 rows where the inputs are 1.76 GB) plus the L2-bound group-table updates.  When the
+// build keys are unique and the group key rides in the slots (JoinTable::rowpay) the work is reorganised into three
+// streaming passes over 16-byte rows (paged_split.cuh):
+//   1. ps_split_kernel<PartBySlotRange>: (fk, value) rows split by the top bits of the key's hash = ranges of table
+//      slots of <= 48 MiB;
+//   2. ja_probe_scatter_kernel: pages are swept partition after partition (every CTA takes every gridDim-th page of
+//      the concatenated page list, so the whole grid works inside one slot range at a time and the range stays in L2);
+//      a probe row becomes (group key, value) and is split again, by group-key hash, into the group-by's partitions;
+//   3. gp2_aggregate_kernel (hash_aggregate.cu): shared-memory aggregation of every partition.
+// Unmatched probe rows simply vanish in pass 2 (inner join).
+struct PartBySlotRange { // partition = top of the hash = contiguous range of table slots (join_slot_of is monotone in the hash)
+    uint64_t P;
+    __device__ __forceinline__ int operator()(unsigned long long key) const { return (int)__umul64hi(nqe_mix64(key), P); }
+};
+
+constexpr int JP_THREADS = 1024, JP_K = 4;
+static_assert(JP_THREADS * JP_K == PS_PAGE_ROWS, "one page per step");
+struct JpSmem {
+    ulonglong2 page[PS_PAGE_ROWS];
+    PsScatterSmem<JP_THREADS, JP_K> sc;
+    PsPageBuf buf;
+    unsigned int pstart[40]; // first page of every input partition in the concatenated page list (P1 <= 32)
+};
+
+__device__ __forceinline__ void jp_locate(const unsigned int *pstart, int P, unsigned w, int *p, unsigned *q) {
+    int pp = *p;
+    while (pp + 1 < P && w >= pstart[pp + 1]) pp++;
+    *p = pp;
+    *q = w - pstart[pp];
+}
+
+__global__ void __launch_bounds__(JP_THREADS, 1)
+ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_constant__ PagedStreams out, const JoinTable jt,
+                        uint32_t P2) {
+    extern __shared__ __align__(128) unsigned char jp_smem_raw[];
+    JpSmem &sm = *reinterpret_cast<JpSmem *>(jp_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        unsigned acc = 0;
+        for (int p = 0; p < in.P; p++) {
+            sm.pstart[p] = acc;
+            acc += (unsigned)((in.cursor[p] + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
+        }
+        sm.pstart[in.P] = acc;
+    }
+    ps_pagebuf_init(sm.buf, JP_THREADS / 32);
+    ps_scatter_init(sm.sc); // __syncthreads inside
+    const unsigned total = sm.pstart[in.P];
+    int p = 0;          // every thread tracks the partition of its current page
+    int pn = 0;         // thread 0: partition of the next page
+    unsigned long long pol = 0;
+    unsigned next_phys = 0;
+    if (tid == 0) {
+        pol = nqe_policy_evict_first();
+        unsigned q;
+        if (blockIdx.x < total) {
+            jp_locate(sm.pstart, in.P, blockIdx.x, &pn, &q);
+            ps_issue_page(in, sm.buf, sm.page, in.pt[(size_t)pn * in.pt_stride + q] - 1u, ps_page_rows(in, pn, q), pol);
+        }
+        if (blockIdx.x + gridDim.x < total) {
+            jp_locate(sm.pstart, in.P, blockIdx.x + gridDim.x, &pn, &q);
+            next_phys = in.pt[(size_t)pn * in.pt_stride + q] - 1u;
+        }
+    }
+    uint32_t it = 0;
+    for (unsigned w = blockIdx.x; w < total; w += gridDim.x, it++) {
+        unsigned q;
+        jp_locate(sm.pstart, in.P, w, &p, &q);
+        const unsigned fill = ps_page_rows(in, p, q);
+        nqe_mbar_wait(&sm.buf.full, it & 1u);
+        unsigned long long key[JP_K], val[JP_K];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < JP_K; j++) {
+            const unsigned idx = j * JP_THREADS + tid;
+            ulonglong2 r = make_ulonglong2(0ull, 0ull);
+            if (idx < fill) { r = sm.page[idx]; live |= 1u << j; }
+            key[j] = r.x;
+            val[j] = r.y;
+        }
+        __syncwarp();
+        if (lane == 0) nqe_mbar_arrive(&sm.buf.empty);
+        if (tid == 0 && w + gridDim.x < total) {
+            nqe_mbar_wait(&sm.buf.empty, it & 1u);
+            unsigned qn;
+            jp_locate(sm.pstart, in.P, w + gridDim.x, &pn, &qn);
+            ps_issue_page(in, sm.buf, sm.page, next_phys, ps_page_rows(in, pn, qn), pol);
+            if (w + 2 * gridDim.x < total) {
+                int p2 = pn;
+                jp_locate(sm.pstart, in.P, w + 2 * gridDim.x, &p2, &qn);
+                next_phys = in.pt[(size_t)p2 * in.pt_stride + qn] - 1u;
+            }
+        }
+        unsigned long long grp[JP_K];
+        uint64_t slot[JP_K];
+        probe_first<JP_K>(jt, key, live, grp, slot); // unique build keys: the first match is the only one
+        int pid[JP_K];
+#pragma unroll
+        for (int j = 0; j < JP_K; j++) {
+            if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
+            pid[j] = (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
+        }
+        ps_scatter_tile<JP_THREADS, JP_K>(out, sm.sc, grp, val, pid, live);
     }
 }
 
@@ -961,27 +947,9 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
             jt->rowpay_col = rowpay_col;
         }
     }
-    // fat slots when every non-key build column is a NULL-free 8-byte column and there are at most two
-    static int allow_fat = -1;
-    if (allow_fat < 0) {
-        const char *e = getenv("NQE_JOIN_FAT");
-        allow_fat = e ? atoi(e) : 0; // measured (profiles/join_groupby_r01.md): thin 16-byte slots + gather beat fat slots, whose table is twice as large
-    }
-    bool fat = allow_fat && left->cols.size() <= 3 && !jt->rowpay;
-    int n_pay = 0;
-    for (size_t c = 0; c < left->cols.size() && fat; c++) {
-        if ((int)c == lk) continue;
-        const DevColumn &col = left->cols[c];
-        if (col.validity || col.dtype == NQE_BOOL || col.dtype == NQE_UTF8) { fat = false; break; }
-        jt->pay_col[n_pay] = (int)c;
-        jt->pay_src[n_pay] = (const unsigned long long *)col.values;
-        n_pay++;
-    }
-    jt->n_pay = fat ? n_pay : 0;
-    jt->shift = fat ? 2 : 1;
     const uint64_t cap = (uint64_t)((double)nl / 0.5) + 16; // load factor 0.5
     void *slots = nullptr;
-    NQE_TRY(nqe_dev_alloc(ctx, &slots, (cap << jt->shift) * 8));
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, cap * 16));
     jt->words = (unsigned long long *)slots;
     jt->cap = cap;
     uint32_t *status = (uint32_t *)(ctx->d_scratch + 1);
@@ -1102,20 +1070,18 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             }
             int grid = ctx->sm_count * split_ctas;
             if (grid > pj.num_tiles) grid = pj.num_tiles;
-            static int split_gen = 0; // knob NQE_JOIN_SPLIT: 1 = stable ballot-histogram split, 2 = atomic-rank staged split
+            static int split_gen = 0; // knob NQE_JOIN_SPLIT: 2 = atomic-rank staged split, 3 = stable scatter
             if (!split_gen) {
                 const char *e = getenv("NQE_JOIN_SPLIT");
                 split_gen = e ? atoi(e) : 0;
-                if (split_gen < 0 || split_gen > 3) split_gen = 0;
-                if (!split_gen) split_gen = -1; // no knob: chosen per call below
+                if (split_gen != 2 && split_gen != 3) split_gen = -1; // no knob: chosen per call below
             }
             // default: the staged split when the tile-aligned gather follows (payload-in-row tables), else the stable one
             const int split_mode = split_gen > 0 ? split_gen : rowpay_col >= 0 ? 2 : 3;
-            // 1: ballot histograms + stable scatter; 2: atomic histograms + staged (arrival-order) scatter;
-            // 3: atomic histograms for the count, stable scatter (default: the stable order keeps the gather's reads sequential)
+            // 2: atomic histograms + staged (arrival-order) scatter; 3: atomic histograms for the count, stable scatter
+            // (the stable order keeps the streaming gather's reads sequential)
             cudaMemsetAsync(totals, 0, P * 8, ss);
-            if (split_mode == 1) pj_count_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj, (unsigned long long *)totals);
-            else pj2_count_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj, (unsigned long long *)totals);
+            pj2_count_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj, (unsigned long long *)totals);
             pj_scan_kernel<<<(unsigned)P, 1024, 0, ss>>>(pj, (const unsigned long long *)totals);
             if (split_mode == 2) pj2_scatter_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj);
             else pj_scatter_kernel<<<grid, HJ_THREADS, 0, ss>>>(pj);
@@ -1139,23 +1105,24 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     pp.tile_state = (unsigned long long *)lb;
     pp.out_count = (unsigned long long *)ctx->d_scratch;
     pp.ticket = (unsigned int *)(ctx->d_scratch + 2);
-    const bool fat = pp.jt.shift == 2 && pp.key_from_probe;
 
+    // The build key's output VALUES are the probe keys (they matched), but its validity is the build column's own:
+    // key validity is ignored by the join (hash_join.rs:67,86) and `take(left_key, outer_pos)` returns the build
+    // side's slots.  The view's build-key column aliases the probe key values WITHOUT the probe key's bitmap; when the
+    // probe key is NULL-free both key outputs read the one staged probe-key column instead.
+    const int key_src = right->cols[right_key].validity ? left_key : nl + right_key;
     // ---- partitioned probe: unique build keys and a table that does not fit in the L2
     bool part = false;
     if (rc == NQE_OK && split_started) {
         bool emit_fp = true; // emit through the filter/project kernel: NULL-free 8-byte build columns only
         for (int c = 0; c < nl; c++)
             if (left->cols[c].validity || left->cols[c].dtype == NQE_BOOL) emit_fp = false;
-        const bool thin_ok = pp.jt.shift == 1 && emit_fp, fat_ok = fat && emit_fp;
-        if (!pp.jt.has_dups && (thin_ok || fat_ok)) {
+        if (!pp.jt.has_dups && emit_fp) {
             PartJoin &pj = pp.pj;
             auto alloc = [&](void **p, size_t bytes) {
                 if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
                 if (rc == NQE_OK) pj_bufs.push_back(*p);
             };
-            if (fat && pp.jt.n_pay > 1) alloc((void **)&pj.res1, (size_t)pp.n_probe * 8);
-            if (fat) alloc((void **)&pj.mbits, ((size_t)pp.n_probe / 32 + 2) * 4);
             if (rc == NQE_OK) {
                 int grid = ctx->sm_count * 8;
                 if (grid > pj.num_tiles) grid = pj.num_tiles;
@@ -1164,9 +1131,8 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
                     const char *e = getenv("NQE_JOIN_PROBE_K");
                     probe_k = e && atoi(e) == 8 ? 8 : 4;
                 }
-                if (fat) pj_probe_kernel<true, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
-                else if (probe_k == 8) pj_probe_kernel<false, 8><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
-                else pj_probe_kernel<false, 4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                if (probe_k == 8) pj_probe_kernel<8><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
+                else pj_probe_kernel<4><<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, pp.jt);
                 ctx->launches++;
                 if (cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "partitioned probe launch failed");
                 part = true;
@@ -1215,7 +1181,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             std::vector<nqe_expr_node> nodes(nl + nr);
             std::vector<nqe_expr> projs(nl + nr);
             for (int c = 0; c < nl + nr; c++) { // the build key's values are the probe keys: one staged column serves both outputs
-                nodes[c] = nqe_expr_node{NQE_NODE_COLUMN, 0, c == left_key ? nl + right_key : c, 0, 0, 0, {0}};
+                nodes[c] = nqe_expr_node{NQE_NODE_COLUMN, 0, c == left_key ? key_src : c, 0, 0, 0, {0}};
                 projs[c] = nqe_expr{&nodes[c], 1, 0};
             }
             nqe_expr_node pn[3] = {{NQE_NODE_COLUMN, 0, match_col, 0, 0, 0, {0}},
@@ -1240,7 +1206,6 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
         GatherParams gp;
         memset(&gp, 0, sizeof gp);
         gp.pj = pp.pj;
-        gp.fat = fat ? 1 : 0;
         gp.row_is_payload = pp.jt.rowpay ? 1 : 0;
         const int64_t n = pp.n_probe;
         std::vector<void *> gathered(nl, nullptr); // per build column: its values in probe-row order
@@ -1249,12 +1214,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             if (rc == NQE_OK) pj_bufs.push_back(*p);
         };
         alloc((void **)&gp.match, nqe_bitmap_bytes(n));
-        if (fat) {
-            for (int q = 0; q < pp.jt.n_pay; q++) {
-                alloc(&gathered[pp.jt.pay_col[q]], (size_t)n * 8);
-                gp.dst[q] = (unsigned long long *)gathered[pp.jt.pay_col[q]];
-            }
-        } else {
+        {
             for (int c = 0; c < nl; c++) {
                 if (c == left_key) continue;
                 alloc(&gathered[c], (size_t)n * 8);
@@ -1269,7 +1229,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
                 const char *e = getenv("NQE_JOIN_GATHER");
                 gather_gen = e && atoi(e) == 1 ? 1 : 2;
             }
-            if (gather_gen == 2 && gp.row_is_payload && !gp.fat) pj_gather_tile_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
+            if (gather_gen == 2 && gp.row_is_payload) pj_gather_tile_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
             else pj_gather_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gp);
             ctx->launches++;
             // joined table before compaction: [build columns (key = probe key) | probe columns | match]
@@ -1296,7 +1256,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             std::vector<nqe_expr_node> nodes(nl + nr + 1);
             std::vector<nqe_expr> projs(nl + nr);
             // the build key's output values are the probe keys: both outputs read the one staged probe-key column
-            for (int c = 0; c <= nl + nr; c++) nodes[c] = nqe_expr_node{NQE_NODE_COLUMN, 0, c == left_key ? nl + right_key : c, 0, 0, 0, {0}};
+            for (int c = 0; c <= nl + nr; c++) nodes[c] = nqe_expr_node{NQE_NODE_COLUMN, 0, c == left_key ? key_src : c, 0, 0, 0, {0}};
             for (int c = 0; c < nl + nr; c++) projs[c] = nqe_expr{&nodes[c], 1, 0};
             const nqe_expr pred{&nodes[nl + nr], 1, 0};
             nqe_table *joined = nullptr;
@@ -1341,7 +1301,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
             if (pp.num_tiles > 0) {
-                auto kern = fat ? join_probe_kernel<true> : join_probe_kernel<false>;
+                auto kern = join_probe_kernel;
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);
@@ -1459,96 +1419,101 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         allow_rowpay = e ? atoi(e) : 1;
     }
     int32_t rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
-    // which build-side columns can be served from the fat slot's payload words
-    jp.group_pay = -1;
-    for (int a = 0; a < n_aggs; a++) jp.val_pay[a] = -1;
-    if (jp.jt.rowpay) jp.group_pay = 2;
-    if (jp.jt.shift == 2) {
-        for (int q = 0; q < jp.jt.n_pay; q++) {
-            if (jp.group_left && group_column == jp.jt.pay_col[q]) jp.group_pay = q;
-            for (int a = 0; a < n_aggs; a++)
-                if (jp.val_left[a] && aggs[a].column == jp.jt.pay_col[q]) jp.val_pay[a] = q;
-        }
-    }
+    jp.group_in_slot = jp.jt.rowpay ? 1 : 0;
     jp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
     jp.n_probe = right->nrows;
-    // ---- partitioned probe (see "Partitioned probe" above), EXPERIMENTAL for the fused path (NQE_JOINAGG_PART=1):
-    // the probe keys and the probe-side columns the aggregates read are split stably by slot range and the fused
-    // kernel sweeps them partition after partition.  Measured (profiles/README_r01.md): the slot reads become L2
-    // hits (DRAM reads 21 GB -> 4 GB) but the fused kernel stays at ~4.9 ms -- at 122 registers (2 CTAs/SM) it is
-    // bound by the latency of its dependent L2 accesses, not by DRAM -- so with the split passes on top the
-    // direct probe is still faster end to end and remains the default.
-    std::vector<void *> pj_bufs;
-    if (rc == NQE_OK) {
-        static int allow_part = -1;
-        static size_t l2_budget = 0;
-        if (allow_part < 0) {
-            const char *e = getenv("NQE_JOINAGG_PART");
-            allow_part = e ? atoi(e) : 0;
-            e = getenv("NQE_JOIN_PART_MB");
-            l2_budget = (size_t)(e ? atoi(e) : 24) << 20;
-        }
-        const size_t table_bytes = (size_t)(jp.jt.cap << jp.jt.shift) * 8;
-        bool ok = allow_part && !jp.jt.has_dups && jp.n_probe >= (1 << 22) && jp.n_probe < ((int64_t)1 << 32) &&
-                  table_bytes > 2 * l2_budget;
-        // probe-side columns the kernel reads: NULL-free 8-byte columns, at most 8 distinct
-        std::vector<const void *> srcs;
-        auto want = [&](const ColSrc &c) {
-            if (c.validity || c.dtype == NQE_BOOL || c.dtype == NQE_UTF8) { ok = false; return; }
-            for (const void *p : srcs)
-                if (p == c.values) return;
-            srcs.push_back(c.values);
-        };
-        for (int a = 0; a < n_aggs && ok; a++)
-            if (!jp.val_left[a]) want(jp.val[a]);
-        if (ok && !jp.group_left) want(jp.group);
-        if (srcs.size() > 8) ok = false;
-        if (ok) {
-            PartJoin pj;
-            memset(&pj, 0, sizeof pj);
-            int log2p = 1;
-            while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
-            pj.keys = jp.probe_keys;
-            pj.n = jp.n_probe;
-            pj.log2p = log2p;
-            pj.num_tiles = (int32_t)((jp.n_probe + 2048 - 1) / 2048);
-            const size_t P = (size_t)1 << log2p, nt = (size_t)pj.num_tiles;
-            auto alloc = [&](void **p, size_t bytes) {
-                if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, p, bytes);
-                if (rc == NQE_OK) pj_bufs.push_back(*p);
-            };
-            void *totals = nullptr;
-            alloc((void **)&pj.tile_cnt, nt * P * 4);
-            alloc((void **)&pj.tile_off, nt * P * 4);
-            alloc((void **)&pj.part_base, (P + 1) * 8);
-            alloc(&totals, P * 8);
-            alloc((void **)&pj.pkeys, (size_t)jp.n_probe * 8);
-            pj.n_carry = (int)srcs.size();
-            for (int c = 0; c < pj.n_carry; c++) {
-                pj.carry_src[c] = (const unsigned long long *)srcs[c];
-                alloc((void **)&pj.carry_dst[c], (size_t)jp.n_probe * 8);
-            }
-            if (rc == NQE_OK) {
-                cudaMemsetAsync(totals, 0, P * 8, ctx->stream);
-                int grid = ctx->sm_count * 8;
-                if (grid > pj.num_tiles) grid = pj.num_tiles;
-                pj_count_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj, (unsigned long long *)totals);
-                pj_scan_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(pj, (const unsigned long long *)totals);
-                pj_scatter_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(pj);
-                ctx->launches += 3;
-                // the fused kernel now reads the partitioned copies
-                auto moved = [&](ColSrc &c) {
-                    for (int q = 0; q < pj.n_carry; q++)
-                        if (c.values == (const void *)pj.carry_src[q]) { c.values = pj.carry_dst[q]; return; }
-                };
-                jp.probe_keys = pj.pkeys;
-                for (int a = 0; a < n_aggs; a++)
-                    if (!jp.val_left[a]) moved(jp.val[a]);
-                if (!jp.group_left) moved(jp.group);
-            }
-        }
-    }
     nqe_table *t;
+    nqe_table_new(ctx, 0, &t);
+
+    // ---- paged path (see "Fused join -> group-by over paged streams" above): unique build keys, the group key rides
+    // in the slots, every aggregate reads ONE NULL-free 8-byte probe-side column
+    static int allow_paged = -1;
+    static size_t l2_budget = 0;
+    if (allow_paged < 0) {
+        const char *e = getenv("NQE_JOINAGG_PAGED");
+        allow_paged = e ? atoi(e) : 1;
+        e = getenv("NQE_JOIN_PART_MB");
+        l2_budget = (size_t)(e ? atoi(e) : 48) << 20;
+    }
+    bool paged = rc == NQE_OK && allow_paged && jp.jt.rowpay && !jp.jt.has_dups && jp.n_probe >= (1 << 22) && ap.n_states > 0;
+    int need = 0;
+    for (int q = 0; q < ap.n_states && paged; q++) {
+        if (ap.st_src[q] != ap.st_src[0]) paged = false;
+        need |= 1 << ap.st_kind[q];
+    }
+    const ColSrc &vc = jp.val[ap.n_states > 0 ? ap.st_src[0] : 0];
+    if (paged && (vc.validity || (vc.dtype != NQE_INT64 && vc.dtype != NQE_UINT64 && vc.dtype != NQE_FLOAT64))) paged = false;
+    int P2 = 0, m2 = 1;
+    double est_groups = 0;
+    if (paged) {
+        rc = nqe_estimate_distinct_u64(ctx, jp.jt.rowpay, left->nrows, &est_groups);
+        if (rc == NQE_OK && (est_groups < 2048.0 || !nqe_gp2_plan(ctx, est_groups, &P2, &m2))) paged = false;
+    }
+    if (rc == NQE_OK && paged) {
+        const size_t table_bytes = (size_t)jp.jt.cap * 16;
+        int P1 = (int)((table_bytes + l2_budget - 1) / l2_budget);
+        if (P1 < 1) P1 = 1;
+        if (P1 > 32) P1 = 32;
+        PagedStreams s1, s2;
+        memset(&s1, 0, sizeof s1);
+        memset(&s2, 0, sizeof s2);
+        rc = nqe_ps_create(ctx, jp.n_probe, P1, &s1);
+        if (rc == NQE_OK) rc = nqe_ps_create(ctx, jp.n_probe, P2, &s2);
+        if (rc == NQE_OK) {
+            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            const size_t smem1 = nqe_ps_split_smem();
+            const PsSplitArgs sa{jp.probe_keys, (const unsigned long long *)vc.values, jp.n_probe};
+            const int64_t tiles = (jp.n_probe + PS_SPLIT_THREADS * PS_SPLIT_K - 1) / (PS_SPLIT_THREADS * PS_SPLIT_K);
+            int grid = ctx->sm_count * 2;
+            if (grid > tiles) grid = (int)tiles;
+            DevProgramSet none;
+            memset(&none, 0, sizeof none);
+            cudaError_t e1 = cudaFuncSetAttribute(ps_split_kernel<false, PartBySlotRange>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            cudaError_t e2 = cudaFuncSetAttribute(ja_probe_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpSmem));
+            if (e1 == cudaSuccess && e2 == cudaSuccess) {
+                ps_split_kernel<false, PartBySlotRange><<<grid, PS_SPLIT_THREADS, smem1, ctx->stream>>>(s1, sa, PartBySlotRange{(uint64_t)P1}, none, ap.status);
+                ja_probe_scatter_kernel<<<ctx->sm_count, JP_THREADS, sizeof(JpSmem), ctx->stream>>>(s1, s2, jp.jt, (uint32_t)P2);
+                ctx->launches += 2;
+            }
+            if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                rc = nqe_fail(ctx, NQE_ERR_CUDA, "join-aggregate split/probe launch failed");
+        }
+        uint64_t capacity = nqe_agg_capacity(est_groups);
+        for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
+            rc = nqe_agg_table_create(ctx, &ap, capacity);
+            if (rc != NQE_OK) break;
+            rc = nqe_gp2_aggregate(ctx, s2, ap, m2, vc.dtype, need);
+            if (rc != NQE_OK) break;
+            cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+                rc = nqe_fail(ctx, NQE_ERR_CUDA, "join-aggregate kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            const uint32_t st = (uint32_t)ctx->h_scratch[1];
+            if (st & DEV_ERR_CAPACITY) { rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: paged stream pool exhausted"); break; }
+            if (!(st & DEV_ERR_TABLE_FULL)) break;
+            nqe_dev_free(ctx, ap.table);
+            ap.table = nullptr;
+            capacity *= 8;
+            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
+        }
+        if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, false, left->nrows + 1, t);
+        timer.stop();
+        nqe_ps_destroy(ctx, &s1);
+        nqe_ps_destroy(ctx, &s2);
+        nqe_dev_free(ctx, ap.table);
+        nqe_dev_free(ctx, jp.jt.words);
+        if (rc != NQE_OK) {
+            nqe_table_free(t);
+            return rc;
+        }
+        *out = t;
+        return NQE_OK;
+    }
+
+    // ---- direct path: one pass over the probe side, group table in L2
+    // groups come from one column of one side    nqe_table *t;
     nqe_table_new(ctx, 0, &t);
     // groups come from one column of one side: at most that side's row count
     const int64_t side_rows = jp.group_left ? left->nrows : right->nrows;
@@ -1561,8 +1526,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             const int64_t tiles = (jp.n_probe + HJ_K * HJ_THREADS - 1) / (HJ_K * HJ_THREADS);
             int grid = ctx->sm_count * 8;
             if (grid > tiles) grid = (int)tiles;
-            if (jp.jt.shift == 2) join_aggregate_kernel<true><<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
-            else join_aggregate_kernel<false><<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
+            join_aggregate_kernel<<<grid, HJ_THREADS, 0, ctx->stream>>>(jp, ap);
             ctx->launches++;
         }
         cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1580,7 +1544,6 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     timer.stop();
     nqe_dev_free(ctx, ap.table);
     nqe_dev_free(ctx, jp.jt.words);
-    for (void *p : pj_bufs) nqe_dev_free(ctx, p);
     if (rc != NQE_OK) {
         nqe_table_free(t);
         return rc;

@@ -1,7 +1,8 @@
 """The kernels behind the tuning knobs stay correct: the knobs are read once per process, so each alternative runs a
 slice of the parity suite in a child process with the knob set.  Covers the interpreter kernels (what runs when NVRTC
-is unavailable), the join table with row numbers instead of payloads, the stable ballot split with the streaming
-gather, gathered columns inside the compaction kernel, and the partitioned fused join -> group-by."""
+is unavailable), the join table with row numbers instead of payloads, the stable split with the streaming gather,
+gathered columns inside the compaction kernel, the direct (single-pass) fused join -> group-by and group-by table
+paths behind the paged shared-memory ones, and the paged group-by on small inputs."""
 import os
 import subprocess
 import sys
@@ -15,10 +16,11 @@ CASES = [
     ({"NQE_JIT": "0"}, "filter_project_random or kleene or null_predicate or every_operator or error_behaviour or deep_expression"),
     ({"NQE_JIT_IMPL": "ca"}, "filter_project_many_tiles and not nullable"),
     ({"NQE_JOIN_ROWPAY": "0"}, "partitioned_probe_large or join_aggregate_group_key or join_aggregate_fused"),
-    ({"NQE_JOIN_SPLIT": "1", "NQE_JOIN_GATHER": "1", "NQE_JOIN_OVERLAP": "0"}, "partitioned_probe_large"),
-    ({"NQE_JOIN_FUSE": "1"}, "partitioned_probe_large"),
-    ({"NQE_JOINAGG_PART": "1"}, "join_aggregate_partitioned_large"),
-    ({"NQE_AGG_PART": "1", "NQE_AGG_PART_MIN_ROWS": "1000"}, "group_by"),
+    ({"NQE_JOIN_SPLIT": "3", "NQE_JOIN_GATHER": "1", "NQE_JOIN_OVERLAP": "0"}, "partitioned_probe_large"),
+    ({"NQE_JOIN_FUSE": "1"}, "partitioned_probe"),
+    ({"NQE_JOINAGG_PAGED": "0"}, "join_aggregate_paged_large"),
+    ({"NQE_AGG_PART": "0"}, "group_by_one_value_column"),
+    ({"NQE_AGG_PART_MIN_ROWS": "1000"}, "group_by"),
 ]
 
 

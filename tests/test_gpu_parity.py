@@ -452,6 +452,99 @@ def test_join_aggregate_partitioned_large(group_side):
     assert np.array_equal(out.column(3).to_numpy()[o], mn[present]) and np.array_equal(out.column(4).to_numpy()[o], mx[present])
 
 
+def _group_rows(cnt, sm, mn, mx):
+    """sortable (count, min, max, sum) rows -- the aggregate output carries no key column, so groups are matched through
+    their (count, min, max) triples"""
+    o = np.lexsort((mx, mn, cnt))
+    return cnt[o], mn[o], mx[o], sm[o]
+
+
+@pytest.mark.parametrize("nl,g", [(2_000_000, 60_000), (5_000_000, 150_000)])
+def test_join_aggregate_paged_large(nl, g):
+    """The paged fused join -> group-by (hash_join.cu: split by slot range, probe + re-split by group hash, shared-memory
+    aggregation): unique build keys, group key from the build side, every aggregate over one probe-side column; 30 % of
+    the probe rows find no match; the group keys include i64::MIN (the group tables' free-slot marker)."""
+    import ctypes as C
+    import pyarrow as pa
+    rng = np.random.default_rng(nl // 1000 + g)
+    nr = 6_000_011
+    keys = rng.permutation(np.arange(1, 3 * nl + 1, dtype=np.int64))[:nl] * 1_000_003
+    a = rng.integers(0, g, nl).astype(np.int64) * 7919 - 5
+    a[a == -5] = np.iinfo(np.int64).min
+    fk = np.where(rng.random(nr) < 0.7, keys[rng.integers(0, nl, nr)], rng.integers(1, 1 << 50, nr) * 2 + 7).astype(np.int64)
+    b = np.round(rng.normal(0, 1000, nr), 6)
+    b[rng.integers(0, nr, 20)] = np.nan
+    b[rng.integers(0, nr, 20)] = np.inf
+    L = pa.RecordBatch.from_arrays([pa.array(keys), pa.array(a)], names=["k", "a"])
+    R = pa.RecordBatch.from_arrays([pa.array(fk), pa.array(b)], names=["fk", "b"])
+    nq = G.nq
+    lt = nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None).execute_device()
+    rt = nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None).execute_device()
+    aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(o, 3) for o in (0, 1, 2, 3, 4)])  # joined schema: k, a, fk, b
+    h = C.c_void_p()
+    ctx = lt.ctx
+    ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, lt.h, rt.h, 0, 0, 1, aggs, 5, C.byref(h)))
+    out = nq.DeviceTable(ctx, h, ["count", "sum", "avg", "min", "max"]).to_arrow()
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    idx = np.minimum(np.searchsorted(sk, fk), nl - 1)
+    m = sk[idx] == fk
+    grp, bv = a[order[idx[m]]], b[m]
+    uk, inv = np.unique(grp, return_inverse=True)
+    ng = len(uk)
+    assert out.num_rows == ng
+    cnt = np.bincount(inv, minlength=ng)
+    so = np.argsort(inv, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    vs = bv[so]
+    has_nan = np.bincount(inv, weights=np.isnan(bv), minlength=ng) > 0
+    mx = np.where(has_nan, np.nan, np.maximum.reduceat(np.where(np.isnan(vs), -np.inf, vs), starts))
+    mn = np.minimum.reduceat(np.where(np.isnan(vs), np.inf, vs), starts)
+    with np.errstate(invalid="ignore"):
+        sm = np.add.reduceat(vs, starts)
+    key = lambda x: np.nan_to_num(x, nan=1e308, posinf=1e307, neginf=-1e307)
+    got = [out.column(i).to_numpy(zero_copy_only=False) for i in range(5)]
+    gc, gmn, gmx, gsm = _group_rows(got[0].astype(np.int64), got[1], key(got[3]), key(got[4]))
+    wc, wmn, wmx, wsm = _group_rows(cnt, sm, key(mn), key(mx))
+    assert np.array_equal(gc, wc) and np.array_equal(gmn, wmn) and np.array_equal(gmx, wmx)  # count, min, max: exact
+    fin = np.isfinite(wsm)
+    assert np.array_equal(np.isnan(gsm), np.isnan(wsm))
+    scale = np.add.reduceat(np.abs(np.where(np.isfinite(vs), vs, 0.0)), starts)[np.lexsort((key(mx), key(mn), cnt))]
+    assert np.all(np.abs(gsm[fin] - wsm[fin]) <= SUM_REL * np.maximum(scale[fin], 1.0))
+    lt.free()
+    rt.free()
+
+
+def test_hash_join_partitioned_probe_nullable_probe_key():
+    """Partition-size join whose PROBE key column has NULL slots: key validity is ignored (hash_join.rs:67,86), a NULL
+    probe key whose raw value matches joins, the build key output is the build side's (valid) value and only the probe
+    key output carries the NULL -- the same answer the direct probe path gives on small inputs."""
+    import pyarrow as pa
+    rng = np.random.default_rng(123)
+    nl, nr = 2_000_000, 4_500_003
+    keys = rng.permutation(np.arange(1, 3 * nl + 1, dtype=np.int64))[:nl] * 1_000_003
+    pay = rng.integers(-1 << 40, 1 << 40, nl).astype(np.int64)
+    fk = np.where(rng.random(nr) < 0.8, keys[rng.integers(0, nl, nr)], rng.integers(1, 1 << 50, nr) * 2 + 7).astype(np.int64)
+    null = rng.random(nr) < 0.1
+    b = rng.normal(0, 10, nr)
+    L = pa.RecordBatch.from_arrays([pa.array(keys), pa.array(pay)], names=["k", "p"])
+    R = pa.RecordBatch.from_arrays([pa.array(fk, mask=null), pa.array(b)], names=["fk", "b"])
+    nq = G.nq
+    join = nq.HashJoin.create(nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None),
+                              nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None), [("k", "fk")], "Inner")
+    got = join.execute()[0]
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    idx = np.minimum(np.searchsorted(sk, fk), nl - 1)
+    m = sk[idx] == fk
+    assert got.num_rows == int(m.sum())
+    assert got.column(0).null_count == 0 and np.array_equal(got.column(0).to_numpy(), fk[m])
+    assert np.array_equal(got.column(1).to_numpy(), pay[order[idx[m]]])
+    assert got.column(2).null_count == int((null & m).sum())
+    assert np.array_equal(np.asarray(got.column(2).is_null()), null[m])
+    assert np.array_equal(got.column(3).to_numpy(), b[m])
+
+
 def test_hash_join_unique_build_keys_and_u64():
     rng = np.random.default_rng(9)
     nl, nr = 10_000, 50_000
