@@ -172,4 +172,4 @@ uint64_t nqe_agg_capacity(double est);
 struct PagedStreams;
 int32_t nqe_estimate_distinct_u64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, double *est);
 bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m);
-int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int val_dtype, int need);
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need);

@@ -94,174 +94,280 @@ group_aggregate_kernel(const __grid_constant__ DevProgramSet ps, const __grid_co
 //
 // The table path above costs one L2 sector read plus one `red` per additive state per ROW, and the L2 retires only
 // ~1.5e11 of those per second (profiles/README_r01.md 2): 2.25 ms per 1e8 rows whatever the kernel does.  Shared
-// memory takes ~20x that rate, but holds only a few thousand groups per SM.  So the (key, value) rows are first split
-// by key hash into P partitions of ~1400 groups (paged_split.cuh: one pass, no count pass), and every partition is
-// then aggregated by sm_count / P CTAs, each in its own 4096-slot open-addressing table in SHARED memory
-//      ks[slot] = {key, f64 sum bits}   mm[slot] = {min, max} (OrderedFloat encoding)   cnt[slot]
-// Pages (4096 rows, 64 KB) arrive through one cp.async.bulk-filled buffer: a thread copies its four rows into
-// registers, the buffer is handed back at once and the next page flies while the CTA updates its table.  Per row:
-// one 16-byte probe read (key + current sum), a native 32-bit shared atomic for the count, one 64-bit CAS for the sum
-// (seeded with the sum the probe saw; shared memory has no f64 add), one 16-byte read of {min, max} and a CAS only
-// when the value improves one of them.  The four rows of a thread are kept in lock step so that their shared-memory
-// round trips overlap.  At the end every CTA folds its partial states into the global table (one probe + one `red`
-// per state per GROUP).  Rows that do not fit (a partition with more groups than estimated, probe sequence too long)
-// go to the global table one by one, so any key distribution stays correct.
+// memory takes ~20x that rate, but holds only a few thousand groups per SM.  So the (key, value as f64) rows are first
+// split by key hash into P partitions of <= ~700 groups (paged_split.cuh: one pass, no count pass), and every
+// partition is then aggregated by sm_count / P CTAs, each in its own 3072-slot table in SHARED memory:
+//      keys[slot]                     two-slot buckets, a key lives in one of TWO buckets (four candidate slots)
+//      filt[slot] = high halves of the current {min, max} in the ordered encoding
+//      sum[slot]  = f64 sum           cnt[slot] = u32 count           mm[slot] = {min, max}, full 64-bit
+// SIMT shapes the table: with open addressing a warp walks as many probe steps as its unluckiest lane (2.7 extra
+// steps per 32 rows at load 0.33, measured), so the lookup is made branch-free instead -- both buckets are read with
+// two unconditional 16-byte loads and the slot is selected with compares; only the first row of a group per CTA
+// takes the (divergent) insert path.
+// Data movement: every WARP owns a 2 KB stage; its lanes copy their four rows into registers, lane 0 at once issues
+// the cp.async.bulk of the warp's next 128 rows (one 2 KB slice of the CTA's next page), which flies while the warp
+// updates the table -- no CTA-wide barrier anywhere in the main loop, warps drift freely.  Per row: the two bucket
+// reads, a native 32-bit shared atomic for the count, an 8-byte read + one 64-bit CAS for the sum (shared memory has
+// no f64 add; the read is issued right before the CAS so that retries are rare), an 8-byte read of the filter and
+// NOTHING more for min/max unless the value's high half reaches the filter -- then the exact 64-bit compare + CAS run
+// on mm[] and the filter is tightened.  The four rows of a lane are kept in lock step so that their shared-memory
+// round trips overlap, and the warp is re-converged explicitly after every data-dependent loop (without
+// __syncwarp() the compiler lets the stragglers run the rest of the loop body on their own: measured 1.64 -> 1.38 ms).
+// At the end every CTA folds its partial states into the global table (one probe + one `red` per state per GROUP).
+// Rows that do not fit (all four candidate slots taken by other keys; the key i64::MIN) go to the global table one by
+// one, so any key distribution stays correct.
 // Eligible: all aggregates over ONE NULL-free 8-byte column; the key may be any Int64/UInt64 expression.
-constexpr int GA_THREADS = 1024, GA_K = 4;
-constexpr int GA_SLOTS = 4096;
-constexpr int GA_MAX_PROBE = 32;
-static_assert(GA_THREADS * GA_K == PS_PAGE_ROWS, "one page per step");
-constexpr size_t GA_SMEM = (size_t)PS_PAGE_ROWS * 16 + (size_t)GA_SLOTS * 36 + sizeof(PsPageBuf);
-
-// one row straight into the global table (keys that cannot live in the shared table)
-struct OneValueSource {
-    int dtype;
-    uint64_t bits;
-    __device__ __forceinline__ bool operator()(int, int *dt, uint64_t *b) const { *dt = dtype; *b = bits; return true; }
+constexpr int GA_THREADS = 1024, GA_WARPS = GA_THREADS / 32, GA_K = 4;
+constexpr int GA_SLOTS = 3072, GA_BUCKETS = GA_SLOTS / 2;
+constexpr int GA_CHUNK = 32 * GA_K;                 // rows per warp and stage
+constexpr unsigned GA_NONE = 0xFFFFFFFFu;
+static_assert(GA_WARPS * GA_CHUNK == PS_PAGE_ROWS, "a page is one chunk per warp");
+struct GaSmem {
+    ulonglong2 stage[GA_WARPS][GA_CHUNK];           // 64 KB
+    ulonglong2 keys2[GA_BUCKETS];                   // keys[2 b], keys[2 b + 1]
+    ulonglong2 mm[GA_SLOTS];
+    ulonglong2 sf[GA_SLOTS];                        // x: f64 sum; y: filter, low half min_hi (>= high half of the true min), high half max_hi (<=)
+    unsigned int cnt[GA_SLOTS];
+    unsigned long long full[GA_WARPS];
 };
-__device__ __forceinline__ void gp_global_row(const AggParams &ap, uint64_t key, int dtype, uint64_t bits) {
+constexpr size_t GA_SMEM = sizeof(GaSmem);
+
+// one row straight into the global table (keys that cannot live in the shared table); the value is already an f64
+__device__ __noinline__ void gp_global_row(const AggParams &ap, uint64_t key, uint64_t f64bits) {
+    struct Src {
+        uint64_t bits;
+        __device__ __forceinline__ bool operator()(int, int *dt, uint64_t *b) const { *dt = NQE_FLOAT64; *b = bits; return true; }
+    };
     Sector0 s0;
     unsigned long long *rec = find_slot(ap, key, &s0);
-    if (rec) update_states(ap, rec, s0, OneValueSource{dtype, bits});
+    if (rec) update_states(ap, rec, s0, Src{f64bits});
 }
 
-__device__ __forceinline__ unsigned long long ga_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long val) {
-    return atomicCAS(p, cmp, val);
+// the two buckets of a key inside a partition: multiply-shift on the folded key (the partition was chosen by the
+// murmur-style mix of the same key, so the three are independent enough)
+__device__ __forceinline__ void ga_buckets_of(unsigned long long key, unsigned *b1, unsigned *b2) {
+    const unsigned f = (unsigned)key ^ (unsigned)(key >> 32) * 0x85EBCA6Bu;
+    const unsigned x = __umulhi(f * 0x9E3779B1u, (unsigned)GA_BUCKETS), y = __umulhi(f * 0xC2B2AE35u + 0x27D4EB2Fu, (unsigned)GA_BUCKETS - 1u);
+    *b1 = x;
+    *b2 = y + (y >= x); // one of the other GA_BUCKETS - 1 buckets
+}
+
+// claim a slot for `key` among its four candidates (first free one in a fixed order, so that concurrent inserters of
+// the same key agree); GA_NONE: all four belong to other keys
+__device__ __noinline__ unsigned ga_insert(unsigned long long *keys, unsigned long long key) {
+    unsigned b1, b2;
+    ga_buckets_of(key, &b1, &b2);
+    for (int c = 0; c < 4; c++) {
+        const unsigned slot = (c < 2 ? 2 * b1 : 2 * b2) + (c & 1);
+        unsigned long long cur = *(volatile unsigned long long *)&keys[slot];
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&keys[slot], (unsigned long long)EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) return slot;
+        }
+        if (cur == key) return slot;
+    }
+    return GA_NONE;
 }
 
 // need: bit ST_CNT / ST_SUM / ST_MIN / ST_MAX set when the plan has such a state
 __global__ void __launch_bounds__(GA_THREADS, 1)
-gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_constant__ AggParams ap, int m, int val_dtype, int need) {
+gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_constant__ AggParams ap, int m, int need) {
     extern __shared__ __align__(128) unsigned char ga_smem[];
-    ulonglong2 *s_page = (ulonglong2 *)ga_smem;
-    ulonglong2 *s_ks = s_page + PS_PAGE_ROWS;
-    ulonglong2 *s_mm = s_ks + GA_SLOTS;
-    unsigned int *s_cnt = (unsigned int *)(s_mm + GA_SLOTS);
-    PsPageBuf &buf = *(PsPageBuf *)(s_cnt + GA_SLOTS);
-    const int tid = threadIdx.x, lane = tid & 31;
+    GaSmem &sm = *reinterpret_cast<GaSmem *>(ga_smem);
+    unsigned long long *const keys = (unsigned long long *)sm.keys2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x / m, sub = blockIdx.x % m;
     const unsigned long long rows_p = st.cursor[p];
     const unsigned npg = (unsigned)((rows_p + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
+    const unsigned last_fill = (unsigned)(rows_p - ((unsigned long long)(npg ? npg - 1 : 0) << PS_PAGE_SHIFT)); // rows of the last page
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
-        s_ks[i] = make_ulonglong2(EMPTY_KEY, 0ull);  // sum = +0.0
-        s_mm[i] = make_ulonglong2(~0ull, 0ull);      // identities of min / max in the ordered encoding
-        s_cnt[i] = 0u;
+        keys[i] = EMPTY_KEY;
+        sm.mm[i] = make_ulonglong2(~0ull, 0ull);   // identities of min / max in the ordered encoding
+        sm.sf[i] = make_ulonglong2(0ull, 0x00000000FFFFFFFFull); // sum = +0.0; min_hi = ~0, max_hi = 0: everything passes
+        sm.cnt[i] = 0u;
     }
-    ps_pagebuf_init(buf, GA_THREADS / 32);
+    if (lane == 0) nqe_mbar_init(&sm.full[warp], 1);
+    if (tid == 0) nqe_mbar_init_fence();
     __syncthreads();
     const unsigned int *pt = st.pt + (size_t)p * st.pt_stride;
-    unsigned long long pol = 0;
-    unsigned next_phys = 0; // thread 0: pool page of the page after the one in flight
-    if (tid == 0) {
-        pol = nqe_policy_evict_first();
-        if ((unsigned)sub < npg) ps_issue_page(st, buf, s_page, pt[sub] - 1u, ps_page_rows(st, p, sub), pol);
-        if ((unsigned)(sub + m) < npg) next_phys = pt[sub + m] - 1u;
+    // rows of page q that belong to this warp: [128 warp, 128 warp + 128) clipped to the page's fill
+    auto chunk_rows = [&](unsigned q) -> unsigned {
+        const unsigned fill = q + 1 == npg ? last_fill : (unsigned)PS_PAGE_ROWS, lo = warp * GA_CHUNK;
+        return fill <= lo ? 0u : (fill - lo < (unsigned)GA_CHUNK ? fill - lo : (unsigned)GA_CHUNK);
+    };
+    auto issue = [&](unsigned q, unsigned pte) { // lane 0; pte = page table entry (pool page + 1)
+        const unsigned rows = chunk_rows(q);
+        if (!rows) return;
+        nqe_mbar_arrive_expect_tx(&sm.full[warp], rows * 16u);
+        nqe_bulk_g2s(sm.stage[warp], st.pool + ((size_t)(pte - 1u) << PS_PAGE_SHIFT) + warp * GA_CHUNK, rows * 16u, &sm.full[warp],
+                     nqe_policy_evict_first());
+    };
+    unsigned next_pte = 0; // lane 0: loaded one iteration before it is used, so that nobody waits for the L2 round trip
+    if (lane == 0) {
+        if ((unsigned)sub < npg) issue(sub, pt[sub]);
+        if ((unsigned)(sub + m) < npg) next_pte = pt[sub + m];
     }
-    uint32_t it = 0;
-    for (unsigned q = sub; q < npg; q += m, it++) {
-        const unsigned fill = ps_page_rows(st, p, q);
-        nqe_mbar_wait(&buf.full, it & 1u);
+    uint32_t it = 0; // stages this warp has consumed
+    for (unsigned q = sub; q < npg; q += m) {
+        const unsigned rows = chunk_rows(q);
         unsigned long long key[GA_K], bits[GA_K];
         uint32_t live = 0;
+        if (rows) {
+            nqe_mbar_wait(&sm.full[warp], it & 1u);
+            it++;
 #pragma unroll
-        for (int j = 0; j < GA_K; j++) {
-            const unsigned idx = j * GA_THREADS + tid;
-            ulonglong2 r = make_ulonglong2(0ull, 0ull);
-            if (idx < fill) { r = s_page[idx]; live |= 1u << j; }
-            key[j] = r.x;
-            bits[j] = r.y;
-        }
-        __syncwarp();
-        if (lane == 0) nqe_mbar_arrive(&buf.empty);
-        if (tid == 0 && q + m < npg) { // the producer: refill the buffer as soon as every warp has let go of it
-            nqe_mbar_wait(&buf.empty, it & 1u);
-            ps_issue_page(st, buf, s_page, next_phys, ps_page_rows(st, p, q + m), pol);
-            if (q + 2 * m < npg) next_phys = pt[q + 2 * m] - 1u;
-        }
-        // ---- find or claim the slots: first probes of the four rows together, collisions walked one row at a time
-        unsigned slot[GA_K];
-        ulonglong2 ks[GA_K];
-#pragma unroll
-        for (int j = 0; j < GA_K; j++) {
-            slot[j] = __umulhi((unsigned)nqe_mix64(key[j]), (unsigned)GA_SLOTS);
-            ks[j] = s_ks[slot[j]];
-        }
-        uint32_t found = 0;
-#pragma unroll
-        for (int j = 0; j < GA_K; j++) {
-            if (!((live >> j) & 1u)) continue;
-            if (key[j] == EMPTY_KEY) continue; // i64::MIN marks free slots: that key lives in the global table only
-            for (int probe = 0; probe < GA_MAX_PROBE; probe++) {
-                unsigned long long k = ks[j].x;
-                if (k == EMPTY_KEY) {
-                    k = ga_cas64(&s_ks[slot[j]].x, (unsigned long long)EMPTY_KEY, key[j]);
-                    if (k == EMPTY_KEY) k = key[j];
-                }
-                if (k == key[j]) { found |= 1u << j; break; }
-                slot[j] = slot[j] + 1 == GA_SLOTS ? 0 : slot[j] + 1;
-                ks[j] = s_ks[slot[j]];
+            for (int j = 0; j < GA_K; j++) {
+                const unsigned idx = j * 32 + lane;
+                ulonglong2 r = make_ulonglong2(EMPTY_KEY, 0ull);
+                if (idx < rows) { r = sm.stage[warp][idx]; live |= 1u << j; }
+                key[j] = r.x;
+                bits[j] = r.y;
             }
         }
-        const uint32_t lost = live & ~found; // shared table full / i64::MIN key: straight to the global table
+        __syncwarp(); // the stage is in registers: refill it while the warp works
+        if (lane == 0 && q + m < npg) {
+            issue(q + m, next_pte);
+            if (q + 2 * m < npg) next_pte = pt[q + 2 * m];
+        }
+        if (!rows) continue;
+        // ---- branch-free lookup: both buckets of a row, then compares (two rows at a time: registers)
+        unsigned slot[GA_K];
+        uint32_t miss = 0;
+#pragma unroll
+        for (int h = 0; h < GA_K; h += 2) {
+            ulonglong2 A[2], B[2];
+            unsigned b1[2], b2[2];
+#pragma unroll
+            for (int j = h; j < h + 2; j++) {
+                ga_buckets_of(key[j], &b1[j - h], &b2[j - h]);
+                A[j - h] = sm.keys2[b1[j - h]];
+            }
+#pragma unroll
+            for (int j = h; j < h + 2; j++) { // the second bucket only if some lane needs it (most keys sit in their first)
+                const bool inA = A[j - h].x == key[j] || A[j - h].y == key[j] || key[j] == EMPTY_KEY;
+                B[j - h] = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
+                if (__any_sync(0xffffffffu, !inA)) B[j - h] = sm.keys2[b2[j - h]];
+            }
+#pragma unroll
+            for (int j = h; j < h + 2; j++) {
+                const unsigned long long k = key[j];
+                const ulonglong2 a = A[j - h], b = B[j - h];
+                const unsigned s1 = 2 * b1[j - h], s2 = 2 * b2[j - h];
+                unsigned s = GA_NONE; // selects, not branches
+                s = b.y == k ? s2 + 1 : s;
+                s = b.x == k ? s2 : s;
+                s = a.y == k ? s1 + 1 : s;
+                s = a.x == k ? s1 : s;
+                s = k == EMPTY_KEY ? GA_NONE : s; // i64::MIN marks free slots (and dead lanes): that key lives in the global table only
+                slot[j] = s;
+                miss |= (k != EMPTY_KEY && s == GA_NONE) ? 1u << j : 0u;
+            }
+        }
+        if (miss) { // first row of a group in this CTA (or a row that raced with it)
+#pragma unroll
+            for (int j = 0; j < GA_K; j++)
+                if ((miss >> j) & 1u) slot[j] = ga_insert(keys, key[j]);
+        }
+        __syncwarp();
+        uint32_t found = 0;
+#pragma unroll
+        for (int j = 0; j < GA_K; j++)
+            if (slot[j] != GA_NONE) found |= 1u << j;
+        const uint32_t lost = live & ~found; // no room in the shared table / i64::MIN key: straight to the global table
         if (lost) {
 #pragma unroll
             for (int j = 0; j < GA_K; j++)
-                if ((lost >> j) & 1u) gp_global_row(ap, key[j], val_dtype, bits[j]);
+                if ((lost >> j) & 1u) gp_global_row(ap, key[j], bits[j]);
         }
-        // ---- updates, the four rows in lock step (bits[j] becomes the value as f64)
-        unsigned long long seen[GA_K], old[GA_K];
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < GA_K; j++) {
-            seen[j] = ks[j].y;
-            bits[j] = (unsigned long long)__double_as_longlong(value_as_f64(val_dtype, bits[j]));
-            if (((found >> j) & 1u) && (need & (1 << ST_CNT))) atomicAdd(&s_cnt[slot[j]], 1u);
+        for (int j = 0; j < GA_K; j++)
+            if (!((found >> j) & 1u)) slot[j] = 0; // harmless address for the unconditional reads below
+        // ---- updates, the four rows in lock step (key[j] is dead from here on)
+        if (need & (1 << ST_CNT)) {
+#pragma unroll
+            for (int j = 0; j < GA_K; j++)
+                if ((found >> j) & 1u) atomicAdd(&sm.cnt[slot[j]], 1u);
         }
+        unsigned long long flt[GA_K];
         if (need & (1 << ST_SUM)) {
+            unsigned long long seen[GA_K], old[GA_K];
+#pragma unroll
+            for (int j = 0; j < GA_K; j++) {
+                const ulonglong2 r = sm.sf[slot[j]]; // the sum right before its CAS (retries stay rare) and the min/max filter
+                seen[j] = r.x;
+                flt[j] = r.y;
+            }
 #pragma unroll
             for (int j = 0; j < GA_K; j++) {
                 old[j] = seen[j];
                 if ((found >> j) & 1u)
-                    old[j] = ga_cas64(&s_ks[slot[j]].y, seen[j],
-                                      (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
-                                                                               __longlong_as_double((long long)bits[j])));
+                    old[j] = atomicCAS(&sm.sf[slot[j]].x, seen[j],
+                                       (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
+                                                                                __longlong_as_double((long long)bits[j])));
             }
 #pragma unroll
             for (int j = 0; j < GA_K; j++) {
-                if (!((found >> j) & 1u)) continue;
+#pragma unroll 1
                 while (old[j] != seen[j]) { // another row of this group got in between: retry on the value it left
                     seen[j] = old[j];
-                    old[j] = ga_cas64(&s_ks[slot[j]].y, seen[j],
-                                      (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
-                                                                               __longlong_as_double((long long)bits[j])));
+                    old[j] = atomicCAS(&sm.sf[slot[j]].x, seen[j],
+                                       (unsigned long long)__double_as_longlong(__longlong_as_double((long long)seen[j]) +
+                                                                                __longlong_as_double((long long)bits[j])));
                 }
+                __syncwarp();
             }
         }
         if (need & ((1 << ST_MIN) | (1 << ST_MAX))) {
+            uint32_t maybe = 0;
+            if (!(need & (1 << ST_SUM))) {
+#pragma unroll
+                for (int j = 0; j < GA_K; j++) flt[j] = sm.sf[slot[j]].y;
+            }
 #pragma unroll
             for (int j = 0; j < GA_K; j++) {
-                if (!((found >> j) & 1u)) continue;
-                const ulonglong2 mm = s_mm[slot[j]];
+                // high half of the ordered encoding (hash_common.cuh) -- NaN encodes as all ones
+                const int hi = (int)(bits[j] >> 32);
+                unsigned ohi = hi < 0 ? ~(unsigned)hi : (unsigned)hi | 0x80000000u;
                 const double v = __longlong_as_double((long long)bits[j]);
-                const unsigned long long o = nqe_f64_to_ord(v);
-                if ((need & (1 << ST_MAX)) && o > mm.y) atomicMax(&s_mm[slot[j]].y, o);
-                if ((need & (1 << ST_MIN)) && v == v && o < mm.x) atomicMin(&s_mm[slot[j]].x, o); // min never picks NaN (min.rs:49)
+                if (v != v) ohi = 0xFFFFFFFFu;
+                if (((found >> j) & 1u) && (ohi <= (unsigned)flt[j] || ohi >= (unsigned)(flt[j] >> 32))) maybe |= 1u << j;
             }
+            if (maybe) {
+#pragma unroll
+                for (int j = 0; j < GA_K; j++) {
+                    if (!((maybe >> j) & 1u)) continue;
+                    const double v = __longlong_as_double((long long)bits[j]);
+                    const unsigned long long o = nqe_f64_to_ord(v);
+                    const ulonglong2 cur = sm.mm[slot[j]];
+                    unsigned int *filt = (unsigned int *)&sm.sf[slot[j]].y;
+                    if ((need & (1 << ST_MAX)) && o > cur.y) {
+                        atomicMax(&sm.mm[slot[j]].y, o);
+                        atomicMax(filt + 1, (unsigned)(o >> 32));
+                    }
+                    if ((need & (1 << ST_MIN)) && v == v && o < cur.x) { // min never picks NaN (min.rs:49)
+                        atomicMin(&sm.mm[slot[j]].x, o);
+                        atomicMin(filt, (unsigned)(o >> 32));
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
     // partial states of this CTA -> global table
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
-        const ulonglong2 e = s_ks[i];
-        if (e.x == EMPTY_KEY) continue;
+        const unsigned long long key = keys[i];
+        if (key == EMPTY_KEY) continue;
         Sector0 s0;
-        unsigned long long *rec = find_slot(ap, e.x, &s0);
+        unsigned long long *rec = find_slot(ap, key, &s0);
         if (!rec) continue; // table full: flagged, the host grows the table and repeats this kernel
-        const ulonglong2 x = s_mm[i];
+        const ulonglong2 x = sm.mm[i];
         for (int s = 0; s < ap.n_states; s++) {
             unsigned long long *w = rec + ap.st_off[s];
             switch (ap.st_kind[s]) {
-            case ST_CNT: red_add_u64(w, (unsigned long long)s_cnt[i]); break;
-            case ST_SUM: red_add_f64(w, __longlong_as_double((long long)e.y)); break;
+            case ST_CNT: red_add_u64(w, (unsigned long long)sm.cnt[i]); break;
+            case ST_SUM: red_add_f64(w, __longlong_as_double((long long)sm.sf[i].x)); break;
             case ST_MIN: red_min_u64(w, x.x); break;
             default: red_max_u64(w, x.y); break;
             }
@@ -407,9 +513,9 @@ int32_t nqe_estimate_distinct_u64(nqe_ctx *ctx, const unsigned long long *col, i
     return NQE_OK;
 }
 
-// partitions for the shared-memory group-by: <= 0.45 * GA_SLOTS expected groups per partition, P * m CTAs, one per SM
+// partitions for the shared-memory group-by: <= 0.3 * GA_SLOTS expected groups per partition, P * m CTAs, one per SM
 bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m) {
-    const int want = (int)(est_groups * 1.15 / (0.45 * GA_SLOTS)) + 1;
+    const int want = (int)(est_groups * 1.15 / (0.3 * GA_SLOTS)) + 1;
     if (want > ctx->sm_count || want > PS_MAX_PARTS) return false;
     *m = ctx->sm_count / want;
     *P = ctx->sm_count / *m;
@@ -417,9 +523,9 @@ bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m) {
     return true;
 }
 
-int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int val_dtype, int need) {
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need) {
     NQE_CUDA(ctx, cudaFuncSetAttribute(gp2_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
-    gp2_aggregate_kernel<<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, val_dtype, need);
+    gp2_aggregate_kernel<<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, need);
     ctx->launches++;
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
@@ -705,26 +811,11 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 gp_dtype = vc.dtype;
                 rc = nqe_ps_create(ctx, n, P, &streams);
                 if (rc == NQE_OK) {
-                    const size_t smem = nqe_ps_split_smem();
                     PsSplitArgs sa{simple ? (const unsigned long long *)ps.cols[key_slot].values : nullptr,
-                                   (const unsigned long long *)vc.values, n};
-                    const int64_t tiles = (n + PS_SPLIT_THREADS * PS_SPLIT_K - 1) / (PS_SPLIT_THREADS * PS_SPLIT_K);
-                    int grid = ctx->sm_count * 2;
-                    if (grid > tiles) grid = (int)tiles;
+                                   (const unsigned long long *)vc.values, n, gp_dtype};
                     const PartByHash part{(uint32_t)P};
-                    cudaError_t e1, e2 = cudaSuccess;
-                    if (simple) {
-                        e1 = cudaFuncSetAttribute(ps_split_kernel<false, PartByHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        if (e1 == cudaSuccess && e2 == cudaSuccess)
-                            ps_split_kernel<false, PartByHash><<<grid, PS_SPLIT_THREADS, smem, ctx->stream>>>(streams, sa, part, ps, ap.status);
-                    } else {
-                        e1 = cudaFuncSetAttribute(ps_split_kernel<true, PartByHash>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        if (e1 == cudaSuccess && e2 == cudaSuccess)
-                            ps_split_kernel<true, PartByHash><<<grid, PS_SPLIT_THREADS, smem, ctx->stream>>>(streams, sa, part, ps, ap.status);
-                    }
-                    ctx->launches++;
-                    if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGetLastError() != cudaSuccess)
-                        rc = nqe_fail(ctx, NQE_ERR_CUDA, "group-by split launch failed");
+                    if (simple) rc = ps_split_launch<false, PartByHash>(ctx, streams, sa, part, ps, ap.status);
+                    else rc = ps_split_launch<true, PartByHash>(ctx, streams, sa, part, ps, ap.status);
                     use_part = rc == NQE_OK;
                 }
             }
@@ -744,7 +835,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 const int64_t tiles = (n + kk * AG_THREADS - 1) / (kk * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                if (use_part) rc = nqe_gp2_aggregate(ctx, streams, ap, gp_m, gp_dtype, gp_need);
+                if (use_part) rc = nqe_gp2_aggregate(ctx, streams, ap, gp_m, gp_need);
                 else if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple && agk == 8) group_aggregate_kernel<true, 8><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple) group_aggregate_kernel<true, 4><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);

@@ -128,7 +128,10 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
 // K rows is issued together (K independent loads in flight; at load factor <= 0.6 most rows
-// resolve there), collisions are then walked one row at a time.
+// resolve there), collisions are then walked one row at a time.  (Advancing the K sequences together -- one
+// table round trip per pass over all rows instead of per row and step -- was measured and is SLOWER: fused
+// join -> group-by 5.17 -> 5.66 ms, paged variant 4.78 -> 5.18 ms; the per-row loop is tighter and most lanes
+// never enter it.)
 template <int K>
 __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
                                             unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
@@ -828,27 +831,40 @@ struct PartBySlotRange { // partition = top of the hash = contiguous range of ta
     __device__ __forceinline__ int operator()(unsigned long long key) const { return (int)__umul64hi(nqe_mix64(key), P); }
 };
 
-constexpr int JP_THREADS = 1024, JP_K = 4;
-static_assert(JP_THREADS * JP_K == PS_PAGE_ROWS, "one page per step");
+// A CTA works on PIECES of T * K rows (a quarter, a half or a whole page) through one cp.async.bulk-filled buffer:
+// the rows go into registers, the buffer is handed back to thread 0 -- the elected producer -- which issues the copy
+// of the CTA's next piece at once, so it flies while the CTA probes and scatters.  Several small CTAs per SM overlap
+// each other's phases (bulk-copy wait, L2 probe latency, the scatter's barriers and its global cursor round trip).
+template <int T, int K>
 struct JpSmem {
-    ulonglong2 page[PS_PAGE_ROWS];
-    PsScatterSmem<JP_THREADS, JP_K> sc;
+    ulonglong2 piece[T * K];
+    PsScatterSmem<T, K> sc;
     PsPageBuf buf;
     unsigned int pstart[40]; // first page of every input partition in the concatenated page list (P1 <= 32)
 };
 
-__device__ __forceinline__ void jp_locate(const unsigned int *pstart, int P, unsigned w, int *p, unsigned *q) {
+// piece i of the concatenated page list -> (partition, page, first row inside the page, rows); *p is a running cursor
+template <int PIECE>
+__device__ __forceinline__ unsigned jp_locate(const PagedStreams &in, const unsigned int *pstart, unsigned i, int *p, unsigned *q,
+                                              unsigned *row0) {
+    constexpr unsigned PER_PAGE = PS_PAGE_ROWS / PIECE;
+    const unsigned w = i / PER_PAGE;
     int pp = *p;
-    while (pp + 1 < P && w >= pstart[pp + 1]) pp++;
+    while (pp + 1 < in.P && w >= pstart[pp + 1]) pp++;
     *p = pp;
     *q = w - pstart[pp];
+    *row0 = (i % PER_PAGE) * PIECE;
+    const unsigned fill = ps_page_rows(in, pp, *q);
+    return fill <= *row0 ? 0u : (fill - *row0 < (unsigned)PIECE ? fill - *row0 : (unsigned)PIECE);
 }
 
-__global__ void __launch_bounds__(JP_THREADS, 1)
+template <int T, int K, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_constant__ PagedStreams out, const JoinTable jt,
                         uint32_t P2) {
+    constexpr int PIECE = T * K;
     extern __shared__ __align__(128) unsigned char jp_smem_raw[];
-    JpSmem &sm = *reinterpret_cast<JpSmem *>(jp_smem_raw);
+    JpSmem<T, K> &sm = *reinterpret_cast<JpSmem<T, K> *>(jp_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
         unsigned acc = 0;
@@ -858,64 +874,87 @@ ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_co
         }
         sm.pstart[in.P] = acc;
     }
-    ps_pagebuf_init(sm.buf, JP_THREADS / 32);
+    ps_pagebuf_init(sm.buf, T / 32);
     ps_scatter_init(sm.sc); // __syncthreads inside
-    const unsigned total = sm.pstart[in.P];
-    int p = 0;          // every thread tracks the partition of its current page
-    int pn = 0;         // thread 0: partition of the next page
-    unsigned long long pol = 0;
-    unsigned next_phys = 0;
-    if (tid == 0) {
-        pol = nqe_policy_evict_first();
-        unsigned q;
-        if (blockIdx.x < total) {
-            jp_locate(sm.pstart, in.P, blockIdx.x, &pn, &q);
-            ps_issue_page(in, sm.buf, sm.page, in.pt[(size_t)pn * in.pt_stride + q] - 1u, ps_page_rows(in, pn, q), pol);
+    const unsigned total = sm.pstart[in.P] * (PS_PAGE_ROWS / PIECE);
+    // thread 0 walks the piece list one step ahead of the CTA (pn, in, next piece with rows)
+    int pn = 0;
+    unsigned nxt = blockIdx.x; // next piece to issue
+    auto issue_next = [&]() {  // thread 0: issue the copy of the next non-empty piece at or after `nxt`
+        while (nxt < total) {
+            unsigned q, row0;
+            const unsigned rows = jp_locate<PIECE>(in, sm.pstart, nxt, &pn, &q, &row0);
+            nxt += gridDim.x;
+            if (!rows) continue;
+            const unsigned pte = in.pt[(size_t)pn * in.pt_stride + q];
+            nqe_mbar_arrive_expect_tx(&sm.buf.full, rows * 16u);
+            const ulonglong2 *src = in.pool + ((size_t)(pte - 1u) << PS_PAGE_SHIFT) + row0;
+            for (unsigned off = 0; off < rows; off += 1024u) {
+                const unsigned len = rows - off < 1024u ? rows - off : 1024u;
+                nqe_bulk_g2s(sm.piece + off, src + off, len * 16u, &sm.buf.full, nqe_policy_evict_first());
+            }
+            return;
         }
-        if (blockIdx.x + gridDim.x < total) {
-            jp_locate(sm.pstart, in.P, blockIdx.x + gridDim.x, &pn, &q);
-            next_phys = in.pt[(size_t)pn * in.pt_stride + q] - 1u;
-        }
-    }
+    };
+    if (tid == 0) issue_next();
+    int p = 0;
     uint32_t it = 0;
-    for (unsigned w = blockIdx.x; w < total; w += gridDim.x, it++) {
-        unsigned q;
-        jp_locate(sm.pstart, in.P, w, &p, &q);
-        const unsigned fill = ps_page_rows(in, p, q);
+    for (unsigned i = blockIdx.x; i < total; i += gridDim.x) {
+        unsigned q, row0;
+        const unsigned rows = jp_locate<PIECE>(in, sm.pstart, i, &p, &q, &row0);
+        if (!rows) continue; // CTA-uniform
         nqe_mbar_wait(&sm.buf.full, it & 1u);
-        unsigned long long key[JP_K], val[JP_K];
+        unsigned long long key[K], val[K];
         uint32_t live = 0;
 #pragma unroll
-        for (int j = 0; j < JP_K; j++) {
-            const unsigned idx = j * JP_THREADS + tid;
+        for (int j = 0; j < K; j++) {
+            const unsigned idx = j * T + tid;
             ulonglong2 r = make_ulonglong2(0ull, 0ull);
-            if (idx < fill) { r = sm.page[idx]; live |= 1u << j; }
+            if (idx < rows) { r = sm.piece[idx]; live |= 1u << j; }
             key[j] = r.x;
             val[j] = r.y;
         }
         __syncwarp();
         if (lane == 0) nqe_mbar_arrive(&sm.buf.empty);
-        if (tid == 0 && w + gridDim.x < total) {
+        if (tid == 0) {
             nqe_mbar_wait(&sm.buf.empty, it & 1u);
-            unsigned qn;
-            jp_locate(sm.pstart, in.P, w + gridDim.x, &pn, &qn);
-            ps_issue_page(in, sm.buf, sm.page, next_phys, ps_page_rows(in, pn, qn), pol);
-            if (w + 2 * gridDim.x < total) {
-                int p2 = pn;
-                jp_locate(sm.pstart, in.P, w + 2 * gridDim.x, &p2, &qn);
-                next_phys = in.pt[(size_t)p2 * in.pt_stride + qn] - 1u;
-            }
+            issue_next();
         }
-        unsigned long long grp[JP_K];
-        uint64_t slot[JP_K];
-        probe_first<JP_K>(jt, key, live, grp, slot); // unique build keys: the first match is the only one
-        int pid[JP_K];
+        it++;
+        unsigned long long grp[K];
+        uint64_t slot[K];
+        probe_first<K>(jt, key, live, grp, slot); // unique build keys: the first match is the only one
+        int pid[K];
 #pragma unroll
-        for (int j = 0; j < JP_K; j++) {
+        for (int j = 0; j < K; j++) {
             if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
             pid[j] = (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
         }
-        ps_scatter_tile<JP_THREADS, JP_K>(out, sm.sc, grp, val, pid, live);
+        ps_scatter_tile<T, K>(out, sm.sc, grp, val, pid, live);
+    }
+}
+
+template <int T, int K, int MINB>
+int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2) {
+    auto kern = ja_probe_scatter_kernel<T, K, MINB>;
+    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpSmem<T, K>)));
+    kern<<<ctx->sm_count * MINB, T, sizeof(JpSmem<T, K>), ctx->stream>>>(in, out, jt, P2);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
+// knob NQE_JA_PROBE_SHAPE: 0 (default) = 256 threads x 4 rows (quarter pages, 4 CTAs/SM), 1 = 512 x 4 (half pages,
+// 2 CTAs/SM), 2 = 1024 x 4 (whole pages, 1 CTA/SM).  Measured 1e8 x 1e7: 4.78 / 4.92 / 4.95 ms for the whole operator.
+int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2) {
+    static int shape = -1;
+    if (shape < 0) {
+        const char *e = getenv("NQE_JA_PROBE_SHAPE");
+        shape = e ? atoi(e) : 0;
+    }
+    switch (shape) {
+    case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2);
+    case 2: return ja_probe_scatter_launch_shape<1024, 4, 1>(ctx, in, out, jt, P2);
+    default: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2);
     }
 }
 
@@ -1461,28 +1500,17 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         if (rc == NQE_OK) rc = nqe_ps_create(ctx, jp.n_probe, P2, &s2);
         if (rc == NQE_OK) {
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
-            const size_t smem1 = nqe_ps_split_smem();
-            const PsSplitArgs sa{jp.probe_keys, (const unsigned long long *)vc.values, jp.n_probe};
-            const int64_t tiles = (jp.n_probe + PS_SPLIT_THREADS * PS_SPLIT_K - 1) / (PS_SPLIT_THREADS * PS_SPLIT_K);
-            int grid = ctx->sm_count * 2;
-            if (grid > tiles) grid = (int)tiles;
+            const PsSplitArgs sa{jp.probe_keys, (const unsigned long long *)vc.values, jp.n_probe, vc.dtype};
             DevProgramSet none;
             memset(&none, 0, sizeof none);
-            cudaError_t e1 = cudaFuncSetAttribute(ps_split_kernel<false, PartBySlotRange>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-            cudaError_t e2 = cudaFuncSetAttribute(ja_probe_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpSmem));
-            if (e1 == cudaSuccess && e2 == cudaSuccess) {
-                ps_split_kernel<false, PartBySlotRange><<<grid, PS_SPLIT_THREADS, smem1, ctx->stream>>>(s1, sa, PartBySlotRange{(uint64_t)P1}, none, ap.status);
-                ja_probe_scatter_kernel<<<ctx->sm_count, JP_THREADS, sizeof(JpSmem), ctx->stream>>>(s1, s2, jp.jt, (uint32_t)P2);
-                ctx->launches += 2;
-            }
-            if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGetLastError() != cudaSuccess)
-                rc = nqe_fail(ctx, NQE_ERR_CUDA, "join-aggregate split/probe launch failed");
+            rc = ps_split_launch<false, PartBySlotRange>(ctx, s1, sa, PartBySlotRange{(uint64_t)P1}, none, ap.status);
+            if (rc == NQE_OK) rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2);
         }
         uint64_t capacity = nqe_agg_capacity(est_groups);
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
             rc = nqe_agg_table_create(ctx, &ap, capacity);
             if (rc != NQE_OK) break;
-            rc = nqe_gp2_aggregate(ctx, s2, ap, m2, vc.dtype, need);
+            rc = nqe_gp2_aggregate(ctx, s2, ap, m2, need);
             if (rc != NQE_OK) break;
             cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {

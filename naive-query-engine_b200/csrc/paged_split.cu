@@ -1,4 +1,5 @@
 // paged_split.cu -- host side of the paged partition streams (see paged_split.cuh)
+#include <cstdlib>
 #include <cstring>
 
 #include "paged_split.cuh"
@@ -34,4 +35,12 @@ void nqe_ps_destroy(nqe_ctx *ctx, PagedStreams *ps) {
     memset(ps, 0, sizeof *ps);
 }
 
-size_t nqe_ps_split_smem() { return sizeof(PsScatterSmem<PS_SPLIT_THREADS, PS_SPLIT_K>); }
+int nqe_ps_split_shape() {
+    static int shape = -1;
+    if (shape < 0) {
+        const char *e = getenv("NQE_PS_SPLIT_SHAPE");
+        shape = e ? atoi(e) : 0;
+        if (shape < 0 || shape > 2) shape = 0;
+    }
+    return shape;
+}

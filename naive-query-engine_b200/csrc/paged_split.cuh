@@ -1,4 +1,4 @@
-// paged_split.cuh -- "paged partition streams": one pass that splits 16-byte rows {key, value} into P partitions
+// paged_split.cuh -- "paged partition streams": one pass that splits 16-byte rows {key, value as f64} into P partitions
 // without knowing the partition sizes beforehand (no count pass, no scan pass).
 //
 // A partition is a VIRTUAL row stream: a 64-bit append cursor per partition plus a page table that maps its 4096-row
@@ -162,7 +162,13 @@ __device__ __forceinline__ void ps_scatter_tile(const PagedStreams &ps, PsScatte
 struct PsSplitArgs {
     const unsigned long long *keys, *vals;
     int64_t n;
+    int32_t val_dtype; // the value travels "as f64" (sum.rs:44 `val as f64`): Int64 / UInt64 values are converted here, once
 };
+__device__ __forceinline__ unsigned long long ps_as_f64_bits(int dtype, unsigned long long bits) {
+    if (dtype == NQE_INT64) return (unsigned long long)__double_as_longlong(__ll2double_rn((long long)bits));
+    if (dtype == NQE_UINT64) return (unsigned long long)__double_as_longlong(__ull2double_rn(bits));
+    return bits;
+}
 struct PartByHash { // partition = high 32 bits of the key's hash, range-reduced
     uint32_t P;
     __device__ __forceinline__ int operator()(unsigned long long key) const {
@@ -170,13 +176,14 @@ struct PartByHash { // partition = high 32 bits of the key's hash, range-reduced
     }
 };
 
-constexpr int PS_SPLIT_THREADS = 512, PS_SPLIT_K = 8;
-
-template <bool KEYEXPR, typename Part>
-__global__ void __launch_bounds__(PS_SPLIT_THREADS, 2)
+// Tile shapes of the split kernel (knob NQE_PS_SPLIT_SHAPE): 0 (default) = 256 threads x 8 rows (2048-row tiles,
+// 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM), 2 = 1024 x 4 (4096-row tiles, 1 CTA/SM).  Measured, group-by
+// of 1e8 rows into 148 partitions: 1.95 / 1.98 / 2.24 ms for the whole operator.
+template <bool KEYEXPR, typename Part, int T, int K, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 ps_split_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, const Part part,
                 const __grid_constant__ DevProgramSet prog, uint32_t *status) {
-    constexpr int T = PS_SPLIT_THREADS, K = PS_SPLIT_K, TILE = T * K;
+    constexpr int TILE = T * K;
     extern __shared__ __align__(16) unsigned char ps_smem_raw[];
     PsScatterSmem<T, K> &sm = *reinterpret_cast<PsScatterSmem<T, K> *>(ps_smem_raw);
     ps_scatter_init(sm);
@@ -200,10 +207,38 @@ ps_split_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, co
             for (int j = 0; j < K; j++) key[j] = ((live >> j) & 1u) ? ld_stream_u64(a.keys + e0 + (int64_t)j * T) : 0ull;
         }
 #pragma unroll
-        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ld_stream_u64(a.vals + e0 + (int64_t)j * T) : 0ull;
+        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ps_as_f64_bits(a.val_dtype, ld_stream_u64(a.vals + e0 + (int64_t)j * T)) : 0ull;
 #pragma unroll
         for (int j = 0; j < K; j++) pid[j] = part(key[j]);
         ps_scatter_tile<T, K>(ps, sm, key, val, pid, live);
+    }
+}
+
+int nqe_ps_split_shape(); // paged_split.cu: knob NQE_PS_SPLIT_SHAPE
+
+template <bool KEYEXPR, typename Part, int T, int K, int MINB>
+static int32_t ps_split_launch_shape(nqe_ctx *ctx, const PagedStreams &ps, const PsSplitArgs &a, const Part &part,
+                                     const DevProgramSet &prog, uint32_t *status) {
+    auto kern = ps_split_kernel<KEYEXPR, Part, T, K, MINB>;
+    const size_t smem = sizeof(PsScatterSmem<T, K>);
+    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = (a.n + (int64_t)T * K - 1) / ((int64_t)T * K);
+    int grid = ctx->sm_count * MINB;
+    if (grid > tiles) grid = (int)tiles;
+    if (grid < 1) return NQE_OK;
+    kern<<<grid, T, smem, ctx->stream>>>(ps, a, part, prog, status);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
+// split (key | key expression, value) into the streams `ps` on ctx->stream
+template <bool KEYEXPR, typename Part>
+static int32_t ps_split_launch(nqe_ctx *ctx, const PagedStreams &ps, const PsSplitArgs &a, const Part &part,
+                               const DevProgramSet &prog, uint32_t *status) {
+    switch (nqe_ps_split_shape()) {
+    case 1: return ps_split_launch_shape<KEYEXPR, Part, 512, 8, 2>(ctx, ps, a, part, prog, status);
+    case 2: return ps_split_launch_shape<KEYEXPR, Part, 1024, 4, 1>(ctx, ps, a, part, prog, status);
+    default: return ps_split_launch_shape<KEYEXPR, Part, 256, 8, 4>(ctx, ps, a, part, prog, status);
     }
 }
 
@@ -240,4 +275,3 @@ __device__ __forceinline__ void ps_issue_page(const PagedStreams &ps, PsPageBuf 
 // host side (paged_split.cu)
 int32_t nqe_ps_create(nqe_ctx *ctx, int64_t max_rows, int P, PagedStreams *ps);
 void nqe_ps_destroy(nqe_ctx *ctx, PagedStreams *ps);
-size_t nqe_ps_split_smem();
