@@ -112,7 +112,13 @@ typedef struct nqe_expr {
 
 /* AggregateOperator implementations, aggregate/{count,sum,avg,min,max}.rs.
  * The argument is a bare column (planner/mod.rs:104-163). */
-typedef enum nqe_agg_op { NQE_AGG_COUNT = 0, NQE_AGG_SUM = 1, NQE_AGG_AVG = 2, NQE_AGG_MIN = 3, NQE_AGG_MAX = 4 } nqe_agg_op;
+typedef enum nqe_agg_op {
+    NQE_AGG_COUNT = 0, NQE_AGG_SUM = 1, NQE_AGG_AVG = 2, NQE_AGG_MIN = 3, NQE_AGG_MAX = 4,
+    /* EXTENSION (not in the reference, whose aggregate output carries no key column, aggregate/mod.rs:117-121): emits the
+     * group key itself as an Int64 column (UInt64 keys: same bits); `column` is ignored.  Grouped plans only.  The
+     * multi-GPU plans need it to merge partial states by key. */
+    NQE_AGG_GROUP_KEY = 5
+} nqe_agg_op;
 typedef struct nqe_agg { int32_t op; int32_t column; } nqe_agg;
 
 /* ---- context ------------------------------------------------------------ */
@@ -131,7 +137,8 @@ double nqe_ctx_last_op_ms(const nqe_ctx *ctx);
 
 /* ---- tables: ScanPlan / TableSource::scan (scan.rs:34-36, memory.rs:31-41) --- */
 /* Host Arrow buffers -> pinned staging -> HBM.  Replaces the Arc-clone of
- * MemTable batches with a DMA. */
+ * MemTable batches with a DMA.  * The call returns after the copies have completed: the host buffers may be released or
+ * modified as soon as it returns (pinned sources are DMA'd directly, pageable ones staged). */
 int32_t nqe_table_upload(nqe_ctx *ctx, const nqe_column_desc *cols, int32_t n_cols, nqe_table **out);
 /* Wrap device buffers owned by the caller (no copy; must outlive the table). */
 int32_t nqe_table_from_device(nqe_ctx *ctx, const nqe_column_desc *cols, int32_t n_cols, nqe_table **out);
@@ -149,6 +156,11 @@ void nqe_table_free(nqe_table *t);
  * (offset.rs:30-51, limit.rs:32-49).  offset must be a multiple of 8 unless the
  * table has no bitmaps; otherwise a copy is made. */
 int32_t nqe_table_slice(nqe_ctx *ctx, const nqe_table *t, int64_t offset, int64_t len, nqe_table **out);
+/* concat_batches (hash_join.rs:258-273; used on the join's build side, hash_join.rs:131-132, and on the aggregate's
+ * input, aggregate/mod.rs:143-144): the rows of tables[0..n) in order, as one new table.  Column counts and dtypes
+ * must agree (else NQE_ERR_INVALID_ARG); n_tables >= 1 (an empty result needs a schema: pass an empty
+ * table).  The inputs are not consumed. */
+int32_t nqe_table_concat(nqe_ctx *ctx, const nqe_table *const *tables, int32_t n_tables, nqe_table **out);
 
 /* ---- operators ----------------------------------------------------------- */
 /* SelectionPlan::execute (selection.rs:58-107) fused with ProjectionPlan::execute

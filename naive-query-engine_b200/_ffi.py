@@ -72,6 +72,7 @@ SYMBOLS = {
     "nqe_table_download_column": (C.c_int32, [_P, _P, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
     "nqe_table_free": (None, [_P]),
     "nqe_table_slice": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "nqe_table_concat": (C.c_int32, [_P, C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
     "nqe_filter_project": (C.c_int32, [_P, _P, C.POINTER(Expr), C.POINTER(Expr), C.c_int32, C.POINTER(_P)]),
     "nqe_filter_project_host": (C.c_int32, [_P, C.POINTER(ColumnDesc), C.c_int32, C.POINTER(Expr), C.POINTER(Expr), C.c_int32,
                                             C.POINTER(ColumnDesc), C.POINTER(C.c_int64)]),

@@ -238,6 +238,7 @@ static int32_t check_desc(nqe_ctx *ctx, const nqe_column_desc *cols, int32_t n_c
     for (int i = 0; i < n_cols; i++) {
         const nqe_column_desc &c = cols[i];
         if (c.dtype < NQE_BOOL || c.dtype > NQE_UTF8) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "column %d: bad dtype %d", i, c.dtype);
+        if (c.length < 0 || c.data_bytes < 0) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "column %d: negative length", i);
         if (c.length != *nrows) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "column %d: length %lld != %lld", i, (long long)c.length, (long long)*nrows);
         if (c.length > 0 && !c.values) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "column %d: null values buffer", i);
         if (c.null_count > 0 && !c.validity) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "column %d: null_count > 0 without validity", i);
@@ -278,12 +279,15 @@ extern "C" int32_t nqe_table_upload(nqe_ctx *ctx, const nqe_column_desc *cols, i
             return rc;
         }
     }
+    // pinned sources are DMA'd asynchronously: the caller's buffers are free to go when this returns
+    NQE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = t;
     return NQE_OK;
 }
 
 extern "C" int32_t nqe_table_from_device(nqe_ctx *ctx, const nqe_column_desc *cols, int32_t n_cols, nqe_table **out) {
     if (!ctx || !out) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
     int64_t nrows = 0;
     NQE_TRY(check_desc(ctx, cols, n_cols, &nrows));
     nqe_table *t;

@@ -440,8 +440,9 @@ __global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_re
     if (!occ) return;
     const unsigned long long row = base + __popc(m & ((1u << lane) - 1u));
     for (int a = 0; a < ap.n_aggs; a++) {
-        const unsigned long long w = rec[ap.st_off[ap.agg_state[a]]];
+        const unsigned long long w = ap.agg_op[a] == NQE_AGG_GROUP_KEY ? 0ull : rec[ap.st_off[ap.agg_state[a]]];
         switch (ap.agg_op[a]) {
+        case NQE_AGG_GROUP_KEY: ((unsigned long long *)xp.out[a])[row] = r == n_records - 1 ? EMPTY_KEY : rec[0]; break; // last record: the key i64::MIN
         case NQE_AGG_COUNT: ((unsigned long long *)xp.out[a])[row] = w; break;
         case NQE_AGG_SUM: ((unsigned long long *)xp.out[a])[row] = w; break;
         case NQE_AGG_AVG: { // avg.rs:118: sum / cnt as f64, cnt is u32 (wraps in release builds)
@@ -455,17 +456,29 @@ __global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_re
 }
 
 // cardinality estimate by linear counting over a strided sample
+// ... and a 256-bin histogram of the sampled keys over the hash bits the partitioned path splits on: a bin far above the
+// mean is a hot key (all its rows land in one partition, i.e. on one SM)
+constexpr int AGG_SKEW_BINS = 256;
 __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int64_t n_rows, int64_t stride,
-                                  int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status) {
+                                  int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status, unsigned int *bins) {
+    __shared__ unsigned int s_bins[AGG_SKEW_BINS];
+    for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x) s_bins[b] = 0;
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sample) return;
-    const int64_t e = i * stride;
-    RowRegs<1> key;
-    run_program<1>(ps, 0, e, 1, e < n_rows ? 1u : 0u, 0u, 0u, key, status);
-    if (key.valid & 1u) {
-        const uint32_t h = (uint32_t)(nqe_mix64(key.v[0]) >> 32) & bits_mask;
-        atomicOr(bitmap + (h >> 5), 1u << (h & 31));
+    if (i < n_sample) {
+        const int64_t e = i * stride;
+        RowRegs<1> key;
+        run_program<1>(ps, 0, e, 1, e < n_rows ? 1u : 0u, 0u, 0u, key, status);
+        if (key.valid & 1u) {
+            const uint64_t hh = nqe_mix64(key.v[0]);
+            const uint32_t h = (uint32_t)(hh >> 32) & bits_mask;
+            atomicOr(bitmap + (h >> 5), 1u << (h & 31));
+            atomicAdd(&s_bins[hh >> 56], 1u);
+        }
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x)
+        if (s_bins[b]) atomicAdd(bins + b, s_bins[b]);
 }
 __global__ void popcount_kernel(const uint32_t *bitmap, int n_words, unsigned long long *out) {
     unsigned int c = 0;
@@ -557,7 +570,13 @@ int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const 
     };
     for (int a = 0; a < n_aggs; a++) {
         const int op = aggs[a].op;
-        if (op < NQE_AGG_COUNT || op > NQE_AGG_MAX) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad aggregate op %d", op);
+        if (op < NQE_AGG_COUNT || op > NQE_AGG_GROUP_KEY) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "bad aggregate op %d", op);
+        if (op == NQE_AGG_GROUP_KEY) { // extension: the group key as an output column; no state
+            if (!grouped) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "NQE_AGG_GROUP_KEY needs a GROUP BY");
+            ap->agg_op[a] = op;
+            ap->agg_state[a] = ap->agg_state2[a] = 0;
+            continue;
+        }
         const int dt = col_dtypes[a];
         if (op != NQE_AGG_COUNT && (dt == NQE_BOOL || dt == NQE_UTF8)) {
             // update_batch: Err(NotSupported) (sum.rs:91-96); update(row): unimplemented!() (sum.rs:108)
@@ -599,6 +618,7 @@ int32_t nqe_agg_layout(nqe_ctx *ctx, const nqe_agg *aggs, int32_t n_aggs, const 
         ap->st_src[i] = src2[i];
     }
     for (int a = 0; a < n_aggs; a++) {
+        if (ap->agg_op[a] == NQE_AGG_GROUP_KEY) continue;
         ap->agg_state[a] = inv[ap->agg_state[a]];
         ap->agg_state2[a] = inv[ap->agg_state2[a]];
     }
@@ -642,7 +662,8 @@ int32_t nqe_agg_extract(nqe_ctx *ctx, const AggParams &ap, bool is_global, int64
     if (out_cap < 1) out_cap = 1;
     t->cols.resize(ap.n_aggs);
     for (int a = 0; a < ap.n_aggs; a++) {
-        NQE_TRY(nqe_column_alloc(ctx, ap.agg_op[a] == NQE_AGG_COUNT ? NQE_UINT64 : NQE_FLOAT64, out_cap, false, &t->cols[a]));
+        const int32_t odt = ap.agg_op[a] == NQE_AGG_COUNT ? NQE_UINT64 : ap.agg_op[a] == NQE_AGG_GROUP_KEY ? NQE_INT64 : NQE_FLOAT64;
+        NQE_TRY(nqe_column_alloc(ctx, odt, out_cap, false, &t->cols[a]));
         xp.out[a] = t->cols[a].values;
     }
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint64_t), ctx->stream));
@@ -675,8 +696,10 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         in->cols[group_expr->nodes[0].column].dtype == NQE_UTF8) {
         const int kc = group_expr->nodes[0].column;
         for (int a = 0; a < n_aggs; a++) // update(row) on a Utf8 argument: unimplemented!() (sum.rs:108)
-            if (aggs[a].column == kc && aggs[a].op != NQE_AGG_COUNT)
+            if (aggs[a].column == kc && aggs[a].op != NQE_AGG_COUNT && aggs[a].op != NQE_AGG_GROUP_KEY)
                 return nqe_fail(ctx, NQE_ERR_PANIC, "%s func for Utf8 is not supported", agg_fn_name(aggs[a].op));
+        for (int a = 0; a < n_aggs; a++)
+            if (aggs[a].op == NQE_AGG_GROUP_KEY) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "NQE_AGG_GROUP_KEY over a Utf8 key");
         DevColumn ids;
         NQE_TRY(nqe_utf8_key_ids(ctx, in->cols[kc], nullptr, &ids, nullptr));
         nqe_table view;
@@ -710,11 +733,13 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
     if (n_aggs > AG_MAX) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "at most %d aggregates per plan", AG_MAX);
     for (int a = 0; a < n_aggs; a++) {
         const int col = aggs[a].column;
+        if (aggs[a].op == NQE_AGG_GROUP_KEY) { dts[a] = NQE_INT64; continue; } // no argument
         if (col < 0 || col >= (int)in->cols.size()) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", col);
         dts[a] = in->cols[col].dtype;
     }
     int32_t slots[AG_MAX];
     for (int a = 0; a < n_aggs; a++) { // register the argument columns as column slots
+        if (aggs[a].op == NQE_AGG_GROUP_KEY) { slots[a] = 0; continue; }
         const DevColumn &c = in->cols[aggs[a].column];
         int slot = -1;
         for (int q = 0; q < ps.n_cols; q++)
@@ -759,21 +784,31 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         // --- size the table from a sampled cardinality estimate, grow on overflow
         uint64_t capacity = 1024;
         double est_groups = 1e18;
+        bool skewed = false; // a hot key: the partitioned path would put all its rows on one SM (measured, Zipf-1.0: 52 vs 21 ms)
         if (n > 0) {
             const int64_t n_sample = n < (1 << 20) ? n : (1 << 20);
             const int64_t stride = n / n_sample;
             const uint32_t bits = 1u << 23; // 8 Mi bits = 1 MiB bitmap
             void *bm = nullptr;
-            rc = nqe_dev_alloc(ctx, &bm, bits / 8);
+            rc = nqe_dev_alloc(ctx, &bm, bits / 8 + AGG_SKEW_BINS * 4);
             if (rc == NQE_OK) {
-                cudaMemsetAsync(bm, 0, bits / 8, ctx->stream);
+                unsigned int *bins = (unsigned int *)((uint8_t *)bm + bits / 8);
+                unsigned int h_bins[AGG_SKEW_BINS];
+                cudaMemsetAsync(bm, 0, bits / 8 + AGG_SKEW_BINS * 4, ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
                 agg_sample_kernel<<<(unsigned)((n_sample + 255) / 256), 256, 0, ctx->stream>>>(
-                    ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status);
+                    ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status, bins);
                 popcount_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t *)bm, bits / 32, (unsigned long long *)ctx->d_scratch);
                 ctx->launches += 2;
+                cudaMemcpyAsync(h_bins, bins, sizeof h_bins, cudaMemcpyDeviceToHost, ctx->stream);
                 rc = read_scratch(ctx, 2);
                 nqe_dev_free(ctx, bm);
+                if (rc == NQE_OK) {
+                    uint64_t tot = 0, mx = 0;
+                    for (unsigned int c : h_bins) { tot += c; mx = c > mx ? c : mx; }
+                    // a partition of the split holds ~1/148 of the keys; a bin 4x the mean holds a key with > ~1 % of the rows
+                    skewed = tot >= 4096 && mx * AGG_SKEW_BINS > 4 * tot;
+                }
             }
             if (rc == NQE_OK) {
                 const double m = (double)bits, z = m - (double)ctx->h_scratch[0];
@@ -798,7 +833,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         PagedStreams streams;
         memset(&streams, 0, sizeof streams);
         int gp_need = 0, gp_m = 1, gp_dtype = 0;
-        if (rc == NQE_OK && agg_part && n >= agg_part_min_rows && ap.n_states > 0 && est_groups >= 2048.0) {
+        if (rc == NQE_OK && agg_part && !skewed && n >= agg_part_min_rows && ap.n_states > 0 && est_groups >= 2048.0) {
             bool one_src = true;
             for (int q = 0; q < ap.n_states; q++) {
                 if (ap.st_src[q] != ap.st_src[0]) one_src = false;

@@ -1431,6 +1431,11 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     memset(&ap, 0, sizeof ap);
     int32_t dts[AG_MAX], src_ids[AG_MAX];
     for (int a = 0; a < n_aggs; a++) {
+        if (aggs[a].op == NQE_AGG_GROUP_KEY) { // extension: emits the group key; no argument
+            dts[a] = NQE_INT64;
+            src_ids[a] = 0;
+            continue;
+        }
         const DevColumn *c = col_at(aggs[a].column);
         if (!c) return nqe_fail(ctx, NQE_ERR_PANIC, "aggregate column index %d out of range", aggs[a].column);
         dts[a] = c->dtype;
@@ -1438,7 +1443,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         jp.val_left[a] = aggs[a].column < nl;
         src_ids[a] = a; // jp.val[a]; identical columns share an id
         for (int b2 = 0; b2 < a; b2++)
-            if (aggs[b2].column == aggs[a].column) { src_ids[a] = src_ids[b2]; break; }
+            if (aggs[b2].op != NQE_AGG_GROUP_KEY && aggs[b2].column == aggs[a].column) { src_ids[a] = src_ids[b2]; break; }
     }
     NQE_TRY(nqe_agg_layout(ctx, aggs, n_aggs, dts, src_ids, true, &ap));
     fill_src(&jp.group, *g);

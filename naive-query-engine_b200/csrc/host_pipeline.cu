@@ -73,6 +73,26 @@ extern "C" int32_t nqe_filter_project_host(nqe_ctx *ctx, const nqe_column_desc *
     }
     for (int i = 0; i < n_projs && pipelined; i++)
         if (!out_cols[i].values || out_cols[i].length < n || !is_pinned(out_cols[i].values)) pipelined = false;
+    if (pipelined) {
+        // type-check the expressions before the first chunk moves (reference error behaviour: raised before any work)
+        // and keep plans whose outputs are Boolean or may be NULL (a NULL literal, a NULL-able predicate keeping NULL
+        // rows) off the pipeline: it only drains NULL-free 8-byte result columns
+        std::vector<nqe_column_desc> d0(cols, cols + n_cols);
+        for (auto &c : d0) { c.length = 0; c.null_count = 0; c.validity = nullptr; } // a zero-row table of the same schema
+        nqe_table *probe = nullptr;
+        NQE_TRY(nqe_table_from_device(ctx, d0.data(), n_cols, &probe));
+        std::vector<const nqe_expr *> list;
+        if (predicate) list.push_back(predicate);
+        for (int i = 0; i < n_projs; i++) list.push_back(&projs[i]);
+        DevProgramSet ps;
+        memset(&ps, 0, sizeof ps);
+        std::vector<ExprInfo> info(list.size());
+        const int32_t trc = nqe_compile_exprs(ctx, probe, list.data(), (int32_t)list.size(), &ps, info.data());
+        nqe_table_free(probe);
+        if (trc != NQE_OK) return trc;
+        for (size_t i = 0; i < info.size(); i++)
+            if (info[i].nullable || (info[i].result_dtype == NQE_BOOL && !(predicate && i == 0))) pipelined = false;
+    }
 
     if (!pipelined) {
         nqe_table *in = nullptr, *out = nullptr;

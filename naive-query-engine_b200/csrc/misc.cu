@@ -33,6 +33,24 @@ __global__ void utf8_rebase_kernel(const int32_t *__restrict__ src, int64_t n_pl
     if (i < n_plus_1) dst[i] = src[i] - base;
 }
 
+// concat_batches: OR the first n bits of `src` (nullptr = all ones) into `dst` starting at bit `at`.  `dst` was
+// zeroed; words shared by two pieces are why this is an atomicOr.
+__global__ void bitmap_place_kernel(const uint32_t *__restrict__ src, int64_t n, uint32_t *__restrict__ dst, int64_t at) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // source word
+    if (w * 32 >= n) return;
+    const int64_t rem = n - w * 32;
+    uint32_t v = src ? src[w] : 0xffffffffu;
+    if (rem < 32) v &= (1u << rem) - 1u;
+    const int64_t b = at + w * 32;
+    const int sh = (int)(b & 31);
+    if (v << sh) atomicOr(dst + (b >> 5), v << sh);
+    if (sh && (v >> (32 - sh))) atomicOr(dst + (b >> 5) + 1, v >> (32 - sh));
+}
+__global__ void utf8_offsets_place_kernel(const int32_t *__restrict__ src, int64_t n, int32_t add, int32_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+
 constexpr int MAX_PARTS = 64;
 
 struct PartParams {
@@ -405,5 +423,92 @@ extern "C" int32_t nqe_radix_partition(nqe_ctx *ctx, const nqe_table *in, int32_
         return rc;
     }
     *out = t;
+    return NQE_OK;
+}
+
+// concat_batches (hash_join.rs:258-273: column-wise arrow `concat`; used on the join's build side :131-132 and on the
+// aggregate's input, aggregate/mod.rs:143-144) for device tables: one device-to-device copy per value buffer, bitmaps
+// (validity, Boolean values) placed at their bit offsets, Utf8 offsets rebased.  Schemas must agree column by column.
+extern "C" int32_t nqe_table_concat(nqe_ctx *ctx, const nqe_table *const *tables, int32_t n_tables, nqe_table **out) {
+    if (!ctx || !out || n_tables < 0 || (n_tables > 0 && !tables)) return NQE_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    if (n_tables == 0) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "concat of zero tables needs a schema: pass an empty table");
+    const size_t ncols = tables[0]->cols.size();
+    int64_t total = 0;
+    for (int t = 0; t < n_tables; t++) {
+        if (!tables[t] || tables[t]->cols.size() != ncols) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "concat: batch %d has a different column count", t);
+        for (size_t c = 0; c < ncols; c++)
+            if (tables[t]->cols[c].dtype != tables[0]->cols[c].dtype)
+                return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "concat: column %d of batch %d has a different type", (int)c, t); // arrow: ArrowError::InvalidArgumentError
+        total += tables[t]->nrows;
+    }
+    if (total >= ((int64_t)1 << 31)) {
+        for (size_t c = 0; c < ncols; c++)
+            if (tables[0]->cols[c].dtype == NQE_UTF8) return nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "concat: Utf8 column beyond 2^31 rows");
+    }
+    nqe_table *r;
+    nqe_table_new(ctx, total, &r);
+    r->cols.resize(ncols);
+    int32_t rc = NQE_OK;
+    for (size_t c = 0; c < ncols && rc == NQE_OK; c++) {
+        const int32_t dt = tables[0]->cols[c].dtype;
+        bool any_valid = false;
+        int64_t data_bytes = 0, nulls = 0;
+        for (int t = 0; t < n_tables; t++) {
+            const DevColumn &s = tables[t]->cols[c];
+            if (s.validity) any_valid = true;
+            data_bytes += s.data_bytes;
+            nulls += s.null_count;
+        }
+        DevColumn &d = r->cols[c];
+        rc = nqe_column_alloc(ctx, dt, total, any_valid, &d);
+        if (rc != NQE_OK) break;
+        if (dt == NQE_UTF8) {
+            if (data_bytes >= ((int64_t)1 << 31)) { rc = nqe_fail(ctx, NQE_ERR_NOT_SUPPORTED, "concat: Utf8 data beyond 2^31 bytes"); break; }
+            d.data_bytes = data_bytes;
+            rc = nqe_dev_alloc(ctx, (void **)&d.data, (size_t)data_bytes + 64);
+            if (rc != NQE_OK) break;
+        }
+        if (dt == NQE_BOOL) cudaMemsetAsync(d.values, 0, nqe_bitmap_bytes(total), ctx->stream);
+        if (any_valid) cudaMemsetAsync(d.validity, 0, nqe_bitmap_bytes(total), ctx->stream);
+        int64_t at = 0, byte_at = 0;
+        for (int t = 0; t < n_tables; t++) {
+            const DevColumn &s = tables[t]->cols[c];
+            const int64_t n = tables[t]->nrows;
+            const unsigned wgrid = (unsigned)(((n + 31) / 32 + 255) / 256);
+            if (n == 0) continue;
+            if (dt == NQE_BOOL) {
+                bitmap_place_kernel<<<wgrid, 256, 0, ctx->stream>>>((const uint32_t *)s.values, n, (uint32_t *)d.values, at);
+            } else if (dt == NQE_UTF8) {
+                // offsets[0 .. n) of the piece, rebased; the closing offset is written after the last piece
+                utf8_offsets_place_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const int32_t *)s.values, n, (int32_t)byte_at,
+                                                                                                (int32_t *)d.values + at);
+                if (s.data_bytes) cudaMemcpyAsync(d.data + byte_at, s.data, (size_t)s.data_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+            } else {
+                cudaMemcpyAsync((uint64_t *)d.values + at, s.values, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+            }
+            if (any_valid) bitmap_place_kernel<<<wgrid, 256, 0, ctx->stream>>>((const uint32_t *)s.validity, n, (uint32_t *)d.validity, at);
+            ctx->launches++;
+            at += n;
+            byte_at += s.data_bytes;
+        }
+        if (dt == NQE_UTF8) {
+            const int32_t end = (int32_t)data_bytes;
+            cudaMemcpyAsync((int32_t *)d.values + total, &end, 4, cudaMemcpyHostToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream); // `end` lives on this stack frame
+        }
+        d.null_count = nulls;
+        if (any_valid && nulls == 0) { // arrow `concat`: no nulls => no bitmap
+            nqe_dev_free(ctx, d.validity);
+            d.validity = nullptr;
+        }
+    }
+    if (rc == NQE_OK && cudaGetLastError() != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "concat failed");
+    if (rc != NQE_OK) {
+        nqe_table_free(r);
+        return rc;
+    }
+    *out = r;
     return NQE_OK;
 }

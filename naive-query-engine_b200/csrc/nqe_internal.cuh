@@ -98,7 +98,10 @@ struct OpTimer {
     explicit OpTimer(nqe_ctx *c) : ctx(c) {
         if (c->timer_depth++ == 0) cudaEventRecord(c->ev0, c->stream);
     }
-    bool marked = false;
+    bool marked = false, stopped = false;
+    ~OpTimer() { // an early return (NQE_CUDA / NQE_TRY) must not leave the context's timer nesting depth raised
+        if (!stopped) --ctx->timer_depth;
+    }
     // end of the timed kernels, recorded without blocking: a caller that synchronises the stream anyway
     // (to read back a row count) marks first, so that stop() finds the event complete
     void mark_end() {
@@ -108,6 +111,8 @@ struct OpTimer {
         }
     }
     void stop() {
+        if (stopped) return;
+        stopped = true;
         if (--ctx->timer_depth > 0) return;
         if (!marked) cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);

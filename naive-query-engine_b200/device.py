@@ -44,6 +44,11 @@ class Context:
             cls._default = Context(0)
         return cls._default
 
+    @classmethod
+    def set_default(cls, ctx: "Context") -> None:
+        """The context host-side plans (`plan.execute()` over MemTables) run on: one process per GPU sets its own."""
+        cls._default = ctx
+
     def check(self, rc: int):
         if rc != 0:
             raise NqeError(rc, self.lib.nqe_last_error(self.h).decode())
@@ -196,6 +201,15 @@ class DeviceTable:
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.nqe_table_slice(self.ctx.h, self.h, offset, length, C.byref(h)))
         return DeviceTable(self.ctx, h, self.names)
+
+    @classmethod
+    def concat(cls, tables: Sequence["DeviceTable"]) -> "DeviceTable":
+        """concat_batches (hash_join.rs:258-273) on the device: the rows of `tables` in order, as one new table."""
+        ctx = tables[0].ctx
+        arr = (C.c_void_p * len(tables))(*[t.h for t in tables])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_table_concat(ctx.h, arr, len(tables), C.byref(h)))
+        return cls(ctx, h, list(tables[0].names))
 
     def free(self):
         if self.h:

@@ -1,5 +1,18 @@
-"""Multi-GPU plan for hash-join + group-by: one process per GPU,
+"""Multi-GPU plans for hash-join and group-by: one process per GPU,
 `torch.distributed` for the plumbing.
+
+Three operators, each with the exchange SURVEY.md 8(e) names for it:
+
+    distributed_group_by     local pre-aggregate -> partial states exchanged by group-key radix -> merge
+                             (plan (ii) of 8e: G x 40 bytes on the wire instead of N x 16)
+    distributed_hash_join    `shuffle`: both sides exchanged by join-key radix, local join of what arrives
+                             `broadcast`: the build side all-gathered, every rank joins its own probe rows
+                             (output = concatenation in rank order = the reference's probe-row-major order)
+    join + group-by          `shuffled_join_group_by` (both tables shuffled by join key, below) or
+                             `broadcast_join_group_by` (build side all-gathered -- 160 MB for configs[4] -- the probe
+                             rows never move, only partial states are exchanged; the default for small build sides)
+
+The shuffle in detail:
 
     rank r owns a row range of L (build) and R (probe)
     1+2. radix partition fused with the exchange (`exchange_peer`): every rank counts its rows per
@@ -56,6 +69,14 @@ class Engine:
         """group by key over partial states -> [key, count, sum, min, max] (one row per key)"""
         raise NotImplementedError
 
+    def partial_aggregate(self, cols: Sequence):
+        """group by cols[0] over (k i64, v f64-bits) -> [key, count, sum f64-bits, min f64-bits, max f64-bits]"""
+        raise NotImplementedError
+
+    def hash_join(self, lcols: Sequence, rcols: Sequence):
+        """inner join on lcols[0] = rcols[0] (Int64 keys) -> columns of L then columns of R, probe-row-major"""
+        raise NotImplementedError
+
 
 def exchange(dist, torch, engine: Engine, cols: Sequence, key: int, world: int):
     """Steps 1-2 for one table.  Returns (received columns, rows sent to other ranks)."""
@@ -102,7 +123,96 @@ def exchange_peer(dist, torch, engine: Engine, cols: Sequence, key: int, world: 
     return [xbuf.local(c)[:total] for c in range(len(cols))], sum(counts) - counts[rank]
 
 
-def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int, xbufs=None):
+class Phases:
+    """Per-phase device times of one plan execution: `mark(name)` closes the phase that started at the previous mark.
+    Events are recorded on the current stream of `torch`; `ms()` synchronises and returns {phase: milliseconds}."""
+
+    def __init__(self, torch):
+        self.torch, self.names, self.events = torch, [], []
+        self._rec()
+
+    def _rec(self):
+        cuda = getattr(self.torch, "cuda", None)
+        if cuda is not None and cuda.is_available():
+            e = cuda.Event(enable_timing=True)
+            e.record()
+            self.events.append(e)
+        else:
+            import time
+            self.events.append(time.perf_counter())
+
+    def mark(self, name: str):
+        self.names.append(name)
+        self._rec()
+
+    def ms(self):
+        out = {}
+        for i, n in enumerate(self.names):
+            a, b = self.events[i], self.events[i + 1]
+            if isinstance(a, float):
+                out[n] = out.get(n, 0.0) + (b - a) * 1e3
+            else:
+                b.synchronize()
+                out[n] = out.get(n, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def all_gather_rows(dist, torch, cols: Sequence, world: int):
+    """All ranks' rows of `cols` (equal-dtype 1-D tensors) in rank order, with ONE collective per call for the sizes
+    and one for the data: the columns travel packed as a (rows, n_cols) matrix, padded to the largest rank."""
+    n = int(cols[0].numel())
+    sizes = torch.tensor([n], dtype=torch.int64, device=cols[0].device)
+    all_sizes = torch.empty(world, dtype=torch.int64, device=cols[0].device)
+    dist.all_gather_into_tensor(all_sizes, sizes)
+    nl = [int(x) for x in all_sizes.tolist()]
+    nmax = max(max(nl), 1)
+    packed = torch.zeros((nmax, len(cols)), dtype=cols[0].dtype, device=cols[0].device)
+    packed[:n] = torch.stack(list(cols), dim=1)
+    out = torch.empty((world * nmax, len(cols)), dtype=cols[0].dtype, device=cols[0].device)
+    dist.all_gather_into_tensor(out, packed)
+    if all(x == nmax for x in nl):
+        rows = out
+    else:
+        rows = torch.cat([out[r * nmax:r * nmax + nl[r]] for r in range(world)])
+    return [rows[:, c].contiguous() for c in range(len(cols))], nl
+
+
+def exchange_partials(dist, torch, engine: Engine, partial: Sequence, world: int):
+    """Partial aggregate states [key, count, sum, min, max] -> every rank receives the states of the groups it owns
+    (owner = mix64(key) % world): one radix partition of the (small) partial table, one count exchange, ONE
+    all-to-all of 40-byte records.  Returns (received columns, rows sent to other ranks)."""
+    part, counts = engine.partition(partial, 0, world)
+    rank = dist.get_rank()
+    dev = part[0].device
+    send = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    send_l, recv_l = [int(x) for x in counts], [int(x) for x in recv.tolist()]
+    rows = torch.stack([c if c.dtype == torch.int64 else c.view(torch.int64) for c in part], dim=1).contiguous()
+    got = torch.empty((sum(recv_l), len(part)), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(got, rows, output_split_sizes=recv_l, input_split_sizes=send_l)
+    return [got[:, c].contiguous() for c in range(len(part))], sum(send_l) - send_l[rank]
+
+
+def merge_exchanged_partials(dist, torch, engine: Engine, partial: Sequence, world: int, gather: bool = True, phases=None):
+    """Step 4 of every aggregate plan: partial states -> final groups.  The states are exchanged by group-key radix
+    and merged by their owners; gather=True then all-gathers the owners' slices so that every rank returns the whole
+    result [key, count, sum, min, max], else every rank returns the groups it owns."""
+    recv, sent = exchange_partials(dist, torch, engine, partial, world)
+    if phases is not None:
+        phases.mark("partial_exchange")
+    merged = engine.merge_partials(recv)
+    if phases is not None:
+        phases.mark("merge")
+    if gather:
+        merged, _ = all_gather_rows(dist, torch, merged, world)
+        if phases is not None:
+            phases.mark("result_gather")
+    return merged, sent
+
+
+def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int, xbufs=None,
+                           phases=None):
     """Steps 1-4.  Every rank returns the full merged result
     [key, count, sum, min, max] (tensors) and the number of rows it sent over the wire.
     xbufs = (build-side, probe-side) exchange buffers: rows travel through peer memory; None: NCCL all-to-all."""
@@ -112,22 +222,73 @@ def shuffled_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: 
     else:
         l_recv, s1 = exchange(dist, torch, engine, lcols, 0, world)
         r_recv, s2 = exchange(dist, torch, engine, rcols, 0, world)
+    if phases is not None:
+        phases.mark("row_exchange")
     partial = engine.join_partial_aggregate(l_recv, r_recv)
-    g = int(partial[0].numel())
-    sizes = torch.tensor([g], dtype=torch.int64, device=partial[0].device)
-    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    gl = [int(x.item()) for x in all_sizes]
-    gmax = max(max(gl), 1)
-    gathered = []
-    for c in partial:
-        src = torch.zeros(gmax, dtype=c.dtype, device=c.device)
-        src[:g] = c
-        bufs = [torch.empty_like(src) for _ in range(world)]
-        dist.all_gather(bufs, src)
-        gathered.append(torch.cat([bufs[r][:gl[r]] for r in range(world)]))
-    merged = engine.merge_partials(gathered)
+    if phases is not None:
+        phases.mark("local_join_aggregate")
+    merged, _ = merge_exchanged_partials(dist, torch, engine, partial, world, True, phases)
     return merged, s1 + s2
+
+
+def broadcast_join_group_by(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int, phases=None):
+    """Join + group-by WITHOUT moving the probe side: the build side (small: 160 MB for configs[4]) is all-gathered,
+    every rank runs the fused join -> partial aggregate over its own probe rows against the whole build table, and only
+    partial states (G x 40 bytes) are exchanged and merged.  Every rank returns ([key, count, sum, min, max], rows
+    received over the wire)."""
+    rank = dist.get_rank()
+    l_all, nl = all_gather_rows(dist, torch, lcols, world)
+    if phases is not None:
+        phases.mark("build_all_gather")
+    partial = engine.join_partial_aggregate(l_all, rcols)
+    if phases is not None:
+        phases.mark("local_join_aggregate")
+    merged, _ = merge_exchanged_partials(dist, torch, engine, partial, world, True, phases)
+    return merged, sum(nl) - nl[rank]
+
+
+def distributed_group_by(dist, torch, engine: Engine, cols: Sequence, world: int, gather: bool = True, phases=None):
+    """`select count(v), sum(v), avg(v), min(v), max(v) from t group by k` over row-sharded t(k, v): local
+    pre-aggregate -> partial states exchanged by group-key radix -> merge (plan (ii) of SURVEY.md 8e; avg = sum / count).
+    -> ([key, count, sum, min, max], partial rows sent to other ranks)."""
+    partial = engine.partial_aggregate(cols)
+    if phases is not None:
+        phases.mark("local_aggregate")
+    return merge_exchanged_partials(dist, torch, engine, partial, world, gather, phases)
+
+
+def distributed_hash_join(dist, torch, engine: Engine, lcols: Sequence, rcols: Sequence, world: int, plan: str = "broadcast",
+                          xbufs=None, phases=None):
+    """`select * from L join R on L.c0 = R.c0` over row-sharded tables; every rank keeps its slice of the joined rows
+    (columns of L then columns of R, nothing is gathered).
+      broadcast: L all-gathered, local join with this rank's R rows -- the concatenation of the ranks' outputs in rank
+                 order is exactly the reference's probe-row-major order;
+      shuffle:   both sides exchanged by join-key radix (through `xbufs` peer memory if given, else NCCL all-to-all),
+                 local join of what arrives -- same multiset of rows, order by (key owner, arrival).
+    -> (joined columns, rows received or sent over the wire)."""
+    rank = dist.get_rank()
+    if plan == "broadcast":
+        l_all, nl = all_gather_rows(dist, torch, lcols, world)
+        if phases is not None:
+            phases.mark("build_all_gather")
+        out = engine.hash_join(l_all, rcols)
+        wire = sum(nl) - nl[rank]
+    elif plan == "shuffle":
+        if xbufs is not None:
+            l_recv, s1 = exchange_peer(dist, torch, engine, lcols, 0, world, xbufs[0])
+            r_recv, s2 = exchange_peer(dist, torch, engine, rcols, 0, world, xbufs[1])
+        else:
+            l_recv, s1 = exchange(dist, torch, engine, lcols, 0, world)
+            r_recv, s2 = exchange(dist, torch, engine, rcols, 0, world)
+        if phases is not None:
+            phases.mark("row_exchange")
+        out = engine.hash_join(l_recv, r_recv)
+        wire = s1 + s2
+    else:
+        raise ValueError(plan)
+    if phases is not None:
+        phases.mark("local_join")
+    return out, wire
 
 
 class CudaEngine(Engine):
@@ -137,6 +298,13 @@ class CudaEngine(Engine):
 
     def __init__(self, nq, ctx, torch):
         self.nq, self.ctx, self.torch = nq, ctx, torch
+
+    def _bind(self):
+        """Stream contract: every kernel of this engine runs on torch's CURRENT stream (the context is re-bound to it
+        at the start of each call), which is also the stream the symmetric-memory barriers and NCCL collectives of
+        the plans above are queued on -- so a peer's stores, the barrier after them and the kernels that read the
+        receive buffer are ordered by the stream itself, with no host synchronisation in between."""
+        self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream)
 
     def _table(self, names, dtypes, cols):
         return self.nq.DeviceTable.from_device_pointers(self.ctx, names, dtypes, [c.data_ptr() for c in cols],
@@ -153,6 +321,7 @@ class CudaEngine(Engine):
         return v.clone() if copy else v
 
     def partition(self, cols, key, parts):
+        self._bind()
         ctx = self.ctx
         t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
         h = C.c_void_p()
@@ -167,6 +336,7 @@ class CudaEngine(Engine):
         return res, [int(x) for x in counts]
 
     def partition_counts(self, cols, key, parts):
+        self._bind()
         ctx = self.ctx
         t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
         counts = (C.c_int64 * parts)()
@@ -195,6 +365,7 @@ class CudaEngine(Engine):
         return self._SymmExchange(self.torch, capacity_rows, n_cols, group)
 
     def scatter_to_peers(self, cols, key, parts, xbuf, offsets):
+        self._bind()
         ctx = self.ctx
         t = self._table([f"c{i}" for i in range(len(cols))], [self.I64] * len(cols), cols)
         dst = (C.c_void_p * (len(cols) * parts))(*[xbuf.ptrs[c][p] for c in range(len(cols)) for p in range(parts)])
@@ -203,11 +374,13 @@ class CudaEngine(Engine):
         t.free()
 
     def join_partial_aggregate(self, lcols, rcols):
+        self._bind()
         ctx, nq = self.ctx, self.nq
         L = self._table(["k", "a"], [self.I64, self.I64], lcols)
         R = self._table(["fk", "b"], [self.I64, self.F64], rcols)
-        # join output schema: k, a, fk, b -> count(b), sum(b), min(b), max(b), min(a) group by a
-        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 3), (1, 3), (3, 3), (4, 3), (3, 1)]])
+        # join output schema: k, a, fk, b -> count(b), sum(b), min(b), max(b), key group by a  (op 5 = NQE_AGG_GROUP_KEY:
+        # the reference's aggregate emits no key column; the merge needs it)
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 3), (1, 3), (3, 3), (4, 3), (5, 0)]])
         h = C.c_void_p()
         ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, L.h, R.h, 0, 0, 1, aggs, 5, C.byref(h)))
         part = nq.DeviceTable(ctx, h, ["count", "sum", "min", "max", "key"])
@@ -215,16 +388,16 @@ class CudaEngine(Engine):
         cols = [self._column(part, i, g) for i in range(5)]
         self.torch.cuda.current_stream().synchronize()
         part.free(); L.free(); R.free()
-        key = cols[4].view(self.torch.float64).to(self.torch.int64)  # min(a) is a Float64 (aggregates are f64)
-        return [key, cols[0], cols[1], cols[2], cols[3]]
+        return [cols[4], cols[0], cols[1], cols[2], cols[3]]
 
     def merge_partials(self, cols):
+        self._bind()
         ctx, nq, torch = self.ctx, self.nq, self.torch
         key, cnt, s, mn, mx = cols
         cnt_f = cnt.to(torch.float64).view(torch.int64)  # counts are summed as f64 (exact below 2^53)
         M = self._table(["key", "cnt", "sum", "min", "max"], [self.I64, self.F64, self.F64, self.F64, self.F64],
                         [key, cnt_f, s, mn, mx])
-        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(3, 0), (1, 1), (1, 2), (3, 3), (4, 4)]])
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(5, 0), (1, 1), (1, 2), (3, 3), (4, 4)]])
         ke, keep = nq.ColumnExpr.try_create(None, 0).to_expr(M.names)
         h = C.c_void_p()
         ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, M.h, C.pointer(ke), aggs, 5, C.byref(h)))
@@ -233,6 +406,34 @@ class CudaEngine(Engine):
         res = [self._column(out, i, g) for i in range(5)]
         torch.cuda.current_stream().synchronize()
         out.free(); M.free()
-        res[0] = res[0].view(torch.float64).to(torch.int64)
         res[1] = res[1].view(torch.float64).to(torch.int64)
+        return res
+
+    def partial_aggregate(self, cols):
+        self._bind()
+        ctx, nq, torch = self.ctx, self.nq, self.torch
+        T = self._table(["k", "v"], [self.I64, self.F64], cols)
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(op, c) for op, c in [(0, 1), (1, 1), (3, 1), (4, 1), (5, 0)]])
+        ke, keep = nq.ColumnExpr.try_create(None, 0).to_expr(T.names)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_hash_aggregate(ctx.h, T.h, C.pointer(ke), aggs, 5, C.byref(h)))
+        part = nq.DeviceTable(ctx, h, ["count", "sum", "min", "max", "key"])
+        g = part.num_rows
+        res = [self._column(part, i, g) for i in range(5)]
+        torch.cuda.current_stream().synchronize()
+        part.free(); T.free()
+        return [res[4], res[0], res[1], res[2], res[3]]
+
+    def hash_join(self, lcols, rcols):
+        self._bind()
+        ctx, nq, torch = self.ctx, self.nq, self.torch
+        L = self._table([f"l{i}" for i in range(len(lcols))], [self.I64] * len(lcols), lcols)
+        R = self._table([f"r{i}" for i in range(len(rcols))], [self.I64] * len(rcols), rcols)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nqe_hash_join(ctx.h, L.h, R.h, 0, 0, C.byref(h)))
+        out = nq.DeviceTable(ctx, h, L.names + R.names)
+        n = out.num_rows
+        res = [self._column(out, i, n) for i in range(len(lcols) + len(rcols))]
+        torch.cuda.current_stream().synchronize()
+        out.free(); L.free(); R.free()
         return res

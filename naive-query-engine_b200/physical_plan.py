@@ -348,11 +348,17 @@ class MemTable:
         """Upload once and keep the table resident in HBM (the GPU analogue of
         the Arc-cloned batches in memory.rs:31-41)."""
         if self._device is None:
-            if len(self.batches) == 1:
-                src = self.batches[0]
+            if len(self.batches) <= 1:
+                src = self.batches[0] if self.batches else pa.Table.from_batches([], schema=self._schema)
+                self._device = DeviceTable.from_arrow(src, ctx)
             else:
-                src = pa.Table.from_batches(self.batches, schema=self._schema)  # concat_batches, hash_join.rs:258-273
-            self._device = DeviceTable.from_arrow(src, ctx)
+                # every operator of the reference that sees several batches concatenates them first (concat_batches,
+                # hash_join.rs:131-132,258-273; aggregate/mod.rs:143-144) or treats them one by one with the same
+                # result as on the concatenation: each batch is uploaded as it is and concatenated on the device
+                parts = [DeviceTable.from_arrow(b, ctx) for b in self.batches]
+                self._device = DeviceTable.concat(parts)
+                for t in parts:
+                    t.free()
         return self._device
 
 

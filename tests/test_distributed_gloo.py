@@ -1,9 +1,10 @@
-"""world_size-2 gloo test of the multi-GPU join + group-by plan (distributed.py) on CPU.
+"""world_size-2 gloo tests of the multi-GPU plans (distributed.py) on CPU: shuffled and broadcast join + group-by,
+the stand-alone distributed group-by and the stand-alone distributed hash join (both plans).
 
-The exchange orchestration (radix partition -> all-to-all with uneven splits ->
-local join + partial aggregate -> all-gather + merge) runs for real over gloo; the
+The exchange orchestration (radix partition -> all-to-all with uneven splits / all-gather of the build side ->
+local operator -> partial states exchanged by group-key radix -> merge -> gather) runs for real over gloo; the
 per-rank operator calls are answered by the CPU oracle (test infrastructure) instead of
-the CUDA kernels, and the merged result must equal the single-process oracle's."""
+the CUDA kernels, and the result must equal the single-process oracle's."""
 import os
 import sys
 
@@ -104,6 +105,23 @@ class OracleEngine:
                 torch.from_numpy(m.cols[4].values.view(np.int64).copy())]
 
 
+    def partial_aggregate(self, cols):
+        O = self.O
+        b = O.Batch(["k", "v"], [O.Col("i64", cols[0].numpy()), O.Col("f64", cols[1].numpy().view(np.float64))])
+        a = O.aggregate(b, ("col", 0), [("count", 1), ("sum", 1), ("min", 1), ("max", 1), ("min", 0)])
+        return [torch.from_numpy(a.cols[4].values.astype(np.int64)), torch.from_numpy(a.cols[0].values.astype(np.int64)),
+                torch.from_numpy(a.cols[1].values.view(np.int64).copy()),
+                torch.from_numpy(a.cols[2].values.view(np.int64).copy()),
+                torch.from_numpy(a.cols[3].values.view(np.int64).copy())]
+
+    def hash_join(self, lcols, rcols):
+        O = self.O
+        L = O.Batch([f"l{i}" for i in range(len(lcols))], [O.Col("i64", c.numpy()) for c in lcols])
+        R = O.Batch([f"r{i}" for i in range(len(rcols))], [O.Col("i64", c.numpy()) for c in rcols])
+        j = O.hash_join_c(L, R, 0, 0)
+        return [torch.from_numpy(np.ascontiguousarray(c.values.astype(np.int64))) for c in j.cols]
+
+
 N_BUILD, N_PROBE, GROUPS = 4000, 30000, 97
 
 
@@ -116,7 +134,7 @@ def _tables(start_l, n_l, start_r, n_r):
     return lk, la, fk, rb
 
 
-def _worker(rank, world, port, out_path, peer_dir=None):
+def _worker(rank, world, port, out_path, peer_dir=None, plan="shuffle"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -130,7 +148,12 @@ def _worker(rank, world, port, out_path, peer_dir=None):
     xbufs = None
     if peer_dir is not None:  # rows travel through "peer memory" (files mapped by every rank)
         xbufs = (engine.alloc_exchange(N_BUILD, 2, None, peer_dir, "l"), engine.alloc_exchange(N_PROBE, 2, None, peer_dir, "r"))
-    merged, sent = D.shuffled_join_group_by(dist, torch, engine, lcols, rcols, world, xbufs)
+    if plan == "broadcast":
+        ph = D.Phases(torch)
+        merged, sent = D.broadcast_join_group_by(dist, torch, engine, lcols, rcols, world, phases=ph)
+        assert set(ph.ms()) == {"build_all_gather", "local_join_aggregate", "partial_exchange", "merge", "result_gather"}
+    else:
+        merged, sent = D.shuffled_join_group_by(dist, torch, engine, lcols, rcols, world, xbufs)
     if rank == 0:
         np.savez(out_path, key=merged[0].numpy(), count=merged[1].numpy(), sum=merged[2].numpy().view(np.float64),
                  min=merged[3].numpy().view(np.float64), max=merged[4].numpy().view(np.float64), sent=sent)
@@ -147,13 +170,14 @@ def test_peer_offsets():
     assert D.peer_offsets(m, 2) == ([5, 8, 5], 9, 12)
 
 
-@pytest.mark.parametrize("peer", [False, True])
-def test_shuffled_join_group_by_world2(tmp_path, peer):
+@pytest.mark.parametrize("plan", ["shuffle", "shuffle-peer", "broadcast"])
+def test_join_group_by_world2(tmp_path, plan):
     from oracle import oracle as O
     world = 2
+    peer = plan == "shuffle-peer"
     out = str(tmp_path / "merged.npz")
-    port = 29500 + (os.getpid() % 2000) + (1 if peer else 0)
-    mp.spawn(_worker, args=(world, port, out, str(tmp_path) if peer else None), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + ["shuffle", "shuffle-peer", "broadcast"].index(plan)
+    mp.spawn(_worker, args=(world, port, out, str(tmp_path) if peer else None, plan.split("-")[0]), nprocs=world, join=True)
     got = np.load(out)
     lk, la, fk, rb = _tables(0, N_BUILD, 0, N_PROBE)
     L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", la)])
@@ -167,3 +191,63 @@ def test_shuffled_join_group_by_world2(tmp_path, peer):
     assert np.array_equal(want.cols[3].values[wo], got["min"][go])
     assert np.array_equal(want.cols[4].values[wo], got["max"][go])
     assert int(got["sent"]) > 0  # rows really crossed ranks
+
+
+def _worker_ops(rank, world, port, out_dir):
+    """stand-alone distributed group-by and hash join (both plans)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from importlib import import_module
+    D = import_module("naive-query-engine_b200.distributed")
+    nl, nr = N_BUILD // world, N_PROBE // world
+    lk, la, fk, rb = _tables(rank * nl, nl, rank * nr, nr)
+    engine = OracleEngine()
+    # group by fk % 301 over the probe table
+    gk = torch.from_numpy((fk % 301).astype(np.int64))
+    gv = torch.from_numpy(rb.view(np.int64).copy())
+    full, sent_g = D.distributed_group_by(dist, torch, engine, [gk, gv], world, gather=True)
+    own, _ = D.distributed_group_by(dist, torch, engine, [gk, gv], world, gather=False)
+    owner = (_mix64(own[0].numpy().view(np.uint64)) % np.uint64(world)).astype(np.int64)
+    assert np.all(owner == rank)  # without the gather every rank keeps exactly the groups it owns
+    lcols = [torch.from_numpy(lk), torch.from_numpy(la)]
+    rcols = [torch.from_numpy(fk), torch.from_numpy(rb.view(np.int64).copy())]
+    jb, wire_b = D.distributed_hash_join(dist, torch, engine, lcols, rcols, world, plan="broadcast")
+    js, wire_s = D.distributed_hash_join(dist, torch, engine, lcols, rcols, world, plan="shuffle")
+    np.savez(os.path.join(out_dir, f"ops_{rank}.npz"), gb=np.stack([c.numpy() for c in full]), sent_g=sent_g,
+             jb=np.stack([c.numpy() for c in jb]), js=np.stack([c.numpy() for c in js]), wire_b=wire_b, wire_s=wire_s)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_group_by_and_hash_join_world2(tmp_path):
+    from oracle import oracle as O
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_worker_ops, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(str(tmp_path / f"ops_{r}.npz")) for r in range(world)]
+    lk, la, fk, rb = _tables(0, N_BUILD, 0, N_PROBE)
+    # ---- group-by: every rank holds the whole result
+    T = O.Batch(["k", "v"], [O.Col("i64", (fk % 301).astype(np.int64)), O.Col("f64", rb)])
+    want = O.aggregate(T, ("col", 0), [("min", 0), ("count", 1), ("sum", 1), ("min", 1), ("max", 1)])
+    wk = want.cols[0].values.astype(np.int64)
+    wo = np.argsort(wk)
+    for r in range(world):
+        gb = got[r]["gb"]
+        go = np.argsort(gb[0])
+        assert np.array_equal(wk[wo], gb[0][go]) and np.array_equal(want.cols[1].values[wo].astype(np.int64), gb[1][go])
+        assert np.allclose(want.cols[2].values[wo], gb[2][go].view(np.float64), rtol=1e-9, atol=0)
+        assert np.array_equal(want.cols[3].values[wo], gb[3][go].view(np.float64))
+        assert np.array_equal(want.cols[4].values[wo], gb[4][go].view(np.float64))
+    assert sum(int(g["sent_g"]) for g in got) > 0
+    # ---- hash join
+    L = O.Batch(["k", "a"], [O.Col("i64", lk), O.Col("i64", la)])
+    R = O.Batch(["fk", "b"], [O.Col("i64", fk), O.Col("i64", rb.view(np.int64).copy())])
+    wj = np.stack([c.values.astype(np.int64) for c in O.hash_join_c(L, R, 0, 0).cols])
+    # broadcast plan: concatenation in rank order IS the reference's probe-row-major order
+    assert np.array_equal(np.concatenate([g["jb"] for g in got], axis=1), wj)
+    # shuffle plan: same multiset of rows
+    js = np.concatenate([g["js"] for g in got], axis=1)
+    assert js.shape == wj.shape
+    assert np.array_equal(js[:, np.lexsort(js[::-1])], wj[:, np.lexsort(wj[::-1])])
+    assert all(int(g["wire_b"]) > 0 and int(g["wire_s"]) > 0 for g in got)

@@ -84,6 +84,123 @@ def test_golden_abs_sin():  # unary.rs:123-170
         assert abs(got - want) <= 4 * math.ulp(want)
 
 
+def test_cos_and_tan_is_cos():  # unary.rs:92-96: `Tan` evaluates cos
+    t1 = numeric_only(golden_table("t1"))
+    out = G.gpu_projection(t1, [("un", "cos", ("col", 2)), ("un", "tan", ("col", 2))])
+    want = O.projection(t1, [("un", "cos", ("col", 2)), ("un", "tan", ("col", 2))])
+    assert want.cols[0].to_pylist() == want.cols[1].to_pylist() == [math.cos(x) for x in t1.cols[2].values]
+    for c in (0, 1):
+        for got, w in zip(out.cols[c].to_pylist(), want.cols[c].to_pylist()):
+            assert abs(got - w) <= 4 * math.ulp(w)
+    assert out.cols[0].to_pylist() == out.cols[1].to_pylist()  # bit-identical to each other: it IS cos
+    # a few hundred random arguments, including large ones and NULLs
+    rng = np.random.default_rng(3)
+    b = O.Batch(["x"], [O.Col("f64", np.concatenate([rng.normal(0, 10, 300), rng.normal(0, 1e6, 100)]),
+                               (rng.random(400) > 0.1).astype(np.uint8))])
+    g = G.gpu_projection(b, [("un", "tan", ("col", 0))])
+    w = O.projection(b, [("un", "tan", ("col", 0))])
+    for got, want_ in zip(g.cols[0].to_pylist(), w.cols[0].to_pylist()):
+        assert (got is None) == (want_ is None)
+        if got is not None:
+            assert abs(got - want_) <= 4 * math.ulp(want_)
+
+
+def test_cast_panics_like_the_reference():  # cast.rs:45-87: every arm is todo!()
+    import pyarrow as pa
+    nq = G.nq
+    b = O.Batch(["a"], [O.col("i64", [1, 2, 3])])
+    cast = nq.PhysicalCastExpr.create(nq.ColumnExpr.try_create(None, 0), pa.float64())
+    with pytest.raises(nq.NqeError) as e:
+        cast.evaluate(G.to_arrow(b))
+    assert e.value.kind == "Panic" and e.value.message == "not yet implemented"
+    plan = nq.ProjectionPlan.create(G.scan(b), pa.schema([("a", pa.float64())]), [cast])
+    with pytest.raises(nq.NqeError) as e:
+        plan.execute()
+    assert e.value.kind == "Panic"
+    sel = nq.SelectionPlan.create(G.scan(b), nq.PhysicalBinaryExpr.create(cast, "Gt", nq.PhysicalLiteralExpr.create(nq.ScalarValue.Float64(1.0))))
+    with pytest.raises(nq.NqeError) as e:
+        sel.execute()
+    assert e.value.kind == "Panic"
+
+
+def test_utf8_comparisons_in_expressions_are_not_implemented():
+    """binary.rs:127-132 compares any arrow-comparable dtype, Utf8 included; the CUDA path does not:
+    this pins the error a caller sees instead of a silent wrong answer."""
+    import pyarrow as pa
+    nq = G.nq
+    rb = pa.RecordBatch.from_arrays([pa.array(["a", "b", "a"]), pa.array(["a", "a", "c"]), pa.array([1, 2, 3])], names=["s", "t", "x"])
+    scan = nq.ScanPlan.create(nq.MemTable.try_create(rb.schema, [rb]), None)
+    pred = nq.PhysicalBinaryExpr.create(nq.ColumnExpr.try_create(None, 0), "Eq", nq.ColumnExpr.try_create(None, 1))
+    with pytest.raises(nq.NqeError) as e:
+        nq.SelectionPlan.create(scan, pred).execute()
+    assert e.value.kind == "NotImplemented"
+    with pytest.raises(nq.NqeError) as e:
+        nq.PhysicalLiteralExpr.create(nq.ScalarValue.Utf8("a")).evaluate(rb)
+    assert e.value.kind == "NotImplemented"
+
+
+def _three_batches(rng, n, with_strings):
+    """three ragged batches (17, n, 1 rows; offsets not multiples of 8 or 32) with NULLs, a Boolean and a Utf8 column,
+    as oracle batches (raw values under NULL slots are part of the data: the join reads them, hash_join.rs:67)"""
+    out = []
+    for m in [17, n, 1]:
+        cols = [O.Col("i64", rng.integers(0, 40, m).astype(np.int64), (rng.random(m) >= 0.1).astype(np.uint8)),
+                O.Col("f64", np.round(rng.normal(0, 10, m), 3), (rng.random(m) >= 0.2).astype(np.uint8)),
+                O.Col("bool", (rng.random(m) < 0.5).astype(np.uint8), (rng.random(m) >= 0.15).astype(np.uint8))]
+        names = ["k", "v", "f"]
+        if with_strings:
+            cols.append(O.col("utf8", [None if rng.random() < 0.1 else "s" * int(rng.integers(0, 5)) + str(int(rng.integers(0, 9))) for _ in range(m)]))
+            names.append("s")
+        out.append(O.Batch(names, cols))
+    return out
+
+
+def _concat_oracle(batches):
+    cols = []
+    for i, c0 in enumerate(batches[0].cols):
+        if c0.dtype == "utf8":
+            vals = [v for b in batches for v in b.cols[i].to_pylist()]
+            cols.append(O.col("utf8", vals))
+        else:
+            cols.append(O.Col(c0.dtype, np.concatenate([b.cols[i].values for b in batches]),
+                              np.concatenate([b.cols[i].valid if b.cols[i].valid is not None else np.ones(b.num_rows, np.uint8) for b in batches])))
+    return O.Batch(batches[0].names, cols)
+
+
+@pytest.mark.parametrize("n", [0, 100, 5003])
+def test_device_concat_equals_arrow_concat(n):  # concat_batches, hash_join.rs:258-273
+    import pyarrow as pa
+    nq = G.nq
+    rng = np.random.default_rng(n)
+    batches = [G.to_arrow(b) for b in _three_batches(rng, n, True)]
+    parts = [nq.DeviceTable.from_arrow(b) for b in batches]
+    got = nq.DeviceTable.concat(parts).to_arrow()
+    want = pa.Table.from_batches(batches).combine_chunks().to_batches()[0]
+    assert got.num_rows == want.num_rows
+    for i in range(want.num_columns):
+        assert got.column(i).to_pylist() == want.column(i).to_pylist(), want.schema.names[i]
+        assert got.column(i).null_count == want.column(i).null_count
+
+
+def test_multi_batch_inputs_through_join_and_group_by():
+    """A 3-batch MemTable on the join's build side (hash_join.rs:131-132: concat_batches), on its probe side
+    (:168-254: one output batch per probe batch, i.e. the concatenation) and under a GROUP BY (aggregate/mod.rs:143-144)."""
+    import pyarrow as pa
+    nq = G.nq
+    rng = np.random.default_rng(8)
+    ol, orr = _three_batches(rng, 300, False), _three_batches(rng, 2000, False)
+    lb, rb = [G.to_arrow(b) for b in ol], [G.to_arrow(b) for b in orr]
+    lsrc, rsrc = nq.MemTable.try_create(lb[0].schema, lb), nq.MemTable.try_create(rb[0].schema, rb)
+    L, R = _concat_oracle(ol), _concat_oracle(orr)
+    join = nq.HashJoin.create(nq.ScanPlan.create(lsrc, None), nq.ScanPlan.create(rsrc, None), [("k", "k")], "Inner")
+    same(G.from_arrow(join.execute()[0]), O.hash_join_c(L, R, 0, 0))
+    aggs = [("count", 1), ("sum", 1), ("avg", 1), ("min", 1), ("max", 1), ("min", 0)]
+    plan = nq.PhysicalAggregatePlan.create([nq.ColumnExpr.try_create(None, 0)],
+                                           [G._AGG[op].create(nq.ColumnExpr.try_create(None, ci)) for op, ci in aggs],
+                                           nq.ScanPlan.create(rsrc, None))
+    same(G.from_arrow(plan.execute()[0]), O.aggregate(R, ("col", 0), aggs), rel=SUM_REL, ordered=False, sort_cols=[5])
+
+
 def test_golden_readme_groupby():  # README.md:105-111
     t1 = numeric_only(golden_table("t1"))
     out = G.gpu_aggregate(t1, ("bin", "Modulos", ("col", 0), lit(3)),
@@ -654,6 +771,55 @@ def test_group_by_one_value_column(n, groups, vtype):
     assert np.all(np.abs(gsum[fin] - wsum[fin]) <= SUM_REL * np.maximum(scale[fin], 1.0))
     gavg = got[2][gi][uniq]
     assert np.all(np.abs(gavg[fin] - (wsum / cnt[wi][uniq])[fin]) <= SUM_REL * np.maximum(scale[fin] / cnt[wi][uniq][fin], 1.0))
+
+
+@pytest.mark.parametrize("n,groups", [(1000, 7), (300_000, 5000), (5_000_000, 40_000)])
+def test_group_key_extension(n, groups):
+    """NQE_AGG_GROUP_KEY (op 5, an extension: the reference's aggregate emits no key column, aggregate/mod.rs:117-121)
+    returns the group key next to the aggregates -- on the table path and on the paged shared-memory path, through
+    nqe_hash_aggregate and through the fused nqe_join_aggregate; the key i64::MIN included."""
+    import ctypes as C
+    import pyarrow as pa
+    nq = G.nq
+    rng = np.random.default_rng(n + groups)
+    k = rng.integers(0, groups, n).astype(np.int64) * 104729 - 77
+    k[rng.integers(0, n, 5)] = np.iinfo(np.int64).min
+    v = np.round(rng.normal(0, 100, n), 4)
+    t = nq.DeviceTable.from_arrow(pa.RecordBatch.from_arrays([pa.array(k), pa.array(v)], names=["k", "v"]))
+    ke, keep = nq.ColumnExpr.try_create(None, 0).to_expr(t.names)
+    aggs = (nq._ffi.Agg * 4)(*[nq._ffi.Agg(o, c) for o, c in [(5, 0), (0, 1), (1, 1), (4, 1)]])
+    h = C.c_void_p()
+    t.ctx.check(t.ctx.lib.nqe_hash_aggregate(t.ctx.h, t.h, C.pointer(ke), aggs, 4, C.byref(h)))
+    out = nq.DeviceTable(t.ctx, h, ["key", "count", "sum", "max"]).to_arrow()
+    assert out.schema.field(0).type == pa.int64()
+    uk, inv = np.unique(k, return_inverse=True)
+    o = np.argsort(out.column(0).to_numpy())
+    assert np.array_equal(out.column(0).to_numpy()[o], uk)
+    assert np.array_equal(out.column(1).to_numpy()[o], np.bincount(inv).astype(np.uint64))
+    assert np.allclose(out.column(2).to_numpy()[o], np.bincount(inv, weights=v), rtol=SUM_REL, atol=1e-6)
+    mx = np.full(len(uk), -np.inf)
+    np.maximum.at(mx, inv, v)
+    assert np.array_equal(out.column(3).to_numpy()[o], mx)
+    # fused join -> group-by with the key: L(id, k-of-id) x R(fk = row's id, v)
+    ids = np.arange(len(uk), dtype=np.int64) * 3 + 1
+    L = nq.DeviceTable.from_arrow(pa.RecordBatch.from_arrays([pa.array(ids), pa.array(uk)], names=["id", "g"]))
+    R = nq.DeviceTable.from_arrow(pa.RecordBatch.from_arrays([pa.array(ids[inv]), pa.array(v)], names=["fk", "v"]))
+    aggs = (nq._ffi.Agg * 4)(*[nq._ffi.Agg(o_, c) for o_, c in [(5, 0), (0, 3), (1, 3), (4, 3)]])
+    h = C.c_void_p()
+    t.ctx.check(t.ctx.lib.nqe_join_aggregate(t.ctx.h, L.h, R.h, 0, 0, 1, aggs, 4, C.byref(h)))
+    out2 = nq.DeviceTable(t.ctx, h, ["key", "count", "sum", "max"]).to_arrow()
+    o2 = np.argsort(out2.column(0).to_numpy())
+    assert np.array_equal(out2.column(0).to_numpy()[o2], uk)
+    assert np.array_equal(out2.column(1).to_numpy()[o2], out.column(1).to_numpy()[o])
+    assert np.allclose(out2.column(2).to_numpy()[o2], out.column(2).to_numpy()[o], rtol=SUM_REL, atol=1e-6)
+    assert np.array_equal(out2.column(3).to_numpy()[o2], mx)
+    # the global (no GROUP BY) plan has no key
+    aggs = (nq._ffi.Agg * 2)(nq._ffi.Agg(5, 0), nq._ffi.Agg(0, 1))
+    with pytest.raises(nq.NqeError) as e:
+        t.ctx.check(t.ctx.lib.nqe_hash_aggregate(t.ctx.h, t.h, None, aggs, 2, C.byref(h)))
+    assert e.value.kind == "InvalidArgument"
+    for x in (t, L, R):
+        x.free()
 
 
 def test_group_by_expression_key_and_special_values():
