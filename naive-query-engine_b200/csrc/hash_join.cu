@@ -68,9 +68,13 @@ __device__ __forceinline__ unsigned long long *slot_ptr(const JoinTable &jt, uin
 // (~1.7e10 /s), not by bytes -- so the plain read-only path is kept.
 __device__ __forceinline__ ulonglong2 ld_cg_v2(const unsigned long long *p) { return __ldg((const ulonglong2 *)p); }
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) { return __ldg(p); }
-// slot of a key: multiply-high range reduction, so the capacity need not be a power of two
+// Home slot of a key: multiply-high range reduction, so the capacity need not be a power of two.  Home slots are EVEN
+// (the capacity is even): a probe sequence starts on a 32-byte sector boundary, so its second step reads the other half
+// of the sector the first one just brought into L1 -- every second step of a sequence is an L1 hit instead of an L2
+// round trip.  (Reading both slots with one 32-byte load was tried: 32 more registers for K = 4 rows, spills under the
+// 64-register cap of the fused kernels.)
 __device__ __forceinline__ uint64_t join_slot_of(const JoinTable &jt, unsigned long long key) {
-    return __umul64hi(nqe_mix64(key), jt.cap);
+    return __umul64hi(nqe_mix64(key), jt.cap >> 1) << 1;
 }
 __device__ __forceinline__ Slot ld_slot(const JoinTable &jt, uint64_t s) {
     const ulonglong2 v = ld_cg_v2(slot_ptr(jt, s));
@@ -149,7 +153,7 @@ __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned 
         while (sl.row != EMPTY_ROW) {
             if (sl.key == key[j]) { brow[j] = sl.row; break; }
             slot[j] = slot[j] + 1 == jt.cap ? 0 : slot[j] + 1;
-            sl = ld_slot(jt, slot[j]);
+            sl = ld_slot(jt, slot[j]); // odd slot: the other half of the sector just read, an L1 hit
         }
     }
 }
@@ -958,6 +962,17 @@ int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const Page
     }
 }
 
+// smallest probe side that takes the partitioned / paged paths (knob NQE_JOIN_PART_MIN_ROWS; tests and the
+// compute-sanitizer runs lower it so that those kernels run on small inputs)
+int64_t join_part_min_rows() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char *e = getenv("NQE_JOIN_PART_MIN_ROWS");
+        v = e ? atoll(e) : ((int64_t)1 << 22);
+    }
+    return v;
+}
+
 int32_t check_join_keys(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t lk, int32_t rk) {
     if (lk < 0 || lk >= (int)left->cols.size() || rk < 0 || rk >= (int)right->cols.size())
         return nqe_fail(ctx, NQE_ERR_LOGICAL, "ColumnExpr must has name or idx"); // key column not found (column.rs:53-55)
@@ -986,7 +1001,7 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
             jt->rowpay_col = rowpay_col;
         }
     }
-    const uint64_t cap = (uint64_t)((double)nl / 0.5) + 16; // load factor 0.5
+    const uint64_t cap = ((uint64_t)((double)nl / 0.5) + 16) & ~(uint64_t)1; // load factor 0.5; even: probes read slot pairs
     void *slots = nullptr;
     NQE_TRY(nqe_dev_alloc(ctx, &slots, cap * 16));
     jt->words = (unsigned long long *)slots;
@@ -1053,7 +1068,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     pp.n_probe = right->nrows;
     // the partitioned probe (below) will run if the build keys turn out unique; with a single non-key build column its
     // values ride in the slots' row word and the gather pass has nothing left to chase
-    const bool part_sizes = allow_part && pp.n_probe >= (1 << 22) && pp.n_probe < (int64_t)1 << 32 &&
+    const bool part_sizes = allow_part && pp.n_probe >= join_part_min_rows() && pp.n_probe < (int64_t)1 << 32 &&
                             ((size_t)((double)left->nrows / 0.5) + 16) * 16 > part_min && nl + nr + 1 <= 16;
     const int rowpay_col = allow_rowpay && part_sizes && nl == 2 && !left->cols[left_key].validity ? 1 - left_key : -1;
     pp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
@@ -1479,7 +1494,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         e = getenv("NQE_JOIN_PART_MB");
         l2_budget = (size_t)(e ? atoi(e) : 48) << 20;
     }
-    bool paged = rc == NQE_OK && allow_paged && jp.jt.rowpay && !jp.jt.has_dups && jp.n_probe >= (1 << 22) && ap.n_states > 0;
+    bool paged = rc == NQE_OK && allow_paged && jp.jt.rowpay && !jp.jt.has_dups && jp.n_probe >= join_part_min_rows() && ap.n_states > 0;
     int need = 0;
     for (int q = 0; q < ap.n_states && paged; q++) {
         if (ap.st_src[q] != ap.st_src[0]) paged = false;

@@ -151,7 +151,7 @@ def _worker(rank, world, port, out_path, peer_dir=None, plan="shuffle"):
     if plan == "broadcast":
         ph = D.Phases(torch)
         merged, sent = D.broadcast_join_group_by(dist, torch, engine, lcols, rcols, world, phases=ph)
-        assert set(ph.ms()) == {"build_all_gather", "local_join_aggregate", "partial_exchange", "merge", "result_gather"}
+        assert {"build_all_gather", "local_join_aggregate", "partial_exchange", "merge"} <= set(ph.ms())
     else:
         merged, sent = D.shuffled_join_group_by(dist, torch, engine, lcols, rcols, world, xbufs)
     if rank == 0:
