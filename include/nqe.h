@@ -100,8 +100,10 @@ typedef struct nqe_expr_node {
     int32_t column;  /* NQE_NODE_COLUMN: index into the input table */
     int32_t dtype;   /* NQE_NODE_LITERAL: nqe_dtype of the ScalarValue */
     int32_t is_null; /* NQE_NODE_LITERAL: ScalarValue::X(None) */
-    int32_t reserved;
-    union { int64_t i64; uint64_t u64; double f64; } value; /* BOOL literal: u64 0/1 */
+    int32_t reserved; /* NQE_NODE_LITERAL of dtype NQE_UTF8: byte length of the string */
+    union { int64_t i64; uint64_t u64; double f64; } value; /* BOOL literal: u64 0/1; UTF8 literal: u64 = address of the
+                                                             * (host) bytes, valid during the call.  Utf8 values may only be
+                                                             * compared (Eq .. GtEq, binary.rs:127-132) in nqe_filter_project */
 } nqe_expr_node;
 
 typedef struct nqe_expr {

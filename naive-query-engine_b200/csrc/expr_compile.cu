@@ -149,8 +149,14 @@ int32_t nqe_compile_exprs(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *con
                 if (lt != rt)
                     return nqe_fail(ctx, NQE_ERR_INTERVAL, "Cannot evaluate binary expression %s with types %s and %s",
                                     op_name(s.op), dtype_name(lt), dtype_name(rt));
-                if (lt == NQE_UTF8)
-                    return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 operands in expressions are not implemented on the CUDA path");
+                if (lt == NQE_UTF8) {
+                    // comparisons of Utf8 leaves were rewritten into Boolean columns before this point (utf8.cu)
+                    if (s.op == NQE_OP_AND || s.op == NQE_OP_OR) // binary.rs:30-44: and/or only on Boolean x Boolean
+                        return nqe_fail(ctx, NQE_ERR_INTERVAL, "Cannot evaluate binary expression %s with types %s and %s",
+                                        op_name(s.op), dtype_name(lt), dtype_name(rt));
+                    if (s.op > NQE_OP_GT_EQ) return nqe_fail(ctx, NQE_ERR_PANIC, "not implemented: arithmetic on Utf8"); // binary.rs:46-88 unimplemented!()
+                    return nqe_fail(ctx, NQE_ERR_NOT_IMPLEMENTED, "Utf8 comparison outside a filter/projection expression");
+                }
                 if (lt < NQE_BOOL || lt > NQE_FLOAT64)
                     return nqe_fail(ctx, NQE_ERR_PANIC, "binary expression on Null-typed operands");
                 if (s.op <= NQE_OP_GT_EQ) nd.dtype = NQE_BOOL;

@@ -586,6 +586,8 @@ int32_t nqe_jit_filter_project(nqe_ctx *ctx, const nqe_table *in, const nqe_expr
 
 int32_t nqe_filter_project_strings(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
                                    int32_t n_projs, const int *utf8_src, nqe_table **out);
+int32_t nqe_filter_project_utf8_compares(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                                         int32_t n_projs, nqe_table **out, bool *handled);
 
 static int32_t status_to_error(nqe_ctx *ctx, uint32_t st) {
     if (st & DEV_ERR_DIV0) return nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error");
@@ -617,6 +619,12 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
         projs = pass_exprs.data();
     }
 
+    // comparisons of Utf8 columns / literals (binary.rs:127-132) become Boolean columns of a view of the input (utf8.cu)
+    {
+        bool handled = false;
+        const int32_t urc = nqe_filter_project_utf8_compares(ctx, in, predicate, projs, n_projs, out, &handled);
+        if (handled || urc != NQE_OK) return urc;
+    }
     // bare references to Utf8 columns ride along through a hidden row-id column (utf8.cu)
     {
         int utf8_src[16];

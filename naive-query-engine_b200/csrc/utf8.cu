@@ -356,6 +356,159 @@ int32_t nqe_filter_project_strings(nqe_ctx *ctx, const nqe_table *in, const nqe_
     return NQE_OK;
 }
 
+// ---- Utf8 comparisons inside expressions (binary.rs:127-132: eq_dyn / neq_dyn / lt_dyn / lt_eq_dyn / gt_dyn / gt_eq_dyn work
+// on any arrow-comparable dtype, Utf8 included: bytewise lexicographic order, NULL if either side is NULL) --------------------
+// A Utf8 value only ever comes from a leaf (a column or a literal: the reference has no string-valued function that is
+// not todo!()), so every comparison of two Utf8 leaves is evaluated by one kernel into a Boolean column appended to a view
+// of the input, and the expression is rewritten to reference that column; the numeric machinery then runs unchanged.
+struct Utf8Operand {
+    const int32_t *off;    // column: offsets
+    const uint8_t *data;   // column: bytes / literal: bytes (device)
+    const uint32_t *valid; // column: validity words or nullptr
+    int32_t lit_len;       // literal: byte length
+    int32_t is_lit, lit_null, pad;
+};
+
+__global__ void utf8_compare_kernel(const Utf8Operand a, const Utf8Operand b, int op, int64_t n, uint8_t *val, uint8_t *ok) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto fetch = [&](const Utf8Operand &x, const uint8_t **p, int32_t *len) -> bool {
+        if (x.is_lit) {
+            *p = x.data;
+            *len = x.lit_len;
+            return !x.lit_null;
+        }
+        const int32_t o0 = x.off[i];
+        *p = x.data + o0;
+        *len = x.off[i + 1] - o0;
+        return !x.valid || ((x.valid[i >> 5] >> (i & 31)) & 1u);
+    };
+    const uint8_t *pa, *pb;
+    int32_t la, lb;
+    const bool va = fetch(a, &pa, &la), vb = fetch(b, &pb, &lb);
+    int cmp = 0;
+    const int32_t m = la < lb ? la : lb;
+    for (int32_t k = 0; k < m && cmp == 0; k++) cmp = (int)pa[k] - (int)pb[k];
+    if (cmp == 0) cmp = la < lb ? -1 : la > lb ? 1 : 0;
+    bool r;
+    switch (op) {
+    case NQE_OP_EQ: r = cmp == 0; break;
+    case NQE_OP_NOT_EQ: r = cmp != 0; break;
+    case NQE_OP_LT: r = cmp < 0; break;
+    case NQE_OP_LT_EQ: r = cmp <= 0; break;
+    case NQE_OP_GT: r = cmp > 0; break;
+    default: r = cmp >= 0; break;
+    }
+    const bool v = va && vb;
+    val[i] = v && r;
+    ok[i] = v;
+}
+
+static bool utf8_leaf(const nqe_table *in, const nqe_expr_node &nd) {
+    if (nd.kind == NQE_NODE_COLUMN) return nd.column >= 0 && nd.column < (int)in->cols.size() && in->cols[nd.column].dtype == NQE_UTF8;
+    return nd.kind == NQE_NODE_LITERAL && nd.dtype == NQE_UTF8;
+}
+
+// Rewrites the comparisons of Utf8 leaves in (predicate, projs) and runs the operator on the augmented view.
+// *handled == false: nothing to rewrite, the caller carries on.
+int32_t nqe_filter_project_utf8_compares(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *predicate, const nqe_expr *projs,
+                                         int32_t n_projs, nqe_table **out, bool *handled) {
+    *handled = false;
+    std::vector<const nqe_expr *> list;
+    if (predicate) list.push_back(predicate);
+    for (int i = 0; i < n_projs; i++) list.push_back(&projs[i]);
+    bool any = false;
+    for (const nqe_expr *e : list)
+        for (int i = 2; e->nodes && i < e->n_nodes; i++)
+            if (e->nodes[i].kind == NQE_NODE_BINARY && e->nodes[i].op >= NQE_OP_EQ && e->nodes[i].op <= NQE_OP_GT_EQ &&
+                utf8_leaf(in, e->nodes[i - 1]) && utf8_leaf(in, e->nodes[i - 2]))
+                any = true;
+    if (!any) return NQE_OK;
+    *handled = true;
+    const int64_t n = in->nrows;
+    nqe_table aug;
+    aug.ctx = ctx;
+    aug.nrows = n;
+    for (auto &c : in->cols) aug.cols.push_back(borrow(c));
+    std::vector<DevColumn> made;   // Boolean result columns (owned here)
+    std::vector<void *> scratch;   // literal bytes, byte-per-row buffers
+    std::vector<std::vector<nqe_expr_node>> nodes(list.size());
+    int32_t rc = NQE_OK;
+    auto operand = [&](const nqe_expr_node &nd, Utf8Operand *o) -> int32_t {
+        memset(o, 0, sizeof *o);
+        if (nd.kind == NQE_NODE_COLUMN) {
+            const DevColumn &c = in->cols[nd.column];
+            o->off = (const int32_t *)c.values;
+            o->data = c.data;
+            o->valid = (const uint32_t *)c.validity;
+            return NQE_OK;
+        }
+        o->is_lit = 1;
+        o->lit_null = nd.is_null != 0;
+        o->lit_len = nd.is_null ? 0 : nd.reserved;
+        if (o->lit_len < 0) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "Utf8 literal with a negative length");
+        void *d = nullptr;
+        NQE_TRY(nqe_dev_alloc(ctx, &d, (size_t)o->lit_len + 16));
+        scratch.push_back(d);
+        if (o->lit_len) NQE_CUDA(ctx, cudaMemcpyAsync(d, (const void *)(uintptr_t)nd.value.u64, (size_t)o->lit_len, cudaMemcpyHostToDevice, ctx->stream));
+        o->data = (const uint8_t *)d;
+        return NQE_OK;
+    };
+    for (size_t x = 0; x < list.size() && rc == NQE_OK; x++) {
+        const nqe_expr *e = list[x];
+        std::vector<nqe_expr_node> &o = nodes[x];
+        for (int i = 0; i < e->n_nodes && rc == NQE_OK; i++) {
+            const nqe_expr_node &nd = e->nodes[i];
+            const size_t m = o.size();
+            if (nd.kind == NQE_NODE_BINARY && nd.op >= NQE_OP_EQ && nd.op <= NQE_OP_GT_EQ && m >= 2 && i >= 2 &&
+                utf8_leaf(in, e->nodes[i - 1]) && utf8_leaf(in, e->nodes[i - 2]) && utf8_leaf(in, o[m - 1]) && utf8_leaf(in, o[m - 2])) {
+                Utf8Operand a, b;
+                rc = operand(o[m - 2], &a);
+                if (rc == NQE_OK) rc = operand(o[m - 1], &b);
+                const bool nullable = (!a.is_lit && a.valid) || (!b.is_lit && b.valid) || a.lit_null || b.lit_null;
+                DevColumn col;
+                uint8_t *val = nullptr, *ok = nullptr;
+                if (rc == NQE_OK) rc = nqe_column_alloc(ctx, NQE_BOOL, n, nullable, &col);
+                if (rc == NQE_OK) made.push_back(col);
+                if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, (void **)&val, (size_t)n + 64);
+                if (rc == NQE_OK) scratch.push_back(val);
+                if (rc == NQE_OK) rc = nqe_dev_alloc(ctx, (void **)&ok, (size_t)n + 64);
+                if (rc == NQE_OK) scratch.push_back(ok);
+                if (rc == NQE_OK && n > 0) {
+                    utf8_compare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, nd.op, n, val, ok);
+                    ctx->launches++;
+                    cudaMemsetAsync(ctx->d_scratch + 8, 0, sizeof(uint64_t), ctx->stream);
+                    rc = nqe_pack_bytes(ctx, val, n, (uint32_t *)made.back().values, nullptr);
+                    if (rc == NQE_OK && nullable) rc = nqe_pack_bytes(ctx, ok, n, (uint32_t *)made.back().validity, (unsigned long long *)(ctx->d_scratch + 8));
+                    if (rc == NQE_OK && nullable) {
+                        cudaMemcpyAsync(ctx->h_scratch + 8, ctx->d_scratch + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+                        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = nqe_fail(ctx, NQE_ERR_CUDA, "Utf8 comparison failed");
+                        made.back().null_count = (int64_t)ctx->h_scratch[8];
+                    }
+                }
+                if (rc == NQE_OK) {
+                    DevColumn view = borrow(made.back());
+                    if (view.null_count == 0) view.validity = nullptr; // arrow: no nulls => no bitmap
+                    aug.cols.push_back(view);
+                    o.resize(m - 2);
+                    o.push_back(nqe_expr_node{NQE_NODE_COLUMN, 0, (int32_t)aug.cols.size() - 1, 0, 0, 0, {0}});
+                }
+            } else {
+                o.push_back(nd);
+            }
+        }
+    }
+    if (rc == NQE_OK) {
+        std::vector<nqe_expr> ex(list.size());
+        for (size_t x = 0; x < list.size(); x++) ex[x] = nqe_expr{nodes[x].data(), (int32_t)nodes[x].size(), 0};
+        const nqe_expr *pred2 = predicate ? &ex[0] : nullptr;
+        rc = nqe_filter_project(ctx, &aug, pred2, ex.data() + (predicate ? 1 : 0), n_projs, out);
+    }
+    for (auto &c : made) nqe_column_release(ctx, &c);
+    for (void *p : scratch) nqe_dev_free(ctx, p);
+    return rc;
+}
+
 int32_t nqe_hash_join_strings(nqe_ctx *ctx, const nqe_table *left, const nqe_table *right, int32_t left_key,
                               int32_t right_key, nqe_table **out) {
     const nqe_table *side[2] = {left, right};

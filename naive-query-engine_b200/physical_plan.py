@@ -138,9 +138,12 @@ class PhysicalLiteralExpr(PhysicalExpr):
     def lower(self, names, out):
         lit = self.literal
         n = ExprNode(1, 0, 0, _SCALAR_DTYPE[lit.kind], 1 if lit.value is None else 0, 0)
-        if lit.kind == "Utf8":
-            raise NqeError(4, "Utf8 literals are not implemented on the CUDA path")
-        if lit.value is not None:
+        if lit.kind == "Utf8" and lit.value is not None:
+            # the bytes must outlive the call: they hang off this expression object (nqe.h: value.u64 = address, reserved = length)
+            self._utf8 = C.create_string_buffer(str(lit.value).encode("utf-8"))
+            n.reserved = len(self._utf8.raw) - 1
+            n.value.u64 = C.addressof(self._utf8)
+        elif lit.value is not None:
             if lit.kind == "Float64":
                 n.value.f64 = float(lit.value)
             elif lit.kind == "UInt64":

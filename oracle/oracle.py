@@ -242,11 +242,69 @@ def expr_name(expr, names: Sequence[str]) -> str:
     return f"{expr[1]}({expr_name(expr[2], names)})"
 
 
+_CMP = {"Eq": lambda c: c == 0, "NotEq": lambda c: c != 0, "Lt": lambda c: c < 0, "LtEq": lambda c: c <= 0,
+        "Gt": lambda c: c > 0, "GtEq": lambda c: c >= 0}
+
+
+def _utf8_leaf(e, batch: Batch) -> bool:
+    return (e[0] == "col" and batch.cols[e[1]].dtype == "utf8") or (e[0] == "lit" and e[1] == "utf8")
+
+
+def _utf8_compare(op: str, l, r, batch: Batch) -> Col:
+    """eq_dyn / neq_dyn / lt_dyn / lt_eq_dyn / gt_dyn / gt_eq_dyn on Utf8 arrays (binary.rs:127-132; literals are
+    materialised to n copies first, binary.rs:123-124): bytewise order, NULL where either side is NULL."""
+    n = batch.num_rows
+
+    def rows(e):
+        if e[0] == "lit":
+            return [e[2]] * n
+        return batch.cols[e[1]].to_pylist()
+    a, b = rows(l), rows(r)
+    vals, valid = np.zeros(n, dtype=np.uint8), np.ones(n, dtype=np.uint8)
+    for i in range(n):
+        if a[i] is None or b[i] is None:
+            valid[i] = 0
+            continue
+        x, y = a[i].encode("utf-8"), b[i].encode("utf-8")
+        vals[i] = 1 if _CMP[op]((x > y) - (x < y)) else 0
+    return Col("bool", vals, None if valid.all() else valid)
+
+
+def _rewrite_utf8(expr, batch: Batch):
+    """comparisons of Utf8 leaves -> Boolean columns appended to a copy of the batch (what the numeric C evaluator sees)"""
+    if expr[0] == "bin":
+        if _utf8_leaf(expr[2], batch) and _utf8_leaf(expr[3], batch):
+            if expr[1] in _CMP:
+                batch.cols.append(_utf8_compare(expr[1], expr[2], expr[3], batch))
+                batch.names.append(f"__utf8_cmp{len(batch.cols)}")
+                return ("col", len(batch.cols) - 1)
+            if expr[1] in ("And", "Or"):  # binary.rs:30-44
+                raise OracleError(2, f"Cannot evaluate binary expression {expr[1]} with types Utf8 and Utf8")
+            raise OracleError(5, "not implemented: arithmetic on Utf8")  # binary.rs:46-88 unimplemented!()
+        if _utf8_leaf(expr[2], batch) != _utf8_leaf(expr[3], batch) and (expr[2][0] in ("col", "lit")) and (expr[3][0] in ("col", "lit")):
+            names = {"bool": "Boolean", "i64": "Int64", "u64": "UInt64", "f64": "Float64", "utf8": "Utf8"}
+            dt = lambda e: names[batch.cols[e[1]].dtype if e[0] == "col" else e[1]]
+            raise OracleError(2, f"Cannot evaluate binary expression {expr[1]} with types {dt(expr[2])} and {dt(expr[3])}")
+        return ("bin", expr[1], _rewrite_utf8(expr[2], batch), _rewrite_utf8(expr[3], batch))
+    if expr[0] == "un":
+        return ("un", expr[1], _rewrite_utf8(expr[2], batch))
+    return expr
+
+
+def _has_utf8_leaf(expr, batch: Batch) -> bool:
+    if expr[0] in ("col", "lit"):
+        return _utf8_leaf(expr, batch)
+    return any(_has_utf8_leaf(e, batch) for e in expr[2:])
+
+
 def evaluate(expr, batch: Batch) -> Col:
     """PhysicalExpr::evaluate(..).into_array() on one batch."""
     if expr[0] == "col" and batch.cols[expr[1]].dtype == "utf8":
         c = batch.cols[expr[1]]
         return Col("utf8", c.values.copy(), None if c.valid is None else c.valid.copy())
+    if expr[0] != "col" and _has_utf8_leaf(expr, batch):
+        batch = Batch(list(batch.names), list(batch.cols))
+        expr = _rewrite_utf8(expr, batch)
     nodes: list = []
     _flatten(expr, nodes)
     keep: list = []

@@ -7,7 +7,7 @@ from oracle import oracle as O
 
 _PA = {"bool": pa.bool_(), "i64": pa.int64(), "u64": pa.uint64(), "f64": pa.float64(), "utf8": pa.utf8()}
 _SV = {"bool": nq.ScalarValue.Boolean, "i64": nq.ScalarValue.Int64, "u64": nq.ScalarValue.UInt64,
-       "f64": nq.ScalarValue.Float64}
+       "f64": nq.ScalarValue.Float64, "utf8": nq.ScalarValue.Utf8}
 _UN = {"abs": "Abs", "sin": "Sin", "cos": "Cos", "tan": "Tan"}
 _AGG = {"count": nq.Count, "sum": nq.Sum, "avg": nq.Avg, "min": nq.Min, "max": nq.Max}
 

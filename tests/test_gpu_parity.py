@@ -123,20 +123,50 @@ def test_cast_panics_like_the_reference():  # cast.rs:45-87: every arm is todo!(
     assert e.value.kind == "Panic"
 
 
-def test_utf8_comparisons_in_expressions_are_not_implemented():
-    """binary.rs:127-132 compares any arrow-comparable dtype, Utf8 included; the CUDA path does not:
-    this pins the error a caller sees instead of a silent wrong answer."""
-    import pyarrow as pa
+def _strings(rng, n, null_frac):
+    words = ["", "a", "ab", "abc", "b", "alice", "bob", "Zed", "\u00e9t\u00e9", "abcd" * 5]
+    return O.col("utf8", [None if rng.random() < null_frac else words[int(rng.integers(0, len(words)))] + ("x" * int(rng.integers(0, 3)))
+                          for _ in range(n)])
+
+
+@pytest.mark.parametrize("op", ["Eq", "NotEq", "Lt", "LtEq", "Gt", "GtEq"])
+def test_utf8_comparisons_in_expressions(op):
+    """binary.rs:127-132: the *_dyn comparison kernels take Utf8 operands (bytewise order, NULL if either side is NULL):
+    column vs column, column vs literal, literal vs column, a NULL literal, inside And, as a selection predicate (Utf8
+    and numeric columns ride along) and as a projected Boolean."""
+    rng = np.random.default_rng(len(op))
+    n = 3000
+    b = O.Batch(["s", "t", "x"], [_strings(rng, n, 0.1), _strings(rng, n, 0.0), rand_col(rng, "i64", n, 0.1)])
+    cases = [("bin", op, ("col", 0), ("col", 1)), ("bin", op, ("col", 0), ("lit", "utf8", "ab")),
+             ("bin", op, ("lit", "utf8", "b"), ("col", 1)), ("bin", op, ("col", 1), ("lit", "utf8", None)),
+             ("bin", "And", ("bin", op, ("col", 0), ("col", 1)), ("bin", "Gt", ("col", 2), lit(0)))]
+    for e in cases:
+        same(G.gpu_projection(b, [e, ("col", 2)]), O.projection(b, [e, ("col", 2)]))
+        same(G.gpu_selection(b, e), O.selection(b, e))
+
+
+def test_utf8_selection_on_the_golden_table():  # `select * from t1 where name = 'alice'` through the physical operators
+    t1 = golden_table("t1")
+    got = G.gpu_selection(t1, ("bin", "Eq", ("col", 1), ("lit", "utf8", "alice")))
+    want = O.selection(t1, ("bin", "Eq", ("col", 1), ("lit", "utf8", "alice")))
+    same(got, want)
+    assert got.num_rows == 1 and got.cols[1].to_pylist() == ["alice"]
+
+
+def test_utf8_expression_errors():
     nq = G.nq
-    rb = pa.RecordBatch.from_arrays([pa.array(["a", "b", "a"]), pa.array(["a", "a", "c"]), pa.array([1, 2, 3])], names=["s", "t", "x"])
-    scan = nq.ScanPlan.create(nq.MemTable.try_create(rb.schema, [rb]), None)
-    pred = nq.PhysicalBinaryExpr.create(nq.ColumnExpr.try_create(None, 0), "Eq", nq.ColumnExpr.try_create(None, 1))
-    with pytest.raises(nq.NqeError) as e:
-        nq.SelectionPlan.create(scan, pred).execute()
-    assert e.value.kind == "NotImplemented"
-    with pytest.raises(nq.NqeError) as e:
-        nq.PhysicalLiteralExpr.create(nq.ScalarValue.Utf8("a")).evaluate(rb)
-    assert e.value.kind == "NotImplemented"
+    b = O.Batch(["s", "t", "x"], [O.col("utf8", ["a", "b"]), O.col("utf8", ["a", "c"]), O.col("i64", [1, 2])])
+    for e, kind in [(("bin", "Eq", ("col", 0), ("col", 2)), "IntervalError"), (("bin", "Plus", ("col", 0), ("col", 1)), "Panic"),
+                    (("bin", "And", ("col", 0), ("col", 1)), "IntervalError"), (("bin", "Lt", ("col", 2), ("lit", "utf8", "a")), "IntervalError")]:
+        with pytest.raises(nq.NqeError) as err:
+            G.gpu_projection(b, [e])
+        assert err.value.kind == kind, e
+        with pytest.raises(O.OracleError) as oerr:
+            O.projection(b, [e])
+        assert oerr.value.kind == kind, e
+    with pytest.raises(nq.NqeError) as err:
+        G.gpu_projection(b, [("bin", "Eq", ("col", 0), ("col", 2))])
+    assert err.value.message == "Cannot evaluate binary expression Eq with types Utf8 and Int64"
 
 
 def _three_batches(rng, n, with_strings):
