@@ -6,6 +6,8 @@ naive-query-engine's physical_plan pipeline.
     device.py          Arrow RecordBatch <-> HBM tables
     physical_plan.py   host mirror of the reference's PhysicalPlan / PhysicalExpr /
                        AggregateOperator interface
+    sql.py, db.py      `NaiveDB.run_sql()`: the reference's SQL surface and planner wiring in front of those nodes
+    distributed.py     multi-GPU plans (torch.distributed)
     synth.py           deterministic synthetic benchmark tables
 
 The directory name contains a hyphen; import it with
@@ -18,3 +20,4 @@ from .physical_plan import (Avg, ColumnExpr, Count, CsvTable, HashJoin, Max, Mem
                             PhysicalAggregatePlan, PhysicalBinaryExpr, PhysicalCastExpr, PhysicalLimitPlan,
                             PhysicalExpr, PhysicalLiteralExpr, PhysicalOffsetPlan, PhysicalPlan, PhysicalUnaryExpr,
                             ProjectionPlan, ScalarValue, ScanPlan, SelectionPlan, Sum)
+from .db import CsvConfig, NaiveDB, QueryPlanner, SQLPlanner  # noqa: F401,E402
