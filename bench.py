@@ -347,6 +347,36 @@ def pinned_arrow(torch, pa, t, typ):
     return pa.Array.from_buffers(typ, t.numel(), [None, buf])
 
 
+def bind_to_gpu_numa_node(torch, device_index: int):
+    """Pin this process (and therefore its pinned-memory allocations, first touch) to the CPUs of the NUMA node its GPU
+    hangs off: with one process per GPU the host legs of the e2e path (pinned Arrow buffers -> PCIe) otherwise all
+    land on whatever node the launcher started on.  Returns what was done, for the JSON line."""
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        bind_to_gpu_numa_node.original = allowed  # restored before the CPU-baseline legs, which use every host core
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 -- best effort
+        return {"bound": False, "error": f"{type(e).__name__}: {e}"[:120]}
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -354,6 +384,7 @@ def run_gpu(args, rank, local_rank, world):
     import nqe_b200 as nq
     BOOL, I64, U64, F64 = 1, 2, 3, 4
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if os.environ.get("NQE_BENCH_NUMA", "1") != "0" else {"bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = nq.Context(local_rank)
@@ -434,6 +465,8 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.build()
+        if getattr(bind_to_gpu_numa_node, "original", None):
+            os.sched_setaffinity(0, bind_to_gpu_numa_node.original)
         threads = host_threads()
         rps1, _, _ = cpu_filter_project(REF_SAMPLE_ROWS, 3, 1, 1)
         sample = REF_SAMPLE_ROWS * (4 if threads >= 8 else 1)
@@ -473,7 +506,8 @@ def run_gpu(args, rank, local_rank, world):
                          "operator_frac": alg_bytes / (ms / K / 1e3) / 1e9 / hbm_peak},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "path": "pinned host Arrow buffers -> nqe_filter_project_host -> pinned host result buffers"},
+                    "path": "pinned host Arrow buffers -> nqe_filter_project_host -> pinned host result buffers",
+                    "host_numa": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
