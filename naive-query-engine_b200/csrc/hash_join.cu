@@ -947,8 +947,10 @@ int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, cons
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
 }
-// knob NQE_JA_PROBE_SHAPE: 0 (default) = 256 threads x 4 rows (quarter pages, 4 CTAs/SM), 1 = 512 x 4 (half pages,
-// 2 CTAs/SM), 2 = 1024 x 4 (whole pages, 1 CTA/SM).  Measured 1e8 x 1e7: 4.78 / 4.92 / 4.95 ms for the whole operator.
+// knob NQE_JA_PROBE_SHAPE: 0 (default) = 256 threads x 2 rows (512-row pieces, 6 CTAs/SM at 40 registers), 1 = 512 x 4
+// (half pages, 2 CTAs/SM), 2 = 1024 x 4 (whole pages, 1 CTA/SM), 3 = 256 x 4 with 5 CTAs/SM (51 registers), 4 = 256 x 4
+// (quarter pages, 4 CTAs/SM).  Measured 1e8 x 1e7, whole operator: 4.69 / 4.92 / 4.95 / 5.00 / 4.84 ms: the kernel waits
+// on L2 round trips, more resident warps beat more rows per thread.
 int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2) {
     static int shape = -1;
     if (shape < 0) {
@@ -958,7 +960,9 @@ int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const Page
     switch (shape) {
     case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2);
     case 2: return ja_probe_scatter_launch_shape<1024, 4, 1>(ctx, in, out, jt, P2);
-    default: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2);
+    case 3: return ja_probe_scatter_launch_shape<256, 4, 5>(ctx, in, out, jt, P2);
+    case 4: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2);
+    default: return ja_probe_scatter_launch_shape<256, 2, 6>(ctx, in, out, jt, P2);
     }
 }
 

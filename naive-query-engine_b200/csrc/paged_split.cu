@@ -40,7 +40,7 @@ int nqe_ps_split_shape() {
     if (shape < 0) {
         const char *e = getenv("NQE_PS_SPLIT_SHAPE");
         shape = e ? atoi(e) : 0;
-        if (shape < 0 || shape > 2) shape = 0;
+        if (shape < 0 || shape > 4) shape = 0;
     }
     return shape;
 }

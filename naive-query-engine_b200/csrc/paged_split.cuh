@@ -177,8 +177,9 @@ struct PartByHash { // partition = high 32 bits of the key's hash, range-reduced
 };
 
 // Tile shapes of the split kernel (knob NQE_PS_SPLIT_SHAPE): 0 (default) = 256 threads x 8 rows (2048-row tiles,
-// 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM), 2 = 1024 x 4 (4096-row tiles, 1 CTA/SM).  Measured, group-by
-// of 1e8 rows into 148 partitions: 1.95 / 1.98 / 2.24 ms for the whole operator.
+// 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM), 2 = 1024 x 4 (4096-row tiles, 1 CTA/SM), 3 = 256 x 8 with 5
+// CTAs/SM (51 registers), 4 = 256 x 4 (1024-row tiles, 6 CTAs/SM).  Measured, group-by of 1e8 rows into 148
+// partitions, whole operator: 1.95-1.98 / 1.98 / 2.24 / 2.08 / 2.46 ms.
 template <bool KEYEXPR, typename Part, int T, int K, int MINB>
 __global__ void __launch_bounds__(T, MINB)
 ps_split_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, const Part part,
@@ -238,6 +239,8 @@ static int32_t ps_split_launch(nqe_ctx *ctx, const PagedStreams &ps, const PsSpl
     switch (nqe_ps_split_shape()) {
     case 1: return ps_split_launch_shape<KEYEXPR, Part, 512, 8, 2>(ctx, ps, a, part, prog, status);
     case 2: return ps_split_launch_shape<KEYEXPR, Part, 1024, 4, 1>(ctx, ps, a, part, prog, status);
+    case 3: return ps_split_launch_shape<KEYEXPR, Part, 256, 8, 5>(ctx, ps, a, part, prog, status);
+    case 4: return ps_split_launch_shape<KEYEXPR, Part, 256, 4, 6>(ctx, ps, a, part, prog, status);
     default: return ps_split_launch_shape<KEYEXPR, Part, 256, 8, 4>(ctx, ps, a, part, prog, status);
     }
 }

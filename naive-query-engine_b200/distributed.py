@@ -36,7 +36,7 @@ NCCL with the CUDA engine below.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 
 class Engine:
@@ -157,14 +157,21 @@ class Phases:
         return out
 
 
-def all_gather_rows(dist, torch, cols: Sequence, world: int):
-    """All ranks' rows of `cols` (equal-dtype 1-D tensors) in rank order, with ONE collective per call for the sizes
-    and one for the data: the columns travel packed as a (rows, n_cols) matrix, padded to the largest rank."""
-    n = int(cols[0].numel())
-    sizes = torch.tensor([n], dtype=torch.int64, device=cols[0].device)
-    all_sizes = torch.empty(world, dtype=torch.int64, device=cols[0].device)
+def all_gather_sizes(dist, torch, n: int, world: int, device):
+    """every rank's row count, in rank order (one small collective + one host synchronisation)"""
+    sizes = torch.tensor([n], dtype=torch.int64, device=device)
+    all_sizes = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(all_sizes, sizes)
-    nl = [int(x) for x in all_sizes.tolist()]
+    return [int(x) for x in all_sizes.tolist()]
+
+
+def all_gather_rows(dist, torch, cols: Sequence, world: int, nl: Optional[Sequence[int]] = None):
+    """All ranks' rows of `cols` (equal-dtype 1-D tensors) in rank order, with ONE collective per call for the sizes
+    (skipped when the caller already has them: `nl`) and one for the data: the columns travel packed as a
+    (rows, n_cols) matrix, padded to the largest rank."""
+    n = int(cols[0].numel())
+    if nl is None:
+        nl = all_gather_sizes(dist, torch, n, world, cols[0].device)
     nmax = max(max(nl), 1)
     packed = torch.zeros((nmax, len(cols)), dtype=cols[0].dtype, device=cols[0].device)
     packed[:n] = torch.stack(list(cols), dim=1)
@@ -194,7 +201,7 @@ def exchange_partials(dist, torch, engine: Engine, partial: Sequence, world: int
     return [got[:, c].contiguous() for c in range(len(part))], sum(send_l) - send_l[rank]
 
 
-GATHER_MERGE_MAX_ROWS = 1 << 22  # partial rows per rank up to which "all-gather, merge everywhere" beats the radix exchange
+GATHER_MERGE_MAX_ROWS = 1 << 22  # partial rows over all ranks up to which "all-gather, merge everywhere" beats the radix exchange
 
 
 def merge_exchanged_partials(dist, torch, engine: Engine, partial: Sequence, world: int, gather: bool = True, phases=None):
@@ -205,8 +212,9 @@ def merge_exchanged_partials(dist, torch, engine: Engine, partial: Sequence, wor
     configs[4] on 8 GPUs) the radix step is skipped: one all-gather of the partial states, every rank merges all of
     them -- two collectives and one host synchronisation instead of five and three (measured at 8 GPUs: 1.28 -> ms
     in bench.py's phase table)."""
-    if gather and int(partial[0].numel()) <= GATHER_MERGE_MAX_ROWS // max(world, 1):
-        rows, nl = all_gather_rows(dist, torch, [c if c.dtype == torch.int64 else c.view(torch.int64) for c in partial], world)
+    nl = all_gather_sizes(dist, torch, int(partial[0].numel()), world, partial[0].device) if gather else None
+    if gather and sum(nl) <= GATHER_MERGE_MAX_ROWS:  # decided from the gathered sizes: every rank takes the same branch
+        rows, nl = all_gather_rows(dist, torch, [c if c.dtype == torch.int64 else c.view(torch.int64) for c in partial], world, nl)
         if phases is not None:
             phases.mark("partial_exchange")
         merged = engine.merge_partials(rows)
