@@ -172,4 +172,9 @@ uint64_t nqe_agg_capacity(double est);
 struct PagedStreams;
 int32_t nqe_estimate_distinct_u64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, double *est);
 bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m);
-int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need);
+// dense_width != 0: the streams were split by key RANGE (PartByRange in paged_split.cuh): partition p holds the keys
+// [dense_lo + p * dense_width, + dense_width) and is aggregated in a directly indexed table
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need, long long dense_lo = 0,
+                          unsigned dense_width = 0);
+constexpr unsigned NQE_GP2_DENSE_MAX_WIDTH = 3072; // = GA_SLOTS
+int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi);

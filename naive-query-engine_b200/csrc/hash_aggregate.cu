@@ -13,6 +13,7 @@
 // (sum.rs:44 `val as f64`), NULL keys are dropped (mod.rs:63-71), NULL values
 // skipped, and the output carries no key column.
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <algorithm>
@@ -122,6 +123,11 @@ constexpr int GA_SLOTS = 3072, GA_BUCKETS = GA_SLOTS / 2;
 constexpr int GA_CHUNK = 32 * GA_K;                 // rows per warp and stage
 constexpr unsigned GA_NONE = 0xFFFFFFFFu;
 static_assert(GA_WARPS * GA_CHUNK == PS_PAGE_ROWS, "a page is one chunk per warp");
+struct GaDense {
+    long long lo;      // smallest key of partition 0
+    unsigned width;    // keys per partition (<= GA_SLOTS)
+    unsigned pad;
+};
 struct GaSmem {
     ulonglong2 stage[GA_WARPS][GA_CHUNK];           // 64 KB
     ulonglong2 keys2[GA_BUCKETS];                   // keys[2 b], keys[2 b + 1]
@@ -169,9 +175,13 @@ __device__ __noinline__ unsigned ga_insert(unsigned long long *keys, unsigned lo
     return GA_NONE;
 }
 
-// need: bit ST_CNT / ST_SUM / ST_MIN / ST_MAX set when the plan has such a state
+// need: bit ST_CNT / ST_SUM / ST_MIN / ST_MAX set when the plan has such a state.
+// DENSE: the keys of partition p are the integers [dense.lo + p * dense.width, + dense.width) (the split was by key
+// RANGE, PartByRange): the slot of a key is its offset in that range -- no key array, no lookup, no inserts.
+template <bool DENSE>
 __global__ void __launch_bounds__(GA_THREADS, 1)
-gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_constant__ AggParams ap, int m, int need) {
+gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_constant__ AggParams ap, int m, int need,
+                     const GaDense dense) {
     extern __shared__ __align__(128) unsigned char ga_smem[];
     GaSmem &sm = *reinterpret_cast<GaSmem *>(ga_smem);
     unsigned long long *const keys = (unsigned long long *)sm.keys2;
@@ -180,8 +190,9 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
     const unsigned long long rows_p = st.cursor[p];
     const unsigned npg = (unsigned)((rows_p + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
     const unsigned last_fill = (unsigned)(rows_p - ((unsigned long long)(npg ? npg - 1 : 0) << PS_PAGE_SHIFT)); // rows of the last page
+    const unsigned long long dense_base = (unsigned long long)dense.lo + (unsigned long long)p * dense.width; // key of slot 0
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
-        keys[i] = EMPTY_KEY;
+        if (!DENSE) keys[i] = EMPTY_KEY;
         sm.mm[i] = make_ulonglong2(~0ull, 0ull);   // identities of min / max in the ordered encoding
         sm.sf[i] = make_ulonglong2(0ull, 0x00000000FFFFFFFFull); // sum = +0.0; min_hi = ~0, max_hi = 0: everything passes
         sm.cnt[i] = 0u;
@@ -230,45 +241,53 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
             if (q + 2 * m < npg) next_pte = pt[q + 2 * m];
         }
         if (!rows) continue;
-        // ---- branch-free lookup: both buckets of a row, then compares (two rows at a time: registers)
         unsigned slot[GA_K];
-        uint32_t miss = 0;
+        if (DENSE) {
 #pragma unroll
-        for (int h = 0; h < GA_K; h += 2) {
-            ulonglong2 A[2], B[2];
-            unsigned b1[2], b2[2];
-#pragma unroll
-            for (int j = h; j < h + 2; j++) {
-                ga_buckets_of(key[j], &b1[j - h], &b2[j - h]);
-                A[j - h] = sm.keys2[b1[j - h]];
+            for (int j = 0; j < GA_K; j++) {
+                const unsigned long long d = key[j] - dense_base;
+                slot[j] = ((live >> j) & 1u) && d < (unsigned long long)dense.width ? (unsigned)d : GA_NONE; // outside: global table
             }
-#pragma unroll
-            for (int j = h; j < h + 2; j++) { // the second bucket only if some lane needs it (most keys sit in their first)
-                const bool inA = A[j - h].x == key[j] || A[j - h].y == key[j] || key[j] == EMPTY_KEY;
-                B[j - h] = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
-                if (__any_sync(0xffffffffu, !inA)) B[j - h] = sm.keys2[b2[j - h]];
+        } else {
+            // ---- branch-free lookup: both buckets of a row, then compares (two rows at a time: registers)
+            uint32_t miss = 0;
+    #pragma unroll
+            for (int h = 0; h < GA_K; h += 2) {
+                ulonglong2 A[2], B[2];
+                unsigned b1[2], b2[2];
+    #pragma unroll
+                for (int j = h; j < h + 2; j++) {
+                    ga_buckets_of(key[j], &b1[j - h], &b2[j - h]);
+                    A[j - h] = sm.keys2[b1[j - h]];
+                }
+    #pragma unroll
+                for (int j = h; j < h + 2; j++) { // the second bucket only if some lane needs it (most keys sit in their first)
+                    const bool inA = A[j - h].x == key[j] || A[j - h].y == key[j] || key[j] == EMPTY_KEY;
+                    B[j - h] = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
+                    if (__any_sync(0xffffffffu, !inA)) B[j - h] = sm.keys2[b2[j - h]];
+                }
+    #pragma unroll
+                for (int j = h; j < h + 2; j++) {
+                    const unsigned long long k = key[j];
+                    const ulonglong2 a = A[j - h], b = B[j - h];
+                    const unsigned s1 = 2 * b1[j - h], s2 = 2 * b2[j - h];
+                    unsigned s = GA_NONE; // selects, not branches
+                    s = b.y == k ? s2 + 1 : s;
+                    s = b.x == k ? s2 : s;
+                    s = a.y == k ? s1 + 1 : s;
+                    s = a.x == k ? s1 : s;
+                    s = k == EMPTY_KEY ? GA_NONE : s; // i64::MIN marks free slots (and dead lanes): that key lives in the global table only
+                    slot[j] = s;
+                    miss |= (k != EMPTY_KEY && s == GA_NONE) ? 1u << j : 0u;
+                }
             }
-#pragma unroll
-            for (int j = h; j < h + 2; j++) {
-                const unsigned long long k = key[j];
-                const ulonglong2 a = A[j - h], b = B[j - h];
-                const unsigned s1 = 2 * b1[j - h], s2 = 2 * b2[j - h];
-                unsigned s = GA_NONE; // selects, not branches
-                s = b.y == k ? s2 + 1 : s;
-                s = b.x == k ? s2 : s;
-                s = a.y == k ? s1 + 1 : s;
-                s = a.x == k ? s1 : s;
-                s = k == EMPTY_KEY ? GA_NONE : s; // i64::MIN marks free slots (and dead lanes): that key lives in the global table only
-                slot[j] = s;
-                miss |= (k != EMPTY_KEY && s == GA_NONE) ? 1u << j : 0u;
+            if (miss) { // first row of a group in this CTA (or a row that raced with it)
+    #pragma unroll
+                for (int j = 0; j < GA_K; j++)
+                    if ((miss >> j) & 1u) slot[j] = ga_insert(keys, key[j]);
             }
+            __syncwarp();
         }
-        if (miss) { // first row of a group in this CTA (or a row that raced with it)
-#pragma unroll
-            for (int j = 0; j < GA_K; j++)
-                if ((miss >> j) & 1u) slot[j] = ga_insert(keys, key[j]);
-        }
-        __syncwarp();
         uint32_t found = 0;
 #pragma unroll
         for (int j = 0; j < GA_K; j++)
@@ -284,7 +303,7 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
         for (int j = 0; j < GA_K; j++)
             if (!((found >> j) & 1u)) slot[j] = 0; // harmless address for the unconditional reads below
         // ---- updates, the four rows in lock step (key[j] is dead from here on)
-        if (need & (1 << ST_CNT)) {
+        if (DENSE || (need & (1 << ST_CNT))) { // the dense table has no key array: a non-zero count marks a slot as used
 #pragma unroll
             for (int j = 0; j < GA_K; j++)
                 if ((found >> j) & 1u) atomicAdd(&sm.cnt[slot[j]], 1u);
@@ -357,8 +376,8 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
     __syncthreads();
     // partial states of this CTA -> global table
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
-        const unsigned long long key = keys[i];
-        if (key == EMPTY_KEY) continue;
+        const unsigned long long key = DENSE ? dense_base + (unsigned long long)i : keys[i];
+        if (DENSE ? sm.cnt[i] == 0u : key == EMPTY_KEY) continue;
         Sector0 s0;
         unsigned long long *rec = find_slot(ap, key, &s0);
         if (!rec) continue; // table full: flagged, the host grows the table and repeats this kernel
@@ -460,8 +479,10 @@ __global__ void agg_extract_kernel(AggParams ap, ExtractParams xp, uint64_t n_re
 // mean is a hot key (all its rows land in one partition, i.e. on one SM)
 constexpr int AGG_SKEW_BINS = 256;
 __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int64_t n_rows, int64_t stride,
-                                  int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status, unsigned int *bins) {
+                                  int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status, unsigned int *bins,
+                                  long long *minmax) {
     __shared__ unsigned int s_bins[AGG_SKEW_BINS];
+    long long kmin = LLONG_MAX, kmax = LLONG_MIN;
     for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x) s_bins[b] = 0;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,7 +495,18 @@ __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int6
             const uint32_t h = (uint32_t)(hh >> 32) & bits_mask;
             atomicOr(bitmap + (h >> 5), 1u << (h & 31));
             atomicAdd(&s_bins[hh >> 56], 1u);
+            kmin = kmax = (long long)key.v[0];
         }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b > kmax ? b : kmax;
+    }
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+        atomicMin(minmax, kmin);
+        atomicMax(minmax + 1, kmax);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x)
@@ -496,7 +528,46 @@ __global__ void distinct_sample_kernel(const unsigned long long *col, int64_t st
     atomicOr(bitmap + (h >> 5), 1u << (h & 31));
 }
 
+// smallest / largest value of an 8-byte column in signed order
+__global__ void minmax_i64_kernel(const long long *col, int64_t n, long long *out) {
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long v = col[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
 } // namespace
+
+int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi) {
+    *lo = 0;
+    *hi = -1;
+    if (n <= 0) return NQE_OK;
+    long long *d = (long long *)(ctx->d_scratch + 10);
+    const long long init[2] = {LLONG_MAX, LLONG_MIN};
+    NQE_CUDA(ctx, cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    int grid = ctx->sm_count * 8;
+    if ((int64_t)grid * 256 > n) grid = (int)((n + 255) / 256);
+    minmax_i64_kernel<<<grid, 256, 0, ctx->stream>>>((const long long *)col, n, d);
+    ctx->launches++;
+    long long h[2];
+    NQE_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    NQE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *lo = h[0];
+    *hi = h[1];
+    return NQE_OK;
+}
 
 static double linear_count(uint64_t ones, uint32_t bits, int64_t n, int64_t n_sample) {
     const double m = (double)bits, z = m - (double)ones;
@@ -536,9 +607,16 @@ bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m) {
     return true;
 }
 
-int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need) {
-    NQE_CUDA(ctx, cudaFuncSetAttribute(gp2_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
-    gp2_aggregate_kernel<<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, need);
+int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need, long long dense_lo,
+                          unsigned dense_width) {
+    const GaDense dense{dense_lo, dense_width, 0u};
+    if (dense_width) {
+        NQE_CUDA(ctx, cudaFuncSetAttribute(gp2_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
+        gp2_aggregate_kernel<true><<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, need, dense);
+    } else {
+        NQE_CUDA(ctx, cudaFuncSetAttribute(gp2_aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GA_SMEM));
+        gp2_aggregate_kernel<false><<<streams.P * m, GA_THREADS, GA_SMEM, ctx->stream>>>(streams, ap, m, need, dense);
+    }
     ctx->launches++;
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
@@ -784,23 +862,28 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         // --- size the table from a sampled cardinality estimate, grow on overflow
         uint64_t capacity = 1024;
         double est_groups = 1e18;
+        long long key_minmax[2] = {0, -1}; // smallest / largest key of the sample (signed order)
         bool skewed = false; // a hot key: the partitioned path would put all its rows on one SM (measured, Zipf-1.0: 52 vs 21 ms)
         if (n > 0) {
             const int64_t n_sample = n < (1 << 20) ? n : (1 << 20);
             const int64_t stride = n / n_sample;
             const uint32_t bits = 1u << 23; // 8 Mi bits = 1 MiB bitmap
             void *bm = nullptr;
-            rc = nqe_dev_alloc(ctx, &bm, bits / 8 + AGG_SKEW_BINS * 4);
+            rc = nqe_dev_alloc(ctx, &bm, bits / 8 + AGG_SKEW_BINS * 4 + 16);
             if (rc == NQE_OK) {
                 unsigned int *bins = (unsigned int *)((uint8_t *)bm + bits / 8);
+                long long *d_minmax = (long long *)(bins + AGG_SKEW_BINS);
                 unsigned int h_bins[AGG_SKEW_BINS];
+                const long long mm_init[2] = {LLONG_MAX, LLONG_MIN};
                 cudaMemsetAsync(bm, 0, bits / 8 + AGG_SKEW_BINS * 4, ctx->stream);
+                cudaMemcpyAsync(d_minmax, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
                 agg_sample_kernel<<<(unsigned)((n_sample + 255) / 256), 256, 0, ctx->stream>>>(
-                    ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status, bins);
+                    ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status, bins, d_minmax);
                 popcount_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t *)bm, bits / 32, (unsigned long long *)ctx->d_scratch);
                 ctx->launches += 2;
                 cudaMemcpyAsync(h_bins, bins, sizeof h_bins, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(key_minmax, d_minmax, sizeof key_minmax, cudaMemcpyDeviceToHost, ctx->stream);
                 rc = read_scratch(ctx, 2);
                 nqe_dev_free(ctx, bm);
                 if (rc == NQE_OK) {
@@ -833,6 +916,15 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
         PagedStreams streams;
         memset(&streams, 0, sizeof streams);
         int gp_need = 0, gp_m = 1, gp_dtype = 0;
+        long long dense_lo = 0;
+        unsigned dense_width = 0;
+        static int allow_dense = -1; // knob NQE_AGG_DENSE=0: always hash the keys
+        if (allow_dense < 0) {
+            const char *e = getenv("NQE_AGG_DENSE");
+            allow_dense = e ? atoi(e) : 1;
+        }
+        bool try_dense = allow_dense != 0;
+    split_again:
         if (rc == NQE_OK && agg_part && !skewed && n >= agg_part_min_rows && ap.n_states > 0 && est_groups >= 2048.0) {
             bool one_src = true;
             for (int q = 0; q < ap.n_states; q++) {
@@ -842,21 +934,43 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             const DevColRef &vc = ps.cols[ap.st_src[0]];
             int P = 0;
             if (!nqe_gp2_plan(ctx, est_groups, &P, &gp_m)) P = 0;
+            // dense keys (the sampled range is not much larger than the number of groups): split by key RANGE, aggregate in
+            // directly indexed tables; a key outside the sampled range is detected by the split and sends us back to hashing
+            dense_width = 0;
+            if (try_dense && key_minmax[0] <= key_minmax[1]) {
+                const unsigned long long range = (unsigned long long)key_minmax[1] - (unsigned long long)key_minmax[0] + 1ull;
+                const unsigned long long per_part = (range + ctx->sm_count - 1) / ctx->sm_count;
+                if (range < (1ull << 32) && (double)range <= 4.0 * est_groups + 1024.0 && per_part <= NQE_GP2_DENSE_MAX_WIDTH &&
+                    ctx->sm_count <= PS_MAX_PARTS) {
+                    dense_lo = key_minmax[0];
+                    dense_width = (unsigned)(per_part < 64 ? 64 : per_part);
+                    P = (int)((range + dense_width - 1) / dense_width);
+                    gp_m = ctx->sm_count / P;
+                }
+            }
             if (P > 0 && one_src && !vc.validity && (vc.dtype == NQE_INT64 || vc.dtype == NQE_UINT64 || vc.dtype == NQE_FLOAT64)) {
                 gp_dtype = vc.dtype;
                 rc = nqe_ps_create(ctx, n, P, &streams);
                 if (rc == NQE_OK) {
                     PsSplitArgs sa{simple ? (const unsigned long long *)ps.cols[key_slot].values : nullptr,
                                    (const unsigned long long *)vc.values, n, gp_dtype};
-                    const PartByHash part{(uint32_t)P};
-                    if (simple) rc = ps_split_launch<false, PartByHash>(ctx, streams, sa, part, ps, ap.status);
-                    else rc = ps_split_launch<true, PartByHash>(ctx, streams, sa, part, ps, ap.status);
+                    if (dense_width) {
+                        const PartByRange part{dense_lo, (unsigned long long)key_minmax[1] - (unsigned long long)key_minmax[0] + 1ull, dense_width, ap.status};
+                        if (simple) rc = ps_split_launch<false, PartByRange>(ctx, streams, sa, part, ps, ap.status);
+                        else rc = ps_split_launch<true, PartByRange>(ctx, streams, sa, part, ps, ap.status);
+                    } else {
+                        const PartByHash part{(uint32_t)P};
+                        if (simple) rc = ps_split_launch<false, PartByHash>(ctx, streams, sa, part, ps, ap.status);
+                        else rc = ps_split_launch<true, PartByHash>(ctx, streams, sa, part, ps, ap.status);
+                    }
                     use_part = rc == NQE_OK;
                 }
             }
         }
+        uint32_t split_flags = 0; // status bits raised by the split (key expression errors, keys outside the dense range)
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
-            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            // the split ran before this loop and wrote its flags into the same status word: they are read with the first attempt
+            if (!(use_part && attempt == 0)) cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             rc = nqe_agg_table_create(ctx, &ap, capacity);
             if (rc != NQE_OK) break;
             if (n > 0) {
@@ -870,7 +984,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 const int64_t tiles = (n + kk * AG_THREADS - 1) / (kk * AG_THREADS);
                 int grid = ctx->sm_count * 8;
                 if (grid > tiles) grid = (int)tiles;
-                if (use_part) rc = nqe_gp2_aggregate(ctx, streams, ap, gp_m, gp_need);
+                if (use_part) rc = nqe_gp2_aggregate(ctx, streams, ap, gp_m, gp_need, dense_lo, dense_width);
                 else if (simple && agk == 2) group_aggregate_kernel<true, 2><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple && agk == 8) group_aggregate_kernel<true, 8><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
                 else if (simple) group_aggregate_kernel<true, 4><<<grid, AG_THREADS, 0, ctx->stream>>>(ps, ap, key_slot);
@@ -880,10 +994,20 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             }
             rc = read_scratch(ctx, 2);
             if (rc != NQE_OK) break;
-            const uint32_t st = (uint32_t)ctx->h_scratch[1];
+            if (use_part && attempt == 0) split_flags = (uint32_t)ctx->h_scratch[1] & (DEV_ERR_DIV0 | DEV_ERR_OVERFLOW | DEV_ERR_RANGE | DEV_ERR_CAPACITY);
+            const uint32_t st = (uint32_t)ctx->h_scratch[1] | split_flags;
             if (st & DEV_ERR_DIV0) { rc = nqe_fail(ctx, NQE_ERR_DIVIDE_BY_ZERO, "Divide by zero error"); break; }
             if (st & DEV_ERR_OVERFLOW) { rc = nqe_fail(ctx, NQE_ERR_PANIC, "attempt to divide with overflow"); break; }
             if (st & DEV_ERR_CAPACITY) { rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: paged stream pool exhausted"); break; }
+            if (use_part && dense_width && (st & DEV_ERR_RANGE)) { // a key outside the sampled range: hash the keys instead
+                nqe_dev_free(ctx, ap.table);
+                ap.table = nullptr;
+                nqe_ps_destroy(ctx, &streams);
+                use_part = false;
+                try_dense = false;
+                cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+                goto split_again;
+            }
             if (!(st & DEV_ERR_TABLE_FULL)) break;
             nqe_dev_free(ctx, ap.table);
             ap.table = nullptr;

@@ -865,7 +865,7 @@ __device__ __forceinline__ unsigned jp_locate(const PagedStreams &in, const unsi
 template <int T, int K, int MINB>
 __global__ void __launch_bounds__(T, MINB)
 ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_constant__ PagedStreams out, const JoinTable jt,
-                        uint32_t P2) {
+                        uint32_t P2, long long dense_lo, uint32_t dense_width) {
     constexpr int PIECE = T * K;
     extern __shared__ __align__(128) unsigned char jp_smem_raw[];
     JpSmem<T, K> &sm = *reinterpret_cast<JpSmem<T, K> *>(jp_smem_raw);
@@ -932,17 +932,21 @@ ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_co
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
-            pid[j] = (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
+            // dense group keys (their exact range is known from the build side): partition = key range, else key hash
+            pid[j] = dense_width ? (int)((uint32_t)(grp[j] - (unsigned long long)dense_lo) / dense_width)
+                                 : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
+            if (!((live >> j) & 1u)) pid[j] = 0;
         }
         ps_scatter_tile<T, K>(out, sm.sc, grp, val, pid, live);
     }
 }
 
 template <int T, int K, int MINB>
-int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2) {
+int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
+                                      long long dense_lo, uint32_t dense_width) {
     auto kern = ja_probe_scatter_kernel<T, K, MINB>;
     NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpSmem<T, K>)));
-    kern<<<ctx->sm_count * MINB, T, sizeof(JpSmem<T, K>), ctx->stream>>>(in, out, jt, P2);
+    kern<<<ctx->sm_count * MINB, T, sizeof(JpSmem<T, K>), ctx->stream>>>(in, out, jt, P2, dense_lo, dense_width);
     ctx->launches++;
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
@@ -951,18 +955,19 @@ int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, cons
 // (half pages, 2 CTAs/SM), 2 = 1024 x 4 (whole pages, 1 CTA/SM), 3 = 256 x 4 with 5 CTAs/SM (51 registers), 4 = 256 x 4
 // (quarter pages, 4 CTAs/SM).  Measured 1e8 x 1e7, whole operator: 4.69 / 4.92 / 4.95 / 5.00 / 4.84 ms: the kernel waits
 // on L2 round trips, more resident warps beat more rows per thread.
-int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2) {
+int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
+                                long long dense_lo, uint32_t dense_width) {
     static int shape = -1;
     if (shape < 0) {
         const char *e = getenv("NQE_JA_PROBE_SHAPE");
         shape = e ? atoi(e) : 0;
     }
     switch (shape) {
-    case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2);
-    case 2: return ja_probe_scatter_launch_shape<1024, 4, 1>(ctx, in, out, jt, P2);
-    case 3: return ja_probe_scatter_launch_shape<256, 4, 5>(ctx, in, out, jt, P2);
-    case 4: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2);
-    default: return ja_probe_scatter_launch_shape<256, 2, 6>(ctx, in, out, jt, P2);
+    case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2, dense_lo, dense_width);
+    case 2: return ja_probe_scatter_launch_shape<1024, 4, 1>(ctx, in, out, jt, P2, dense_lo, dense_width);
+    case 3: return ja_probe_scatter_launch_shape<256, 4, 5>(ctx, in, out, jt, P2, dense_lo, dense_width);
+    case 4: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2, dense_lo, dense_width);
+    default: return ja_probe_scatter_launch_shape<256, 2, 6>(ctx, in, out, jt, P2, dense_lo, dense_width);
     }
 }
 
@@ -1508,9 +1513,33 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     if (paged && (vc.validity || (vc.dtype != NQE_INT64 && vc.dtype != NQE_UINT64 && vc.dtype != NQE_FLOAT64))) paged = false;
     int P2 = 0, m2 = 1;
     double est_groups = 0;
+    long long dense_lo = 0;
+    uint32_t dense_width = 0;
     if (paged) {
         rc = nqe_estimate_distinct_u64(ctx, jp.jt.rowpay, left->nrows, &est_groups);
         if (rc == NQE_OK && (est_groups < 2048.0 || !nqe_gp2_plan(ctx, est_groups, &P2, &m2))) paged = false;
+    }
+    static int allow_dense = -1; // knob NQE_AGG_DENSE=0: always hash the group keys
+    if (allow_dense < 0) {
+        const char *e = getenv("NQE_AGG_DENSE");
+        allow_dense = e ? atoi(e) : 1;
+    }
+    if (rc == NQE_OK && paged && allow_dense) {
+        // dense group keys: the build side gives their exact range, so the re-split goes by key range and the groups are
+        // aggregated in directly indexed shared-memory tables (no key compares, no inserts)
+        long long lo, hi;
+        rc = nqe_minmax_i64(ctx, jp.jt.rowpay, left->nrows, &lo, &hi);
+        if (rc == NQE_OK && lo <= hi) {
+            const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
+            const unsigned long long per_part = (range + ctx->sm_count - 1) / ctx->sm_count;
+            if (range < (1ull << 32) && (double)range <= 4.0 * est_groups + 1024.0 && per_part <= NQE_GP2_DENSE_MAX_WIDTH &&
+                ctx->sm_count <= PS_MAX_PARTS) {
+                dense_lo = lo;
+                dense_width = (uint32_t)(per_part < 64 ? 64 : per_part);
+                P2 = (int)((range + dense_width - 1) / dense_width);
+                m2 = ctx->sm_count / P2;
+            }
+        }
     }
     if (rc == NQE_OK && paged) {
         const size_t table_bytes = (size_t)jp.jt.cap * 16;
@@ -1528,13 +1557,13 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             DevProgramSet none;
             memset(&none, 0, sizeof none);
             rc = ps_split_launch<false, PartBySlotRange>(ctx, s1, sa, PartBySlotRange{(uint64_t)P1}, none, ap.status);
-            if (rc == NQE_OK) rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2);
+            if (rc == NQE_OK) rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
         }
         uint64_t capacity = nqe_agg_capacity(est_groups);
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
             rc = nqe_agg_table_create(ctx, &ap, capacity);
             if (rc != NQE_OK) break;
-            rc = nqe_gp2_aggregate(ctx, s2, ap, m2, need);
+            rc = nqe_gp2_aggregate(ctx, s2, ap, m2, need, dense_lo, dense_width);
             if (rc != NQE_OK) break;
             cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {

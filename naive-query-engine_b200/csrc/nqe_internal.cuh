@@ -188,6 +188,6 @@ int32_t nqe_compile_exprs(nqe_ctx *ctx, const nqe_table *in, const nqe_expr *con
                           DevProgramSet *set, ExprInfo *info);
 
 // kernels' device status word bits
-enum : uint32_t { DEV_ERR_DIV0 = 1u, DEV_ERR_OVERFLOW = 2u, DEV_ERR_TABLE_FULL = 4u, DEV_ERR_CAPACITY = 8u };
+enum : uint32_t { DEV_ERR_DIV0 = 1u, DEV_ERR_OVERFLOW = 2u, DEV_ERR_TABLE_FULL = 4u, DEV_ERR_CAPACITY = 8u, DEV_ERR_RANGE = 16u };
 
 uint64_t nqe_next_pow2(uint64_t x);

@@ -175,6 +175,24 @@ struct PartByHash { // partition = high 32 bits of the key's hash, range-reduced
         return (int)__umulhi((uint32_t)(nqe_mix64(key) >> 32), P);
     }
 };
+// Dense integer keys (surrogate ids, dictionary codes, `x % n`): partition = key RANGE, so that a partition's keys are
+// the consecutive integers [lo + p * width, lo + (p + 1) * width) and its groups can be aggregated in a directly
+// indexed table.  `range` = hi - lo + 1 as the caller believes it to be: a key outside raises DEV_ERR_RANGE (the caller
+// then falls back to hashing) and is parked in partition 0, where the aggregator sends it to the global table.
+struct PartByRange {
+    long long lo;
+    unsigned long long range;
+    uint32_t width;
+    uint32_t *status;
+    __device__ __forceinline__ int operator()(unsigned long long key) const {
+        const unsigned long long d = key - (unsigned long long)lo;
+        if (d >= range) {
+            atomicOr(status, DEV_ERR_RANGE);
+            return 0;
+        }
+        return (int)((uint32_t)d / width); // range < 2^32 (checked on the host)
+    }
+};
 
 // Tile shapes of the split kernel (knob NQE_PS_SPLIT_SHAPE): 0 (default) = 256 threads x 8 rows (2048-row tiles,
 // 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM), 2 = 1024 x 4 (4096-row tiles, 1 CTA/SM), 3 = 256 x 8 with 5

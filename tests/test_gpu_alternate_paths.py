@@ -21,6 +21,7 @@ CASES = [
     ({"NQE_JOINAGG_PAGED": "0"}, "join_aggregate_paged_large"),
     ({"NQE_AGG_PART": "0"}, "group_by_one_value_column"),
     ({"NQE_AGG_PART_MIN_ROWS": "1000"}, "group_by"),
+    ({"NQE_AGG_DENSE": "0"}, "group_by_one_value or group_by_dense or paged or group_key"),
     ({"NQE_JOIN_PART_MIN_ROWS": "1000", "NQE_JOIN_PART_MIN_MB": "0"}, "hash_join or join_aggregate or golden_readme"),
     ({"NQE_JA_PROBE_SHAPE": "1", "NQE_PS_SPLIT_SHAPE": "1"}, "paged or group_by_one_value or group_key"),
     ({"NQE_JA_PROBE_SHAPE": "2", "NQE_PS_SPLIT_SHAPE": "2"}, "paged or group_by_one_value or group_key"),

@@ -852,6 +852,41 @@ def test_group_key_extension(n, groups):
         x.free()
 
 
+def test_group_by_dense_keys_with_outliers_the_sample_misses():
+    """Dense-key mode of the paged group-by (keys split by RANGE, directly indexed shared-memory tables) is chosen from a
+    strided sample; keys outside the sampled range (here: far outliers and i64::MIN on rows the stride skips) must be
+    detected by the split and answered by falling back to hashing -- same result either way."""
+    import ctypes as C
+    import pyarrow as pa
+    nq = G.nq
+    rng = np.random.default_rng(99)
+    n, groups = 5_000_000, 30_000
+    k = rng.integers(0, groups, n).astype(np.int64) + 1000
+    v = np.round(rng.normal(0, 100, n), 4)
+    for outliers in (False, True):
+        kk = k.copy()
+        if outliers:  # the sample reads rows 0, 4, 8, ... (n / 2^20 = 4): odd rows are never sampled
+            odd = rng.integers(0, n // 2, 40) * 2 + 1
+            kk[odd[:20]] = 10**15 + np.arange(20)
+            kk[odd[20:30]] = -7
+            kk[odd[30:]] = np.iinfo(np.int64).min
+        t = nq.DeviceTable.from_arrow(pa.RecordBatch.from_arrays([pa.array(kk), pa.array(v)], names=["k", "v"]))
+        ke, keep = nq.ColumnExpr.try_create(None, 0).to_expr(t.names)
+        aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(o, c) for o, c in [(5, 0), (0, 1), (1, 1), (3, 1), (4, 1)]])
+        h = C.c_void_p()
+        t.ctx.check(t.ctx.lib.nqe_hash_aggregate(t.ctx.h, t.h, C.pointer(ke), aggs, 5, C.byref(h)))
+        out = nq.DeviceTable(t.ctx, h, ["key", "count", "sum", "min", "max"]).to_arrow()
+        uk, inv = np.unique(kk, return_inverse=True)
+        o = np.argsort(out.column(0).to_numpy())
+        assert np.array_equal(out.column(0).to_numpy()[o], uk)
+        assert np.array_equal(out.column(1).to_numpy()[o], np.bincount(inv).astype(np.uint64))
+        assert np.allclose(out.column(2).to_numpy()[o], np.bincount(inv, weights=v), rtol=SUM_REL, atol=1e-6)
+        mn = np.full(len(uk), np.inf); mx = np.full(len(uk), -np.inf)
+        np.minimum.at(mn, inv, v); np.maximum.at(mx, inv, v)
+        assert np.array_equal(out.column(3).to_numpy()[o], mn) and np.array_equal(out.column(4).to_numpy()[o], mx)
+        t.free()
+
+
 def test_group_by_expression_key_and_special_values():
     nan, inf = float("nan"), float("inf")
     b = O.Batch(["k", "v"], [O.col("i64", [1, 1, None, 2, 3, 3, -2**63, -2**63, 4]),
