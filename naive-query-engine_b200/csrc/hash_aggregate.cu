@@ -191,6 +191,11 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
     const unsigned npg = (unsigned)((rows_p + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
     const unsigned last_fill = (unsigned)(rows_p - ((unsigned long long)(npg ? npg - 1 : 0) << PS_PAGE_SHIFT)); // rows of the last page
     const unsigned long long dense_base = (unsigned long long)dense.lo + (unsigned long long)p * dense.width; // key of slot 0
+    // DENSE: a partition has only `width` groups but ~4096 rows in flight per CTA, i.e. several concurrent updates per
+    // group (measured: ~40 % of the sum CASes lose).  The table is therefore replicated GA_SLOTS / width times and the
+    // warps spread over the copies; the copies are merged in the flush.
+    const unsigned copies = DENSE ? (dense.width ? (unsigned)GA_SLOTS / dense.width : 1u) : 1u;
+    const unsigned copy_off = DENSE ? ((unsigned)warp % copies) * dense.width : 0u;
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
         if (!DENSE) keys[i] = EMPTY_KEY;
         sm.mm[i] = make_ulonglong2(~0ull, 0ull);   // identities of min / max in the ordered encoding
@@ -246,7 +251,7 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
 #pragma unroll
             for (int j = 0; j < GA_K; j++) {
                 const unsigned long long d = key[j] - dense_base;
-                slot[j] = ((live >> j) & 1u) && d < (unsigned long long)dense.width ? (unsigned)d : GA_NONE; // outside: global table
+                slot[j] = ((live >> j) & 1u) && d < (unsigned long long)dense.width ? (unsigned)d + copy_off : GA_NONE; // outside: global table
             }
         } else {
             // ---- branch-free lookup: both buckets of a row, then compares (two rows at a time: registers)
@@ -375,9 +380,39 @@ gp2_aggregate_kernel(const __grid_constant__ PagedStreams st, const __grid_const
     }
     __syncthreads();
     // partial states of this CTA -> global table
+    if (DENSE) {
+        for (unsigned i = tid; i < dense.width; i += GA_THREADS) {
+            unsigned long long c = 0, mn = ~0ull, mx = 0ull;
+            double sum = 0.0;
+            for (unsigned k = 0; k < copies; k++) { // merge the copies
+                const unsigned sl = k * dense.width + i;
+                const unsigned ck = sm.cnt[sl];
+                if (!ck) continue;
+                c += ck;
+                sum += __longlong_as_double((long long)sm.sf[sl].x);
+                const ulonglong2 x = sm.mm[sl];
+                mn = x.x < mn ? x.x : mn;
+                mx = x.y > mx ? x.y : mx;
+            }
+            if (!c) continue;
+            Sector0 s0;
+            unsigned long long *rec = find_slot(ap, dense_base + (unsigned long long)i, &s0);
+            if (!rec) continue; // table full: flagged, the host grows the table and repeats this kernel
+            for (int s = 0; s < ap.n_states; s++) {
+                unsigned long long *w = rec + ap.st_off[s];
+                switch (ap.st_kind[s]) {
+                case ST_CNT: red_add_u64(w, c); break;
+                case ST_SUM: red_add_f64(w, sum); break;
+                case ST_MIN: red_min_u64(w, mn); break;
+                default: red_max_u64(w, mx); break;
+                }
+            }
+        }
+        return;
+    }
     for (int i = tid; i < GA_SLOTS; i += GA_THREADS) {
-        const unsigned long long key = DENSE ? dense_base + (unsigned long long)i : keys[i];
-        if (DENSE ? sm.cnt[i] == 0u : key == EMPTY_KEY) continue;
+        const unsigned long long key = keys[i];
+        if (key == EMPTY_KEY) continue;
         Sector0 s0;
         unsigned long long *rec = find_slot(ap, key, &s0);
         if (!rec) continue; // table full: flagged, the host grows the table and repeats this kernel
@@ -955,7 +990,8 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                     PsSplitArgs sa{simple ? (const unsigned long long *)ps.cols[key_slot].values : nullptr,
                                    (const unsigned long long *)vc.values, n, gp_dtype};
                     if (dense_width) {
-                        const PartByRange part{dense_lo, (unsigned long long)key_minmax[1] - (unsigned long long)key_minmax[0] + 1ull, dense_width, ap.status};
+                        const PartByRange part{dense_lo, (unsigned long long)key_minmax[1] - (unsigned long long)key_minmax[0] + 1ull, dense_width,
+                                               ps_div_magic(dense_width), ap.status};
                         if (simple) rc = ps_split_launch<false, PartByRange>(ctx, streams, sa, part, ps, ap.status);
                         else rc = ps_split_launch<true, PartByRange>(ctx, streams, sa, part, ps, ap.status);
                     } else {

@@ -870,6 +870,7 @@ ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_co
     extern __shared__ __align__(128) unsigned char jp_smem_raw[];
     JpSmem<T, K> &sm = *reinterpret_cast<JpSmem<T, K> *>(jp_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t dense_magic = dense_width ? ps_div_magic(dense_width) : 0u;
     if (tid == 0) {
         unsigned acc = 0;
         for (int p = 0; p < in.P; p++) {
@@ -933,7 +934,7 @@ ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_co
         for (int j = 0; j < K; j++) {
             if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
             // dense group keys (their exact range is known from the build side): partition = key range, else key hash
-            pid[j] = dense_width ? (int)((uint32_t)(grp[j] - (unsigned long long)dense_lo) / dense_width)
+            pid[j] = dense_width ? (int)ps_div((uint32_t)(grp[j] - (unsigned long long)dense_lo), dense_width, dense_magic)
                                  : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
             if (!((live >> j) & 1u)) pid[j] = 0;
         }

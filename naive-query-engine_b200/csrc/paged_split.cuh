@@ -179,10 +179,17 @@ struct PartByHash { // partition = high 32 bits of the key's hash, range-reduced
 // the consecutive integers [lo + p * width, lo + (p + 1) * width) and its groups can be aggregated in a directly
 // indexed table.  `range` = hi - lo + 1 as the caller believes it to be: a key outside raises DEV_ERR_RANGE (the caller
 // then falls back to hashing) and is parked in partition 0, where the aggregator sends it to the global table.
+// d / width for d < 2^32 without a division: magic = ceil(2^32 / width) overshoots the quotient by at most one
+__host__ __device__ __forceinline__ uint32_t ps_div_magic(uint32_t width) { return (uint32_t)((0x100000000ull + width - 1) / width); }
+__device__ __forceinline__ uint32_t ps_div(uint32_t d, uint32_t width, uint32_t magic) {
+    uint32_t q = __umulhi(d, magic);
+    q -= (unsigned long long)q * width > d ? 1u : 0u;
+    return q;
+}
 struct PartByRange {
     long long lo;
     unsigned long long range;
-    uint32_t width;
+    uint32_t width, magic; // magic = ps_div_magic(width)
     uint32_t *status;
     __device__ __forceinline__ int operator()(unsigned long long key) const {
         const unsigned long long d = key - (unsigned long long)lo;
@@ -190,7 +197,7 @@ struct PartByRange {
             atomicOr(status, DEV_ERR_RANGE);
             return 0;
         }
-        return (int)((uint32_t)d / width); // range < 2^32 (checked on the host)
+        return (int)ps_div((uint32_t)d, width, magic); // range < 2^32 (checked on the host)
     }
 };
 
