@@ -517,11 +517,13 @@ __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int6
                                   int64_t n_sample, uint32_t *bitmap, uint32_t bits_mask, uint32_t *status, unsigned int *bins,
                                   long long *minmax) {
     __shared__ unsigned int s_bins[AGG_SKEW_BINS];
+    __shared__ long long s_min[8], s_max[8];
     long long kmin = LLONG_MAX, kmax = LLONG_MIN;
     for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x) s_bins[b] = 0;
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sample) {
+    // grid-stride over the sample: a few hundred CTAs, so that the per-CTA histogram / min / max reach global memory
+    // with a few thousand atomics instead of one set per 256 samples (that was 0.11 ms of same-address atomics)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sample; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = i * stride;
         RowRegs<1> key;
         run_program<1>(ps, 0, e, 1, e < n_rows ? 1u : 0u, 0u, 0u, key, status);
@@ -530,7 +532,9 @@ __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int6
             const uint32_t h = (uint32_t)(hh >> 32) & bits_mask;
             atomicOr(bitmap + (h >> 5), 1u << (h & 31));
             atomicAdd(&s_bins[hh >> 56], 1u);
-            kmin = kmax = (long long)key.v[0];
+            const long long k = (long long)key.v[0];
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
         }
     }
 #pragma unroll
@@ -539,11 +543,21 @@ __global__ void agg_sample_kernel(const __grid_constant__ DevProgramSet ps, int6
         kmin = a < kmin ? a : kmin;
         kmax = b > kmax ? b : kmax;
     }
-    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
-        atomicMin(minmax, kmin);
-        atomicMax(minmax + 1, kmax);
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = kmin;
+        s_max[threadIdx.x >> 5] = kmax;
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+            kmin = s_min[w] < kmin ? s_min[w] : kmin;
+            kmax = s_max[w] > kmax ? s_max[w] : kmax;
+        }
+        if (kmin <= kmax) {
+            atomicMin(minmax, kmin);
+            atomicMax(minmax + 1, kmax);
+        }
+    }
     for (int b = threadIdx.x; b < AGG_SKEW_BINS; b += blockDim.x)
         if (s_bins[b]) atomicAdd(bins + b, s_bins[b]);
 }
@@ -913,7 +927,9 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
                 cudaMemsetAsync(bm, 0, bits / 8 + AGG_SKEW_BINS * 4, ctx->stream);
                 cudaMemcpyAsync(d_minmax, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, ctx->stream);
                 cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
-                agg_sample_kernel<<<(unsigned)((n_sample + 255) / 256), 256, 0, ctx->stream>>>(
+                unsigned sgrid = (unsigned)((n_sample + 255) / 256);
+                if (sgrid > (unsigned)ctx->sm_count * 4) sgrid = (unsigned)ctx->sm_count * 4;
+                agg_sample_kernel<<<sgrid, 256, 0, ctx->stream>>>(
                     ps, n, stride, n_sample, (uint32_t *)bm, bits - 1, ap.status, bins, d_minmax);
                 popcount_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t *)bm, bits / 32, (unsigned long long *)ctx->d_scratch);
                 ctx->launches += 2;
