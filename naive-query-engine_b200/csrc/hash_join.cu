@@ -1487,15 +1487,15 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         const char *e = getenv("NQE_JOIN_ROWPAY");
         allow_rowpay = e ? atoi(e) : 1;
     }
-    int32_t rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
-    jp.group_in_slot = jp.jt.rowpay ? 1 : 0;
     jp.probe_keys = (const unsigned long long *)right->cols[right_key].values;
     jp.n_probe = right->nrows;
-    nqe_table *t;
-    nqe_table_new(ctx, 0, &t);
+    int32_t rc = NQE_OK;
 
     // ---- paged path (see "Fused join -> group-by over paged streams" above): unique build keys, the group key rides
-    // in the slots, every aggregate reads ONE NULL-free 8-byte probe-side column
+    // in the slots, every aggregate reads ONE NULL-free 8-byte probe-side column.  Everything but "unique build keys,
+    // no payload collision" is known before the build, and the first split depends only on the table's SIZE: it is
+    // started on the auxiliary stream and runs beside the build (if the build then disqualifies the plan the split is
+    // simply dropped).
     static int allow_paged = -1;
     static size_t l2_budget = 0;
     if (allow_paged < 0) {
@@ -1507,7 +1507,8 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         e = getenv("NQE_JA_PART_MB");
         l2_budget = (size_t)(e && atoi(e) > 0 ? atoi(e) : 6) << 20;
     }
-    bool paged = rc == NQE_OK && allow_paged && jp.jt.rowpay && !jp.jt.has_dups && jp.n_probe >= join_part_min_rows() && ap.n_states > 0;
+    const DevColumn *gc = only_group_from_build && allow_rowpay ? &left->cols[group_column] : nullptr;
+    bool paged = allow_paged && gc && !gc->validity && jp.n_probe >= join_part_min_rows() && ap.n_states > 0 && left->nrows > 0;
     int need = 0;
     for (int q = 0; q < ap.n_states && paged; q++) {
         if (ap.st_src[q] != ap.st_src[0]) paged = false;
@@ -1520,7 +1521,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     long long dense_lo = 0;
     uint32_t dense_width = 0;
     if (paged) {
-        rc = nqe_estimate_distinct_u64(ctx, jp.jt.rowpay, left->nrows, &est_groups);
+        rc = nqe_estimate_distinct_u64(ctx, (const unsigned long long *)gc->values, left->nrows, &est_groups);
         if (rc == NQE_OK && (est_groups < 2048.0 || !nqe_gp2_plan(ctx, est_groups, &P2, &m2))) paged = false;
     }
     static int allow_dense = -1; // knob NQE_AGG_DENSE=0: always hash the group keys
@@ -1532,7 +1533,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         // dense group keys: the build side gives their exact range, so the re-split goes by key range and the groups are
         // aggregated in directly indexed shared-memory tables (no key compares, no inserts)
         long long lo, hi;
-        rc = nqe_minmax_i64(ctx, jp.jt.rowpay, left->nrows, &lo, &hi);
+        rc = nqe_minmax_i64(ctx, (const unsigned long long *)gc->values, left->nrows, &lo, &hi);
         if (rc == NQE_OK && lo <= hi) {
             const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
             const unsigned long long per_part = (range + ctx->sm_count - 1) / ctx->sm_count;
@@ -1545,24 +1546,54 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             }
         }
     }
+    PagedStreams s1, s2;
+    memset(&s1, 0, sizeof s1);
+    memset(&s2, 0, sizeof s2);
+    bool split_started = false;
+    uint32_t *split_status = (uint32_t *)(ctx->d_scratch + 20); // the split's own status word: the build uses words 1..4
     if (rc == NQE_OK && paged) {
-        const size_t table_bytes = (size_t)jp.jt.cap * 16;
+        const size_t table_bytes = (((size_t)((double)left->nrows / 0.5) + 16) & ~(size_t)1) * 16; // = build_table's capacity
         int P1 = (int)((table_bytes + l2_budget - 1) / l2_budget);
         if (P1 < 1) P1 = 1;
         if (P1 > ctx->sm_count) P1 = ctx->sm_count;
         if (P1 > PS_MAX_PARTS) P1 = PS_MAX_PARTS;
-        PagedStreams s1, s2;
-        memset(&s1, 0, sizeof s1);
-        memset(&s2, 0, sizeof s2);
         rc = nqe_ps_create(ctx, jp.n_probe, P1, &s1);
-        if (rc == NQE_OK) rc = nqe_ps_create(ctx, jp.n_probe, P2, &s2);
+        if (rc == NQE_OK && !ctx->s_aux) {
+            if (cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+                rc = nqe_fail(ctx, NQE_ERR_CUDA, "auxiliary stream creation failed");
+        }
         if (rc == NQE_OK) {
-            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            s1.status = split_status;
+            cudaMemsetAsync(split_status, 0, sizeof(uint64_t), ctx->stream);
+            cudaEventRecord(ctx->ev_fork, ctx->stream); // the streams' buffers were allocated in ctx->stream's order
+            cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0);
             const PsSplitArgs sa{jp.probe_keys, (const unsigned long long *)vc.values, jp.n_probe, vc.dtype};
             DevProgramSet none;
             memset(&none, 0, sizeof none);
-            rc = ps_split_launch<false, PartBySlotRange>(ctx, s1, sa, PartBySlotRange{(uint64_t)P1}, none, ap.status);
-            if (rc == NQE_OK) rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->s_aux; // the split's launches go to the auxiliary stream
+            rc = ps_split_launch<false, PartBySlotRange>(ctx, s1, sa, PartBySlotRange{(uint64_t)P1}, none, split_status);
+            ctx->stream = main_stream;
+            cudaEventRecord(ctx->ev_join, ctx->s_aux);
+            split_started = true;
+        }
+    }
+    if (rc == NQE_OK) rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
+    if (split_started) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); // also orders the frees below
+    jp.group_in_slot = jp.jt.rowpay ? 1 : 0;
+    nqe_table *t;
+    nqe_table_new(ctx, 0, &t);
+    if (paged && (rc != NQE_OK || !jp.jt.rowpay || jp.jt.has_dups)) { // duplicate build keys / a payload equal to the free-slot marker
+        paged = false;
+        nqe_ps_destroy(ctx, &s1);
+    }
+    if (rc == NQE_OK && paged) {
+        rc = nqe_ps_create(ctx, jp.n_probe, P2, &s2);
+        if (rc == NQE_OK) {
+            cudaMemsetAsync(ctx->d_scratch, 0, 16 * sizeof(uint64_t), ctx->stream); // not the split's word
+            rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
         }
         uint64_t capacity = nqe_agg_capacity(est_groups);
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {
@@ -1570,18 +1601,18 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             if (rc != NQE_OK) break;
             rc = nqe_gp2_aggregate(ctx, s2, ap, m2, need, dense_lo, dense_width);
             if (rc != NQE_OK) break;
-            cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
                 rc = nqe_fail(ctx, NQE_ERR_CUDA, "join-aggregate kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
                 break;
             }
-            const uint32_t st = (uint32_t)ctx->h_scratch[1];
+            const uint32_t st = (uint32_t)ctx->h_scratch[1] | ((uint32_t)ctx->h_scratch[20] & DEV_ERR_CAPACITY); // [20]: the first split's word
             if (st & DEV_ERR_CAPACITY) { rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: paged stream pool exhausted"); break; }
             if (!(st & DEV_ERR_TABLE_FULL)) break;
             nqe_dev_free(ctx, ap.table);
             ap.table = nullptr;
             capacity *= 8;
-            cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
+            cudaMemsetAsync(ctx->d_scratch, 0, 16 * sizeof(uint64_t), ctx->stream);
             if (attempt == 7) rc = nqe_fail(ctx, NQE_ERR_OOM, "group-by table kept overflowing");
         }
         if (rc == NQE_OK) rc = nqe_agg_extract(ctx, ap, false, left->nrows + 1, t);
@@ -1599,8 +1630,6 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     }
 
     // ---- direct path: one pass over the probe side, group table in L2
-    // groups come from one column of one side    nqe_table *t;
-    nqe_table_new(ctx, 0, &t);
     // groups come from one column of one side: at most that side's row count
     const int64_t side_rows = jp.group_left ? left->nrows : right->nrows;
     uint64_t capacity = nqe_agg_capacity((double)(side_rows < (1 << 18) ? side_rows : (1 << 18)));
