@@ -177,4 +177,8 @@ bool nqe_gp2_plan(nqe_ctx *ctx, double est_groups, int *P, int *m);
 int32_t nqe_gp2_aggregate(nqe_ctx *ctx, const PagedStreams &streams, const AggParams &ap, int m, int need, long long dense_lo = 0,
                           unsigned dense_width = 0);
 constexpr unsigned NQE_GP2_DENSE_MAX_WIDTH = 3072; // = GA_SLOTS
+// partitions of the dense (key-range) split: the fewest whose per-partition range fits the table, but at least a quarter
+// of the SMs (fewer partitions = longer runs and fewer cursor atomics per tile in the split; the aggregator then runs
+// sm_count / P CTAs per partition).  Knob NQE_DENSE_PARTS overrides.
+int nqe_dense_parts(nqe_ctx *ctx, unsigned long long range);
 int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi);

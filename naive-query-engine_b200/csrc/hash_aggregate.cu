@@ -599,6 +599,20 @@ __global__ void minmax_i64_kernel(const long long *col, int64_t n, long long *ou
 
 } // namespace
 
+int nqe_dense_parts(nqe_ctx *ctx, unsigned long long range) {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NQE_DENSE_PARTS");
+        v = e ? atoi(e) : 0;
+    }
+    if (v > 0 && v <= ctx->sm_count) return v;
+    const unsigned long long least = (range + NQE_GP2_DENSE_MAX_WIDTH - 1) / NQE_GP2_DENSE_MAX_WIDTH;
+    int m = least ? (int)((unsigned long long)ctx->sm_count / least) : 4;
+    if (m > 4) m = 4;
+    if (m < 1) m = 1;
+    return ctx->sm_count / m;
+}
+
 int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi) {
     *lo = 0;
     *hi = -1;
@@ -990,7 +1004,7 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             dense_width = 0;
             if (try_dense && key_minmax[0] <= key_minmax[1]) {
                 const unsigned long long range = (unsigned long long)key_minmax[1] - (unsigned long long)key_minmax[0] + 1ull;
-                const unsigned long long per_part = (range + ctx->sm_count - 1) / ctx->sm_count;
+                const unsigned long long per_part = (range + nqe_dense_parts(ctx, range) - 1) / nqe_dense_parts(ctx, range);
                 if (range < (1ull << 32) && (double)range <= 4.0 * est_groups + 1024.0 && per_part <= NQE_GP2_DENSE_MAX_WIDTH &&
                     ctx->sm_count <= PS_MAX_PARTS) {
                     dense_lo = key_minmax[0];

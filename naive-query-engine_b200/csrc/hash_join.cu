@@ -1536,7 +1536,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         rc = nqe_minmax_i64(ctx, (const unsigned long long *)gc->values, left->nrows, &lo, &hi);
         if (rc == NQE_OK && lo <= hi) {
             const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
-            const unsigned long long per_part = (range + ctx->sm_count - 1) / ctx->sm_count;
+            const unsigned long long per_part = (range + nqe_dense_parts(ctx, range) - 1) / nqe_dense_parts(ctx, range);
             if (range < (1ull << 32) && (double)range <= 4.0 * est_groups + 1024.0 && per_part <= NQE_GP2_DENSE_MAX_WIDTH &&
                 ctx->sm_count <= PS_MAX_PARTS) {
                 dense_lo = lo;
