@@ -50,7 +50,15 @@ struct JoinTable {
     // A payload equal to EMPTY_ROW cannot be stored (it marks a free slot): the build reports it and the host
     // rebuilds with row numbers.
     const unsigned long long *rowpay;
-    int32_t rowpay_col, pad;
+    int32_t rowpay_col;
+    // "direct" table (dense unique build keys, e.g. a primary key): no hashing and no key compares -- slot d = key - lo
+    // is ONE 8-byte word, the row word of the build row with that key (EMPTY_ROW: no such key), cap = hi - lo + 1.  A
+    // probe is exactly one random 8-byte read and the table is 8 bytes per key of the range instead of 32 per build
+    // row: 1e7 keys = 80 MB, most of which stays in the 126 MB L2 (scratch/gather_bw.cu: 1e8 random 8-byte reads cost
+    // 0.50 ms out of <= 60 MB, 0.74 ms out of 80 MB, 1.33 ms out of 160 MB, 2.0 ms out of 320 MB), so the probe side
+    // needs no split by slot range.  A duplicate key found while building sends the host back to the hashed table.
+    int32_t direct;
+    long long lo;
 };
 
 struct ColSrc {
@@ -130,6 +138,32 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
     atomicOr(status, DEV_ERR_TABLE_FULL);
 }
 
+__global__ void join_direct_build_kernel(JoinTable jt, const unsigned long long *__restrict__ keys, int64_t n, uint32_t *dupflag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long rowword = jt.rowpay ? jt.rowpay[i] : (unsigned long long)i;
+    if (rowword == EMPTY_ROW) { // only possible for a payload
+        dupflag[2] = 1u;
+        return;
+    }
+    const unsigned long long d = keys[i] - (unsigned long long)jt.lo; // < cap: lo and cap come from the keys' own min / max
+    if (atomicCAS(jt.words + d, EMPTY_ROW, rowword) != EMPTY_ROW) *dupflag = 1u;
+}
+
+// Direct table: one 8-byte read per row, nothing to compare and nothing to walk.
+template <int K>
+__device__ __forceinline__ void probe_direct(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
+                                             unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        slot[j] = key[j] - (unsigned long long)jt.lo;
+        brow[j] = EMPTY_ROW;
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++)
+        if (((want >> j) & 1u) && slot[j] < jt.cap) brow[j] = ld_cg_u64(jt.words + slot[j]);
+}
+
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
 // K rows is issued together (K independent loads in flight; at load factor <= 0.6 most rows
 // resolve there), collisions are then walked one row at a time.  (Advancing the K sequences together -- one
@@ -139,6 +173,10 @@ __global__ void join_build_kernel(JoinTable jt, const unsigned long long *__rest
 template <int K>
 __device__ __forceinline__ void probe_first(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
                                             unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
+    if (jt.direct) {
+        probe_direct<K>(jt, key, want, brow, slot);
+        return;
+    }
     Slot first[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -678,6 +716,10 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
 #pragma unroll
                 for (int j = 0; j < K; j++)
                     if ((emit >> j) & 1u) out[pos[j]] = key[j];
+            } else if (c == pp.jt.rowpay_col) { // the slot's row word IS this column's value
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if ((emit >> j) & 1u) out[pos[j]] = first[j];
             } else {
 #pragma unroll
                 for (int j = 0; j < K; j++)
@@ -972,6 +1014,76 @@ int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const Page
     }
 }
 
+// The same pass over a DIRECT table (dense unique build keys): the table is probed in place -- 8 bytes per key of the
+// range, mostly L2-resident -- so the probe rows are read straight from their columns, no first split: a probe row
+// (fk, value) becomes (group key, value as f64) and goes into the group-by's partitions.
+template <int T, int K, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+ja_direct_scatter_kernel(const __grid_constant__ PagedStreams out, const PsSplitArgs a, const JoinTable jt, uint32_t P2,
+                         long long dense_lo, uint32_t dense_width) {
+    constexpr int TILE = T * K;
+    extern __shared__ __align__(16) unsigned char jd_smem_raw[];
+    PsScatterSmem<T, K> &sm = *reinterpret_cast<PsScatterSmem<T, K> *>(jd_smem_raw);
+    ps_scatter_init(sm);
+    const uint32_t dense_magic = dense_width ? ps_div_magic(dense_width) : 0u;
+    const int64_t num_tiles = (a.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * TILE + threadIdx.x;
+        unsigned long long key[K], val[K], grp[K];
+        uint64_t slot[K];
+        int pid[K];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if (e0 + (int64_t)j * T < a.n) live |= 1u << j;
+#pragma unroll
+        for (int j = 0; j < K; j++) key[j] = ((live >> j) & 1u) ? ld_stream_u64(a.keys + e0 + (int64_t)j * T) : 0ull;
+        probe_direct<K>(jt, key, live, grp, slot);
+#pragma unroll
+        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ps_as_f64_bits(a.val_dtype, ld_stream_u64(a.vals + e0 + (int64_t)j * T)) : 0ull;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
+            pid[j] = dense_width ? (int)ps_div((uint32_t)(grp[j] - (unsigned long long)dense_lo), dense_width, dense_magic)
+                                 : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
+            if (!((live >> j) & 1u)) pid[j] = 0;
+        }
+        ps_scatter_tile<T, K>(out, sm, grp, val, pid, live);
+    }
+}
+
+template <int T, int K, int MINB>
+int32_t ja_direct_scatter_launch_shape(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
+                                       long long dense_lo, uint32_t dense_width) {
+    auto kern = ja_direct_scatter_kernel<T, K, MINB>;
+    const size_t smem = sizeof(PsScatterSmem<T, K>);
+    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = (a.n + (int64_t)T * K - 1) / ((int64_t)T * K);
+    int grid = ctx->sm_count * MINB;
+    if (grid > tiles) grid = (int)tiles;
+    if (grid < 1) return NQE_OK;
+    kern<<<grid, T, smem, ctx->stream>>>(out, a, jt, P2, dense_lo, dense_width);
+    ctx->launches++;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
+}
+// knob NQE_JA_DIRECT_SHAPE: 0 (default) = 256 threads x 8 rows, 4 CTAs/SM (the plain split's shape), 1 = 256 x 4, 6 CTAs/SM,
+// 2 = 512 x 8, 2 CTAs/SM, 3 = 256 x 8, 3 CTAs/SM
+int32_t ja_direct_scatter_launch(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
+                                 long long dense_lo, uint32_t dense_width) {
+    static int shape = -1;
+    if (shape < 0) {
+        const char *e = getenv("NQE_JA_DIRECT_SHAPE");
+        shape = e ? atoi(e) : 0;
+    }
+    switch (shape) {
+    case 1: return ja_direct_scatter_launch_shape<256, 4, 6>(ctx, a, out, jt, P2, dense_lo, dense_width);
+    case 2: return ja_direct_scatter_launch_shape<512, 8, 2>(ctx, a, out, jt, P2, dense_lo, dense_width);
+    case 3: return ja_direct_scatter_launch_shape<256, 8, 3>(ctx, a, out, jt, P2, dense_lo, dense_width);
+    default: return ja_direct_scatter_launch_shape<256, 8, 4>(ctx, a, out, jt, P2, dense_lo, dense_width);
+    }
+}
+
 // smallest probe side that takes the partitioned / paged paths (knob NQE_JOIN_PART_MIN_ROWS; tests and the
 // compute-sanitizer runs lower it so that those kernels run on small inputs)
 int64_t join_part_min_rows() {
@@ -1038,6 +1150,63 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
     return NQE_OK;
 }
 
+// Direct table over dense unique build keys (JoinTable::direct).  *done = false (and nothing allocated) when the keys are
+// not dense enough, not unique, or a payload collides with the free-slot marker: the caller then builds the hashed table.
+// Knobs: NQE_JOIN_DIRECT=0 switches the direct table off, NQE_JOIN_DIRECT_MIN_ROWS (default 16384) is the smallest build
+// side worth the extra min/max pass and its synchronisation.
+int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt, int rowpay_col, bool *done) {
+    *done = false;
+    static int allow = -1;
+    static int64_t min_rows = 0;
+    if (allow < 0) {
+        const char *e = getenv("NQE_JOIN_DIRECT");
+        allow = e ? atoi(e) : 1;
+        e = getenv("NQE_JOIN_DIRECT_MIN_ROWS");
+        min_rows = e ? atoll(e) : 16384;
+    }
+    const int64_t nl = left->nrows;
+    const DevColumn &kc = left->cols[lk];
+    if (!allow || nl < min_rows || nl < 1 || (kc.dtype != NQE_INT64 && kc.dtype != NQE_UINT64)) return NQE_OK;
+    long long lo, hi;
+    NQE_TRY(nqe_minmax_i64(ctx, (const unsigned long long *)kc.values, nl, &lo, &hi));
+    // as two's-complement offsets from the signed minimum the keys of either dtype fall in [0, range)
+    const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
+    if (lo > hi || range == 0 || range > 4ull * (unsigned long long)nl + 1024ull) return NQE_OK; // sparse keys: <= 32 bytes per build row
+    memset(jt, 0, sizeof *jt);
+    jt->key_col = lk;
+    jt->rowpay_col = -1;
+    jt->direct = 1;
+    jt->lo = lo;
+    jt->cap = range;
+    if (rowpay_col >= 0) {
+        const DevColumn &pc = left->cols[rowpay_col];
+        if (!pc.validity && (pc.dtype == NQE_INT64 || pc.dtype == NQE_UINT64 || pc.dtype == NQE_FLOAT64)) {
+            jt->rowpay = (const unsigned long long *)pc.values;
+            jt->rowpay_col = rowpay_col;
+        }
+    }
+    void *slots = nullptr;
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, range * 8));
+    jt->words = (unsigned long long *)slots;
+    uint32_t *dupflag = (uint32_t *)(ctx->d_scratch + 3);
+    cudaMemsetAsync(slots, 0xff, range * 8, ctx->stream); // EMPTY_ROW everywhere
+    join_direct_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, (const unsigned long long *)kc.values, nl, dupflag);
+    ctx->launches++;
+    cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        nqe_dev_free(ctx, slots);
+        return nqe_fail(ctx, NQE_ERR_CUDA, "join build failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if ((uint32_t)ctx->h_scratch[3] || (uint32_t)ctx->h_scratch[4]) { // duplicate keys / payload == free-slot marker
+        nqe_dev_free(ctx, slots);
+        memset(jt, 0, sizeof *jt);
+        cudaMemsetAsync(ctx->d_scratch + 1, 0, 4 * sizeof(uint64_t), ctx->stream);
+        return NQE_OK;
+    }
+    *done = true;
+    return NQE_OK;
+}
+
 void fill_src(ColSrc *s, const DevColumn &c) {
     s->values = c.values;
     s->validity = (const uint32_t *)c.validity;
@@ -1093,7 +1262,15 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
         const char *e = getenv("NQE_JOIN_OVERLAP");
         allow_overlap = e ? atoi(e) : 1;
     }
-    if (part_sizes) {
+    // dense unique build keys: a direct table, probed in place by the general kernel below (no split, no gather pass);
+    // with a single non-key build column its values ride in the table
+    bool direct = false;
+    {
+        const DevColumn *oc = nl == 2 ? &left->cols[1 - left_key] : nullptr;
+        const bool pay = allow_rowpay && oc && !oc->validity && (oc->dtype == NQE_INT64 || oc->dtype == NQE_UINT64 || oc->dtype == NQE_FLOAT64);
+        rc = build_table_direct(ctx, left, left_key, &pp.jt, pay ? 1 - left_key : -1, &direct);
+    }
+    if (rc == NQE_OK && part_sizes && !direct) {
         const size_t table_bytes = ((size_t)((double)left->nrows / 0.5) + 16) * 16;
         int log2p = 1;
         while (log2p < 5 && (table_bytes >> log2p) > l2_budget) log2p++;
@@ -1155,7 +1332,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             split_started = true;
         }
     }
-    if (rc == NQE_OK) rc = build_table(ctx, left, left_key, &pp.jt, rowpay_col, false);
+    if (rc == NQE_OK && !direct) rc = build_table(ctx, left, left_key, &pp.jt, rowpay_col, false);
     if (split_started && allow_overlap) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); // also orders the frees below
     pp.n_left = nl;
     pp.n_right = nr;
@@ -1334,7 +1511,7 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
         return rc;
     }
 
-    if (rc == NQE_OK && pp.jt.rowpay) rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: payload-in-row table outside the partitioned probe");
+    if (rc == NQE_OK && pp.jt.rowpay && !pp.jt.direct) rc = nqe_fail(ctx, NQE_ERR_CUDA, "internal: payload-in-row table outside the partitioned probe");
     nqe_table *t = nullptr;
     int64_t cap = pp.n_probe > 0 ? pp.n_probe : 1;
     int64_t out_rows = 0;
@@ -1551,7 +1728,10 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     memset(&s2, 0, sizeof s2);
     bool split_started = false;
     uint32_t *split_status = (uint32_t *)(ctx->d_scratch + 20); // the split's own status word: the build uses words 1..4
-    if (rc == NQE_OK && paged) {
+    // dense unique build keys: a direct table (JoinTable::direct) -- no first split, the probe rows are read in place
+    bool direct = false;
+    if (rc == NQE_OK) rc = build_table_direct(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, &direct);
+    if (rc == NQE_OK && paged && !direct) {
         const size_t table_bytes = (((size_t)((double)left->nrows / 0.5) + 16) & ~(size_t)1) * 16; // = build_table's capacity
         int P1 = (int)((table_bytes + l2_budget - 1) / l2_budget);
         if (P1 < 1) P1 = 1;
@@ -1580,7 +1760,7 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
             split_started = true;
         }
     }
-    if (rc == NQE_OK) rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
+    if (rc == NQE_OK && !direct) rc = build_table(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, true);
     if (split_started) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); // also orders the frees below
     jp.group_in_slot = jp.jt.rowpay ? 1 : 0;
     nqe_table *t;
@@ -1593,7 +1773,12 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         rc = nqe_ps_create(ctx, jp.n_probe, P2, &s2);
         if (rc == NQE_OK) {
             cudaMemsetAsync(ctx->d_scratch, 0, 16 * sizeof(uint64_t), ctx->stream); // not the split's word
-            rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
+            if (direct) {
+                const PsSplitArgs sa{jp.probe_keys, (const unsigned long long *)vc.values, jp.n_probe, vc.dtype};
+                rc = ja_direct_scatter_launch(ctx, sa, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
+            } else {
+                rc = ja_probe_scatter_launch(ctx, s1, s2, jp.jt, (uint32_t)P2, dense_lo, dense_width);
+            }
         }
         uint64_t capacity = nqe_agg_capacity(est_groups);
         for (int attempt = 0; rc == NQE_OK && attempt < 8; attempt++) {

@@ -26,6 +26,13 @@ CASES = [
     ({"NQE_JA_PROBE_SHAPE": "1", "NQE_PS_SPLIT_SHAPE": "1"}, "paged or group_by_one_value or group_key"),
     ({"NQE_JA_PROBE_SHAPE": "2", "NQE_PS_SPLIT_SHAPE": "2"}, "paged or group_by_one_value or group_key"),
     ({"NQE_JA_PROBE_SHAPE": "4", "NQE_PS_SPLIT_SHAPE": "4"}, "paged or group_by_one_value or group_key"),
+    # direct join table (dense unique build keys): on every small join of the suite (duplicates, sparse keys and payload
+    # collisions fall back to the hashed table); switched off, the dense-key inputs go through the hashed / paged paths
+    ({"NQE_JOIN_DIRECT_MIN_ROWS": "1"}, "hash_join or join_aggregate or golden_readme or multi_batch or run_sql"),
+    ({"NQE_JOIN_DIRECT": "0"}, "direct_table"),
+    ({"NQE_JA_DIRECT_SHAPE": "1"}, "join_aggregate_direct_table"),
+    ({"NQE_JA_DIRECT_SHAPE": "2"}, "join_aggregate_direct_table"),
+    ({"NQE_JA_DIRECT_SHAPE": "3"}, "join_aggregate_direct_table"),
 ]
 
 

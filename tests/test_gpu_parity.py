@@ -692,6 +692,113 @@ def test_hash_join_partitioned_probe_nullable_probe_key():
     assert np.array_equal(got.column(3).to_numpy(), b[m])
 
 
+def _np_unique_key_join(keys, fk):
+    """(match mask over the probe rows, build row of every match) for unique build keys"""
+    order = np.argsort(keys, kind="stable")
+    sk = keys[order]
+    idx = np.minimum(np.searchsorted(sk, fk), len(keys) - 1)
+    m = sk[idx] == fk
+    return m, order[idx[m]]
+
+
+def _dense_keys(rng, nl, lo, holes=True):
+    """unique keys out of [lo, lo + range): a permutation with (holes) about a third of the range unused"""
+    span = nl + nl // 2 if holes else nl
+    return (rng.permutation(span)[:nl] + lo).astype(np.int64)
+
+
+@pytest.mark.parametrize("n_pay,variant", [(1, "plain"), (1, "poison"), (1, "negative"), (2, "plain"), (2, "nullable"), (0, "plain")])
+def test_hash_join_direct_table(n_pay, variant):
+    """Dense unique build keys -> the direct table (hash_join.cu JoinTable::direct): slot = key - min, one 8-byte read
+    per probe row, probed in place by the general kernel.  Probe keys hit present keys, holes inside the range and keys
+    below / above it.  n_pay == 1: the payload rides in the table (poison: a payload equals the free-slot marker, so the
+    host falls back to the hashed table); 2: row numbers + gathers, with a nullable and a Boolean build column."""
+    import pyarrow as pa
+    rng = np.random.default_rng(1000 + n_pay + len(variant))
+    nl, nr = 300_000, 2_000_003
+    lo = -123_456_789 if variant == "negative" else 5_000
+    keys = _dense_keys(rng, nl, lo)
+    fk = rng.integers(lo - nl // 4, lo + 2 * nl, nr).astype(np.int64)  # present keys, holes, out of range on both sides
+    b = rng.normal(0, 10, nr)
+    pays = [rng.integers(-1 << 40, 1 << 40, nl).astype(np.int64) for _ in range(n_pay)]
+    if variant == "poison":
+        pays[0][rng.integers(0, nl, 20)] = -1
+    arrays = [pa.array(keys)] + [pa.array(p_) for p_ in pays]
+    names = ["k"] + [f"p{i}" for i in range(n_pay)]
+    pmask = flag = None
+    if variant == "nullable":
+        pmask = rng.random(nl) < 0.2
+        arrays[1] = pa.array(pays[0], mask=pmask)
+        flag = rng.random(nl) < 0.5
+        arrays.append(pa.array(flag))
+        names.append("flag")
+    L = pa.RecordBatch.from_arrays(arrays, names=names)
+    R = pa.RecordBatch.from_arrays([pa.array(fk), pa.array(b)], names=["fk", "b"])
+    nq = G.nq
+    join = nq.HashJoin.create(nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None),
+                              nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None), [("k", "fk")], "Inner")
+    got = join.execute()[0]
+    m, brow = _np_unique_key_join(keys, fk)
+    assert 0 < int(m.sum()) < nr and got.num_rows == int(m.sum())
+    assert np.array_equal(got.column(0).to_numpy(), fk[m])
+    for i in range(n_pay):
+        col = got.column(1 + i)
+        if i == 0 and pmask is not None:
+            assert np.array_equal(np.asarray(col.is_null()), pmask[brow])
+            ok = ~pmask[brow]
+            assert np.array_equal(col.to_numpy(zero_copy_only=False)[ok].astype(np.int64), pays[0][brow][ok])
+        else:
+            assert np.array_equal(col.to_numpy(), pays[i][brow]), f"payload {i}"
+    nleft = len(names)
+    if flag is not None:
+        assert np.array_equal(got.column(nleft - 1).to_numpy(zero_copy_only=False), flag[brow])
+    assert np.array_equal(got.column(nleft).to_numpy(), fk[m])
+    assert np.array_equal(got.column(nleft + 1).to_numpy(), b[m])
+
+
+@pytest.mark.parametrize("nr,g,dense_groups", [(6_000_011, 60_000, True), (6_000_011, 150_000, False), (300_007, 5_000, True)])
+def test_join_aggregate_direct_table(nr, g, dense_groups):
+    """Fused join -> group-by over a direct table (dense unique build keys): the probe rows are read in place, become
+    (group key, value) and go straight into the group-by's partitions (ja_direct_scatter_kernel); the small probe side
+    takes the single-pass kernel over the same table.  A quarter of the probe keys miss (holes and out of range)."""
+    import ctypes as C
+    import pyarrow as pa
+    rng = np.random.default_rng(nr % 1000 + g)
+    nl = 2_000_000
+    keys = _dense_keys(rng, nl, -7_000)
+    a = rng.integers(0, g, nl).astype(np.int64)
+    if not dense_groups:
+        a = a * 7919 - 5
+        a[a == -5] = np.iinfo(np.int64).min
+    fk = rng.integers(-7_000 - nl // 8, -7_000 + nl + nl // 2 + nl // 8, nr).astype(np.int64)
+    b = np.round(rng.normal(0, 1000, nr), 6)
+    L = pa.RecordBatch.from_arrays([pa.array(keys), pa.array(a)], names=["k", "a"])
+    R = pa.RecordBatch.from_arrays([pa.array(fk), pa.array(b)], names=["fk", "b"])
+    nq = G.nq
+    lt = nq.ScanPlan.create(nq.MemTable.try_create(L.schema, [L]), None).execute_device()
+    rt = nq.ScanPlan.create(nq.MemTable.try_create(R.schema, [R]), None).execute_device()
+    aggs = (nq._ffi.Agg * 5)(*[nq._ffi.Agg(o, c) for o, c in [(5, 0), (0, 3), (1, 3), (3, 3), (4, 3)]])  # key, count, sum, min, max of b
+    h = C.c_void_p()
+    ctx = lt.ctx
+    ctx.check(ctx.lib.nqe_join_aggregate(ctx.h, lt.h, rt.h, 0, 0, 1, aggs, 5, C.byref(h)))
+    out = nq.DeviceTable(ctx, h, ["key", "count", "sum", "min", "max"]).to_arrow()
+    m, brow = _np_unique_key_join(keys, fk)
+    grp, bv = a[brow], b[m]
+    uk, inv = np.unique(grp, return_inverse=True)
+    key = out.column(0).to_numpy().astype(np.int64)
+    o = np.argsort(key)
+    assert np.array_equal(key[o], uk)
+    cnt = np.bincount(inv, minlength=len(uk))
+    assert np.array_equal(out.column(1).to_numpy()[o], cnt.astype(np.uint64))
+    scale = np.bincount(inv, weights=np.abs(bv), minlength=len(uk))
+    assert np.all(np.abs(out.column(2).to_numpy()[o] - np.bincount(inv, weights=bv, minlength=len(uk))) <= SUM_REL * np.maximum(scale, 1.0))
+    mn = np.full(len(uk), np.inf); mx = np.full(len(uk), -np.inf)
+    np.minimum.at(mn, inv, bv); np.maximum.at(mx, inv, bv)
+    assert np.array_equal(out.column(3).to_numpy()[o], mn) and np.array_equal(out.column(4).to_numpy()[o], mx)
+    lt.free()
+    rt.free()
+
+
 def test_hash_join_unique_build_keys_and_u64():
     rng = np.random.default_rng(9)
     nl, nr = 10_000, 50_000
