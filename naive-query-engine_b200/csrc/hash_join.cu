@@ -150,10 +150,39 @@ __global__ void join_direct_build_kernel(JoinTable jt, const unsigned long long 
     if (atomicCAS(jt.words + d, EMPTY_ROW, rowword) != EMPTY_ROW) *dupflag = 1u;
 }
 
+// streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
+// probed (default policy) is what stays resident
+__device__ __forceinline__ unsigned long long pj_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ld_ef(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_ef(unsigned long long *p, unsigned long long v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
+// table reads of the direct probe: evict_last, so that the 8-byte-per-key table outlives the streams flowing past it
+__device__ __forceinline__ unsigned long long jt_policy_keep() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long ld_keep(const unsigned long long *p, unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // Direct table: one 8-byte read per row, nothing to compare and nothing to walk.
-template <int K>
+template <int K, bool KEEP = false>
 __device__ __forceinline__ void probe_direct(const JoinTable &jt, const unsigned long long (&key)[K], uint32_t want,
                                              unsigned long long (&brow)[K], uint64_t (&slot)[K]) {
+    const unsigned long long pol = KEEP ? jt_policy_keep() : 0ull;
 #pragma unroll
     for (int j = 0; j < K; j++) {
         slot[j] = key[j] - (unsigned long long)jt.lo;
@@ -161,7 +190,7 @@ __device__ __forceinline__ void probe_direct(const JoinTable &jt, const unsigned
     }
 #pragma unroll
     for (int j = 0; j < K; j++)
-        if (((want >> j) & 1u) && slot[j] < jt.cap) brow[j] = ld_cg_u64(jt.words + slot[j]);
+        if (((want >> j) & 1u) && slot[j] < jt.cap) brow[j] = KEEP ? ld_keep(jt.words + slot[j], pol) : ld_cg_u64(jt.words + slot[j]);
 }
 
 // First slot (in probe order) holding `key`, for K probe rows.  The first table probe of all
@@ -258,22 +287,6 @@ struct PartJoin {
     unsigned int *ppos32;           // per probe row (original order): its position in the partitioned order
     unsigned long long *res0;       // per position: build row or payload (EMPTY_ROW: no match)
 };
-
-// streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
-// probed (default policy) is what stays resident
-__device__ __forceinline__ unsigned long long pj_policy() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ unsigned long long ld_ef(const unsigned long long *p, unsigned long long pol) {
-    unsigned long long v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void st_ef(unsigned long long *p, unsigned long long v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
 
 __device__ __forceinline__ int pj_part(unsigned long long key, int log2p) {
     return log2p ? (int)(nqe_mix64(key) >> (64 - log2p)) : 0;
@@ -610,6 +623,9 @@ struct ProbeParams {
     int32_t num_tiles;
 };
 
+#ifndef NQE_LB_WIDE
+#define NQE_LB_WIDE 1
+#endif
 #include "lookback_body.inc"
 
 // one output cell: column c of the joined row (build row | probe row) -> position pos
@@ -633,6 +649,10 @@ __device__ __forceinline__ void emit_row(const ProbeParams &pp, int64_t brow, in
     }
 }
 
+// DIRECT: the table is a direct one (unique keys: no duplicate walks are compiled in); CM (DIRECT only): bit 0 = the
+// streams -- probe columns in, joined columns out -- carry an L2 evict_first policy, bit 1 = the table reads carry
+// evict_last, so that the 8-byte-per-key table stays in the L2 while ~5 GB of rows flow past it.
+template <bool DIRECT, int CM>
 __global__ void __launch_bounds__(HJ_THREADS)
 join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     constexpr int K = HJ_K, TILE = K * HJ_THREADS;
@@ -640,6 +660,12 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     __shared__ unsigned long long s_tile_excl;
     __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long ef = (DIRECT && (CM & 1)) ? pj_policy() : 0ull;
+    auto ld_in = [&](const unsigned long long *p) { return (DIRECT && (CM & 1)) ? ld_ef(p, ef) : (unsigned long long)ld_stream_u64(p); };
+    auto st_out = [&](unsigned long long *p, unsigned long long v) {
+        if (DIRECT && (CM & 1)) st_ef(p, v, ef);
+        else *p = v;
+    };
     while (true) {
         if (tid == 0) s_tile = (int)atomicAdd(pp.ticket, 1u);
         __syncthreads();
@@ -653,10 +679,14 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const int64_t e = e0 + (int64_t)j * HJ_THREADS;
-            key[j] = e < pp.n_probe ? ld_stream_u64(pp.probe_keys + e) : 0ull;
+            key[j] = e < pp.n_probe ? ld_in(pp.probe_keys + e) : 0ull;
             if (e < pp.n_probe) inrange |= 1u << j;
         }
-        if (!pp.jt.has_dups) {
+        if (DIRECT) {
+            probe_direct<K, (CM & 2) != 0>(pp.jt, key, inrange, first, slot);
+#pragma unroll
+            for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
+        } else if (!pp.jt.has_dups) {
             probe_first<K>(pp.jt, key, inrange, first, slot);
 #pragma unroll
             for (int j = 0; j < K; j++) cnt[j] = first[j] != EMPTY_ROW;
@@ -715,11 +745,11 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             if (c == pp.jt.key_col && pp.key_from_probe) {
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((emit >> j) & 1u) out[pos[j]] = key[j];
+                    if ((emit >> j) & 1u) st_out(out + pos[j], key[j]);
             } else if (c == pp.jt.rowpay_col) { // the slot's row word IS this column's value
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((emit >> j) & 1u) out[pos[j]] = first[j];
+                    if ((emit >> j) & 1u) st_out(out + pos[j], first[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < K; j++)
@@ -733,12 +763,12 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
 #pragma unroll
                 for (int j = 0; j < K; j++) {
                     v[j] = 0;
-                    if ((emit >> j) & 1u) v[j] = ld_stream_u64((const unsigned long long *)src.values + e0 + (int64_t)j * HJ_THREADS);
+                    if ((emit >> j) & 1u) v[j] = ld_in((const unsigned long long *)src.values + e0 + (int64_t)j * HJ_THREADS);
                 }
                 unsigned long long *out = (unsigned long long *)pp.out_values[pp.n_left + c];
 #pragma unroll
                 for (int j = 0; j < K; j++)
-                    if ((emit >> j) & 1u) out[pos[j]] = v[j];
+                    if ((emit >> j) & 1u) st_out(out + pos[j], v[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < K; j++)
@@ -747,7 +777,7 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
             }
         }
         // ---- duplicate build keys: the remaining matches of a row, ascending build row
-        if (pp.jt.has_dups) {
+        if (!DIRECT && pp.jt.has_dups) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 unsigned long long brow = first[j];
@@ -761,6 +791,221 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
         }
         __syncthreads();
     }
+}
+
+// ---- direct table, plain 8-byte columns: probe pass + staged emit pass -------------------------------------------
+// join_probe_kernel above is one pass with a decoupled look-back, and it is slow on 1e8 rows (2.3 ms where the traffic is
+// worth 0.8 ms) for two reasons that were measured one by one (profiles/README_r02.md):
+//  * the look-back: all ~600 resident tiles are in the same phase, so a tile's walk crosses hundreds of unresolved
+//    predecessors (37 % of the stall samples sit at the barrier behind the walking warp);
+//  * random table reads and heavy store traffic in ONE kernel: a kernel with the reads alone takes 0.88 ms, with the
+//    stores alone 0.81 ms (5.9 TB/s), with both 2.31 ms -- the table reads queue behind the SM's outstanding stores in the
+//    memory pipeline and every tile waits for them at its barrier.  L2 policies (evict_first streams, evict_last table,
+//    a persisting set-aside) change nothing.
+// So the work is cut where the dependency is: every CTA owns a CONTIGUOUS chunk of tiles;
+//   pass 1 (join_direct_probe_kernel) reads the keys, probes the table, writes the row words as a stream and counts
+//          the chunk's matches -- random reads, almost no stores, no barriers;
+//   pass 2 (join_direct_emit_kernel) starts at the sum of the earlier chunks' counts and walks its chunk with a running
+//          base: the probe-side columns and the row-word stream of its next tiles are in flight as cp.async.bulk
+//          copies into a shared-memory ring, ranks come from ballots (a row has 0 or 1 match), one barrier per tile,
+//          no global loads in the loop at all.
+constexpr int DE_MAX = 4; // columns per side
+struct DirectEmitParams {
+    JoinTable jt;
+    int64_t n_probe;
+    int32_t nl, nr, left_key, right_key;
+    const unsigned long long *right[DE_MAX]; // probe-side columns
+    unsigned long long *out[2 * DE_MAX];
+    unsigned long long *rowwords;            // per probe row: the table's row word (EMPTY_ROW: no match), written by pass 1
+    unsigned long long *chunk_count, *out_count;
+    int32_t num_tiles, tiles_per_chunk, stages, pad;
+};
+
+template <int K>
+__global__ void __launch_bounds__(HJ_THREADS) join_direct_probe_kernel(const __grid_constant__ DirectEmitParams p) {
+    constexpr int T = HJ_THREADS, TILE = T * HJ_K, STEP = T * K;
+    __shared__ unsigned int s_warp[HJ_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * p.tiles_per_chunk;
+    const int64_t t1 = t0 + p.tiles_per_chunk < p.num_tiles ? t0 + p.tiles_per_chunk : p.num_tiles;
+    const int64_t r0 = t0 * TILE, r1 = t1 * TILE < p.n_probe ? t1 * TILE : p.n_probe;
+    const unsigned long long *keys = p.right[p.right_key];
+    const unsigned long long ef = pj_policy();
+    unsigned int cnt = 0;
+    for (int64_t base = r0 + tid; base < r1; base += STEP) {
+        unsigned long long key[K], brow[K];
+        uint64_t slot[K];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int64_t e = base + (int64_t)j * T;
+            key[j] = e < r1 ? ld_ef(keys + e, ef) : 0ull;
+            if (e < r1) live |= 1u << j;
+        }
+        probe_direct<K, false>(p.jt, key, live, brow, slot);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            cnt += brow[j] != EMPTY_ROW;
+            if ((live >> j) & 1u) st_ef(p.rowwords + base + (int64_t)j * T, brow[j], ef);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long total = 0;
+        for (int w = 0; w < HJ_WARPS; w++) total += s_warp[w];
+        p.chunk_count[blockIdx.x] = total;
+    }
+}
+
+// NL build-side columns (the key, and for NL == 2 the one column whose values ride in the table), NR probe-side columns:
+// compile-time, so that every column loop unrolls and the stores need one address computation each.
+template <int K, int NL, int NR>
+__global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const __grid_constant__ DirectEmitParams p) {
+    constexpr int T = HJ_THREADS, TILE = T * K;
+    static_assert(K * HJ_WARPS == 32, "one (row group, warp) count per lane");
+    extern __shared__ __align__(128) unsigned char de_smem[];
+    unsigned long long *full = (unsigned long long *)de_smem, *empty = full + 8; // [stages] each
+    unsigned long long *ring = (unsigned long long *)(de_smem + 128);            // [stages][NR + 1][TILE]: probe columns, row words
+    __shared__ unsigned int s_cnt[2][K * HJ_WARPS];
+    __shared__ unsigned long long s_part[HJ_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = p.stages;
+    const int64_t full_tiles = p.n_probe / TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * p.tiles_per_chunk;
+    const int64_t t1 = t0 + p.tiles_per_chunk < p.num_tiles ? t0 + p.tiles_per_chunk : p.num_tiles;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            nqe_mbar_init(full + s, 1);
+            nqe_mbar_init(empty + s, HJ_WARPS);
+        }
+        nqe_mbar_init_fence();
+    }
+    // first output row of this chunk: the matches of all earlier chunks
+    unsigned long long base = 0;
+    for (int i = tid; i < (int)blockIdx.x; i += T) base += p.chunk_count[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    if (lane == 0) s_part[warp] = base;
+    __syncthreads();
+    base = 0;
+#pragma unroll
+    for (int w = 0; w < HJ_WARPS; w++) base += s_part[w];
+    const unsigned long long ef = pj_policy();
+    auto issue = [&](int64_t tile, int stage) { // thread 0
+        nqe_mbar_arrive_expect_tx(full + stage, (uint32_t)(NR + 1) * TILE * 8u);
+#pragma unroll
+        for (int c = 0; c < NR; c++)
+            nqe_bulk_g2s(ring + ((size_t)stage * (NR + 1) + c) * TILE, p.right[c] + tile * TILE, TILE * 8u, full + stage, ef);
+        nqe_bulk_g2s(ring + ((size_t)stage * (NR + 1) + NR) * TILE, p.rowwords + tile * TILE, TILE * 8u, full + stage, ef);
+    };
+    if (tid == 0)
+        for (int s = 0; s < S; s++)
+            if (t0 + s < t1 && t0 + s < full_tiles) issue(t0 + s, s);
+    uint32_t it = 0;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = t0; tile < t1; tile++, it++) {
+        const bool staged = tile < full_tiles;
+        const unsigned long long *st = ring + (size_t)stage * (NR + 1) * TILE + tid;
+        const int64_t e0 = tile * TILE + tid;
+        unsigned long long key[K], brow[K];
+        if (staged) {
+            nqe_mbar_wait(full + stage, parity);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                key[j] = st[p.right_key * TILE + j * T];
+                brow[j] = st[NR * TILE + j * T];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int64_t e = e0 + (int64_t)j * T;
+                key[j] = e < p.n_probe ? ld_stream_u64(p.right[p.right_key] + e) : 0ull;
+                brow[j] = e < p.n_probe ? ld_stream_u64(p.rowwords + e) : EMPTY_ROW;
+            }
+        }
+        unsigned off[K];
+        uint32_t emit = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const bool m = brow[j] != EMPTY_ROW;
+            const unsigned b = __ballot_sync(0xffffffffu, m);
+            off[j] = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) s_cnt[it & 1u][j * HJ_WARPS + warp] = __popc(b);
+            if (m) emit |= 1u << j;
+        }
+        __syncthreads();
+        // every warp scans the 32 (row group, warp) counts for itself: no second barrier
+        const unsigned mine = s_cnt[it & 1u][lane];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned excl = incl - mine, total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int j = 0; j < K; j++) off[j] += __shfl_sync(0xffffffffu, excl, j * HJ_WARPS + warp);
+#pragma unroll
+        for (int c = 0; c < NL; c++) {
+            unsigned long long *out = p.out[c] + base;
+            const bool is_key = NL == 1 || c == p.left_key; // the build key matched: its value is the probe key
+#pragma unroll
+            for (int j = 0; j < K; j++)
+                if ((emit >> j) & 1u) st_ef(out + off[j], is_key ? key[j] : brow[j], ef);
+        }
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            unsigned long long *out = p.out[NL + c] + base;
+            unsigned long long v[K];
+            if (staged) {
+#pragma unroll
+                for (int j = 0; j < K; j++) v[j] = st[c * TILE + j * T];
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) v[j] = ((emit >> j) & 1u) ? (unsigned long long)ld_stream_u64(p.right[c] + e0 + (int64_t)j * T) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < K; j++)
+                if ((emit >> j) & 1u) st_ef(out + off[j], v[j], ef);
+        }
+        base += total;
+        if (staged) { // hand the stage back; thread 0 refills it with the tile S steps ahead
+            __syncwarp();
+            if (lane == 0) nqe_mbar_arrive(empty + stage);
+            if (tid == 0 && tile + S < t1 && tile + S < full_tiles) {
+                nqe_mbar_wait(empty + stage, parity);
+                issue(tile + S, stage);
+            }
+        }
+        if (++stage == S) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) *p.out_count = base;
+}
+
+template <int NL, int NR>
+int32_t join_direct_emit_launch(nqe_ctx *ctx, DirectEmitParams &de) {
+    de.stages = NR <= 1 ? 3 : 2;
+    const size_t smem = 128 + (size_t)de.stages * (NR + 1) * HJ_K * HJ_THREADS * 8;
+    auto dk = join_direct_emit_kernel<HJ_K, NL, NR>;
+    NQE_CUDA(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int docc = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, dk, HJ_THREADS, smem);
+    int chunks = ctx->sm_count * (docc > 0 ? docc : 1); // one wave of CTAs, a contiguous chunk of tiles each
+    if (chunks > de.num_tiles) chunks = de.num_tiles;
+    de.tiles_per_chunk = (de.num_tiles + chunks - 1) / chunks;
+    chunks = (de.num_tiles + de.tiles_per_chunk - 1) / de.tiles_per_chunk;
+    join_direct_probe_kernel<8><<<chunks, HJ_THREADS, 0, ctx->stream>>>(de);
+    dk<<<chunks, HJ_THREADS, smem, ctx->stream>>>(de);
+    ctx->launches += 2;
+    NQE_CUDA(ctx, cudaGetLastError());
+    return NQE_OK;
 }
 
 // ---- fused join -> group-by aggregate --------------------------------------
@@ -1017,7 +1262,8 @@ int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const Page
 // The same pass over a DIRECT table (dense unique build keys): the table is probed in place -- 8 bytes per key of the
 // range, mostly L2-resident -- so the probe rows are read straight from their columns, no first split: a probe row
 // (fk, value) becomes (group key, value as f64) and goes into the group-by's partitions.
-template <int T, int K, int MINB>
+// CM: bit 0 = the streams (probe rows in, pages out) carry evict_first, bit 1 = the table reads carry evict_last
+template <int T, int K, int MINB, int CM>
 __global__ void __launch_bounds__(T, MINB)
 ja_direct_scatter_kernel(const __grid_constant__ PagedStreams out, const PsSplitArgs a, const JoinTable jt, uint32_t P2,
                          long long dense_lo, uint32_t dense_width) {
@@ -1036,11 +1282,13 @@ ja_direct_scatter_kernel(const __grid_constant__ PagedStreams out, const PsSplit
 #pragma unroll
         for (int j = 0; j < K; j++)
             if (e0 + (int64_t)j * T < a.n) live |= 1u << j;
+        const unsigned long long ef = (CM & 1) ? pj_policy() : 0ull;
+        auto ld_in = [&](const unsigned long long *p) { return (CM & 1) ? ld_ef(p, ef) : (unsigned long long)ld_stream_u64(p); };
 #pragma unroll
-        for (int j = 0; j < K; j++) key[j] = ((live >> j) & 1u) ? ld_stream_u64(a.keys + e0 + (int64_t)j * T) : 0ull;
-        probe_direct<K>(jt, key, live, grp, slot);
+        for (int j = 0; j < K; j++) key[j] = ((live >> j) & 1u) ? ld_in(a.keys + e0 + (int64_t)j * T) : 0ull;
+        probe_direct<K, (CM & 2) != 0>(jt, key, live, grp, slot);
 #pragma unroll
-        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ps_as_f64_bits(a.val_dtype, ld_stream_u64(a.vals + e0 + (int64_t)j * T)) : 0ull;
+        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ps_as_f64_bits(a.val_dtype, ld_in(a.vals + e0 + (int64_t)j * T)) : 0ull;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
@@ -1048,14 +1296,14 @@ ja_direct_scatter_kernel(const __grid_constant__ PagedStreams out, const PsSplit
                                  : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
             if (!((live >> j) & 1u)) pid[j] = 0;
         }
-        ps_scatter_tile<T, K>(out, sm, grp, val, pid, live);
+        ps_scatter_tile<T, K, PsNoHook, (CM & 1) != 0>(out, sm, grp, val, pid, live);
     }
 }
 
-template <int T, int K, int MINB>
+template <int T, int K, int MINB, int CM = 3>
 int32_t ja_direct_scatter_launch_shape(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
                                        long long dense_lo, uint32_t dense_width) {
-    auto kern = ja_direct_scatter_kernel<T, K, MINB>;
+    auto kern = ja_direct_scatter_kernel<T, K, MINB, CM>;
     const size_t smem = sizeof(PsScatterSmem<T, K>);
     NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n + (int64_t)T * K - 1) / ((int64_t)T * K);
@@ -1075,6 +1323,16 @@ int32_t ja_direct_scatter_launch(nqe_ctx *ctx, const PsSplitArgs &a, const Paged
     if (shape < 0) {
         const char *e = getenv("NQE_JA_DIRECT_SHAPE");
         shape = e ? atoi(e) : 0;
+    }
+    static int cm = -1; // knob NQE_JA_DIRECT_CACHE: L2 policies (see the kernel), default 3; applies to the default shape
+    if (cm < 0) {
+        const char *e = getenv("NQE_JA_DIRECT_CACHE");
+        cm = e ? atoi(e) & 3 : 3;
+    }
+    if (shape == 0 && cm != 3) {
+        if (cm == 0) return ja_direct_scatter_launch_shape<256, 8, 4, 0>(ctx, a, out, jt, P2, dense_lo, dense_width);
+        if (cm == 1) return ja_direct_scatter_launch_shape<256, 8, 4, 1>(ctx, a, out, jt, P2, dense_lo, dense_width);
+        return ja_direct_scatter_launch_shape<256, 8, 4, 2>(ctx, a, out, jt, P2, dense_lo, dense_width);
     }
     switch (shape) {
     case 1: return ja_direct_scatter_launch_shape<256, 4, 6>(ctx, a, out, jt, P2, dense_lo, dense_width);
@@ -1352,6 +1610,9 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     // side's slots.  The view's build-key column aliases the probe key values WITHOUT the probe key's bitmap; when the
     // probe key is NULL-free both key outputs read the one staged probe-key column instead.
     const int key_src = right->cols[right_key].validity ? left_key : nl + right_key;
+    // (A direct-table join is a filter/project over the probe side with the build column gathered through the probe key;
+    // running it in the filter/project kernel was tried -- key-indexed gathered columns -- and is much slower, 5.8 vs
+    // 2.5 ms at 1e8 x 1e7: that kernel's 16 worker warps per SM keep too few random reads in flight.)
     // ---- partitioned probe: unique build keys and a table that does not fit in the L2
     bool part = false;
     if (rc == NQE_OK && split_started) {
@@ -1542,13 +1803,66 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
             cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream);
             cudaMemsetAsync(lb, 0, (size_t)(pp.num_tiles + 1) * 8, ctx->stream);
             if (pp.num_tiles > 0) {
-                auto kern = join_probe_kernel;
+                // direct table and nothing but plain 8-byte columns: the staged kernel (knob NQE_JOIN_DIRECT_STAGED=0: the general one)
+                static int allow_staged = -1;
+                if (allow_staged < 0) {
+                    const char *e = getenv("NQE_JOIN_DIRECT_STAGED");
+                    allow_staged = e ? atoi(e) : 1;
+                }
+                // the key and at most the one column that rides in the table on the build side, up to DE_MAX columns on the probe side
+                bool staged = allow_staged && pp.jt.direct && (nl == 1 || (nl == 2 && pp.jt.rowpay)) && nr <= DE_MAX;
+                for (int c = 0; c < nl + nr && staged; c++) {
+                    const DevColumn &src = c < nl ? left->cols[c] : right->cols[c - nl];
+                    if (src.validity || (src.dtype != NQE_INT64 && src.dtype != NQE_UINT64 && src.dtype != NQE_FLOAT64)) staged = false;
+                    if (c >= nl && ((uintptr_t)src.values & 15)) staged = false; // bulk copies read 16-byte aligned columns
+                }
+                if (staged) {
+                    DirectEmitParams de;
+                    memset(&de, 0, sizeof de);
+                    de.jt = pp.jt;
+                    de.n_probe = pp.n_probe;
+                    de.nl = nl;
+                    de.nr = nr;
+                    de.left_key = left_key;
+                    de.right_key = right_key;
+                    for (int c = 0; c < nr; c++) de.right[c] = (const unsigned long long *)right->cols[c].values;
+                    for (int c = 0; c < nl + nr; c++) de.out[c] = (unsigned long long *)pp.out_values[c];
+                    de.out_count = pp.out_count;
+                    de.num_tiles = pp.num_tiles;
+                    de.chunk_count = pp.tile_state; // num_tiles + 1 words: room for one count per chunk
+                    void *rw = nullptr;
+                    rc = nqe_dev_alloc(ctx, &rw, (size_t)pp.n_probe * 8 + 16);
+                    de.rowwords = (unsigned long long *)rw;
+                    if (rc != NQE_OK) break;
+                    switch (nl * 8 + nr) {
+                    case 8 + 1: rc = join_direct_emit_launch<1, 1>(ctx, de); break;
+                    case 8 + 2: rc = join_direct_emit_launch<1, 2>(ctx, de); break;
+                    case 8 + 3: rc = join_direct_emit_launch<1, 3>(ctx, de); break;
+                    case 8 + 4: rc = join_direct_emit_launch<1, 4>(ctx, de); break;
+                    case 16 + 1: rc = join_direct_emit_launch<2, 1>(ctx, de); break;
+                    case 16 + 2: rc = join_direct_emit_launch<2, 2>(ctx, de); break;
+                    case 16 + 3: rc = join_direct_emit_launch<2, 3>(ctx, de); break;
+                    default: rc = join_direct_emit_launch<2, 4>(ctx, de); break;
+                    }
+                    nqe_dev_free(ctx, rw); // stream-ordered: after the two passes
+                } else {
+                static int cm = -1; // knob NQE_JOIN_DIRECT_CACHE: L2 policies of the direct probe (see the kernel), default 3
+                if (cm < 0) {
+                    const char *e = getenv("NQE_JOIN_DIRECT_CACHE");
+                    cm = e ? atoi(e) & 3 : 3;
+                }
+                auto kern = !pp.jt.direct ? join_probe_kernel<false, 0>
+                            : cm == 3     ? join_probe_kernel<true, 3>
+                            : cm == 2     ? join_probe_kernel<true, 2>
+                            : cm == 1     ? join_probe_kernel<true, 1>
+                                          : join_probe_kernel<true, 0>;
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);
                 if (grid > pp.num_tiles) grid = pp.num_tiles;
                 kern<<<grid, HJ_THREADS, 0, ctx->stream>>>(pp);
                 ctx->launches++;
+                }
             }
             cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)

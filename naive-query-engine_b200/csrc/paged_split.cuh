@@ -83,7 +83,8 @@ struct PsNoHook {
 };
 // `after_reads`: called by every thread right after the tile's first barrier, i.e. once the whole CTA has its rows in
 // registers -- where a caller that staged the tile in shared memory hands the buffer back to its producer.
-template <int THREADS, int K, typename Hook = PsNoHook>
+// EF: the page stores carry an L2 evict_first policy (for callers that keep something else resident in the L2).
+template <int THREADS, int K, typename Hook = PsNoHook, bool EF = false>
 __device__ __forceinline__ void ps_scatter_tile(const PagedStreams &ps, PsScatterSmem<THREADS, K> &sm,
                                                 const unsigned long long (&key)[K], const unsigned long long (&val)[K],
                                                 const int (&pid)[K], uint32_t live, const Hook &after_reads = Hook()) {
@@ -149,6 +150,7 @@ __device__ __forceinline__ void ps_scatter_tile(const PagedStreams &ps, PsScatte
         }
     __syncthreads();
     const unsigned total = sm.start[PS_MAX_PARTS];
+    const unsigned long long pol = EF ? nqe_policy_evict_first() : 0ull;
 #pragma unroll
     for (int j = 0; j < K; j++) {
         const unsigned idx = tid + j * THREADS;
@@ -156,7 +158,10 @@ __device__ __forceinline__ void ps_scatter_tile(const PagedStreams &ps, PsScatte
             const int p = sm.pid[idx];
             const unsigned long long v0 = sm.vpos[p], v = v0 + (idx - sm.start[p]);
             const unsigned phys = (v >> PS_PAGE_SHIFT) == (v0 >> PS_PAGE_SHIFT) ? sm.phys_a[p] : sm.phys_b[p];
-            ps.pool[((size_t)phys << PS_PAGE_SHIFT) + (v & (PS_PAGE_ROWS - 1))] = sm.rows[idx];
+            ulonglong2 *dst = ps.pool + ((size_t)phys << PS_PAGE_SHIFT) + (v & (PS_PAGE_ROWS - 1));
+            const ulonglong2 r = sm.rows[idx];
+            if (EF) asm volatile("st.global.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(dst), "l"(r.x), "l"(r.y), "l"(pol) : "memory");
+            else *dst = r;
         }
     }
     // no barrier here: the next tile's first barrier orders these reads before the next writes of start/vpos/rows
