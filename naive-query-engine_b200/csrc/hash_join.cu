@@ -59,6 +59,11 @@ struct JoinTable {
     // needs no split by slot range.  A duplicate key found while building sends the host back to the hashed table.
     int32_t direct;
     long long lo;
+    // narrow direct table: 4-byte slots.  Row numbers always fit (build sides stay below 2^32 - 1 rows); a payload fits
+    // when its column spans less than 2^32 - 1 values and is then stored as value - pay_lo (frame of reference).
+    // 0xffffffff marks a free slot.  Half the bytes = twice the keys that stay L2-resident: 1e7 keys are 40 MB.
+    int32_t narrow, pad;
+    long long pay_lo;
 };
 
 struct ColSrc {
@@ -142,12 +147,17 @@ __global__ void join_direct_build_kernel(JoinTable jt, const unsigned long long 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long rowword = jt.rowpay ? jt.rowpay[i] : (unsigned long long)i;
-    if (rowword == EMPTY_ROW) { // only possible for a payload
+    if (rowword == EMPTY_ROW) { // only possible for a payload; EMPTY_ROW is what a probe returns for "no match"
         dupflag[2] = 1u;
         return;
     }
     const unsigned long long d = keys[i] - (unsigned long long)jt.lo; // < cap: lo and cap come from the keys' own min / max
-    if (atomicCAS(jt.words + d, EMPTY_ROW, rowword) != EMPTY_ROW) *dupflag = 1u;
+    if (jt.narrow) {
+        const unsigned int w = (unsigned int)(rowword - (unsigned long long)jt.pay_lo); // < 0xffffffff by the host's range check
+        if (atomicCAS((unsigned int *)jt.words + d, 0xffffffffu, w) != 0xffffffffu) *dupflag = 1u;
+    } else if (atomicCAS(jt.words + d, EMPTY_ROW, rowword) != EMPTY_ROW) {
+        *dupflag = 1u;
+    }
 }
 
 // streaming accesses of the partitioned probe carry an L2 evict_first policy, so that the slot range being
@@ -187,6 +197,18 @@ __device__ __forceinline__ void probe_direct(const JoinTable &jt, const unsigned
     for (int j = 0; j < K; j++) {
         slot[j] = key[j] - (unsigned long long)jt.lo;
         brow[j] = EMPTY_ROW;
+    }
+    if (jt.narrow) {
+        unsigned int w[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            w[j] = 0xffffffffu;
+            if (((want >> j) & 1u) && slot[j] < jt.cap) w[j] = __ldg((const unsigned int *)jt.words + slot[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if (w[j] != 0xffffffffu) brow[j] = (unsigned long long)w[j] + (unsigned long long)jt.pay_lo;
+        return;
     }
 #pragma unroll
     for (int j = 0; j < K; j++)
@@ -1412,15 +1434,18 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
 // not dense enough, not unique, or a payload collides with the free-slot marker: the caller then builds the hashed table.
 // Knobs: NQE_JOIN_DIRECT=0 switches the direct table off, NQE_JOIN_DIRECT_MIN_ROWS (default 16384) is the smallest build
 // side worth the extra min/max pass and its synchronisation.
-int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt, int rowpay_col, bool *done) {
+int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt, int rowpay_col, bool *done,
+                           const long long *pay_minmax = nullptr) {
     *done = false;
-    static int allow = -1;
+    static int allow = -1, allow_narrow = 1;
     static int64_t min_rows = 0;
     if (allow < 0) {
         const char *e = getenv("NQE_JOIN_DIRECT");
         allow = e ? atoi(e) : 1;
         e = getenv("NQE_JOIN_DIRECT_MIN_ROWS");
         min_rows = e ? atoll(e) : 16384;
+        e = getenv("NQE_JOIN_DIRECT_NARROW"); // 0: always 8-byte slots
+        allow_narrow = e ? atoi(e) : 1;
     }
     const int64_t nl = left->nrows;
     const DevColumn &kc = left->cols[lk];
@@ -1443,11 +1468,25 @@ int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, Join
             jt->rowpay_col = rowpay_col;
         }
     }
+    if (allow_narrow) {
+        if (!jt->rowpay) {
+            jt->narrow = nl < (int64_t)0xffffffffu;
+        } else if (left->cols[rowpay_col].dtype != NQE_FLOAT64) {
+            long long plo, phi;
+            if (pay_minmax) { plo = pay_minmax[0]; phi = pay_minmax[1]; }
+            else NQE_TRY(nqe_minmax_i64(ctx, jt->rowpay, nl, &plo, &phi));
+            if (plo <= phi && (unsigned long long)phi - (unsigned long long)plo < 0xffffffffull) {
+                jt->narrow = 1;
+                jt->pay_lo = plo;
+            }
+        }
+    }
+    const size_t slot_bytes = jt->narrow ? 4 : 8;
     void *slots = nullptr;
-    NQE_TRY(nqe_dev_alloc(ctx, &slots, range * 8));
+    NQE_TRY(nqe_dev_alloc(ctx, &slots, range * slot_bytes + 8));
     jt->words = (unsigned long long *)slots;
     uint32_t *dupflag = (uint32_t *)(ctx->d_scratch + 3);
-    cudaMemsetAsync(slots, 0xff, range * 8, ctx->stream); // EMPTY_ROW everywhere
+    cudaMemsetAsync(slots, 0xff, range * slot_bytes, ctx->stream); // free-slot marker everywhere
     join_direct_build_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(*jt, (const unsigned long long *)kc.values, nl, dupflag);
     ctx->launches++;
     cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
@@ -2020,11 +2059,18 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
         const char *e = getenv("NQE_AGG_DENSE");
         allow_dense = e ? atoi(e) : 1;
     }
+    long long group_minmax[2] = {0, -1};
+    bool have_group_minmax = false;
     if (rc == NQE_OK && paged && allow_dense) {
         // dense group keys: the build side gives their exact range, so the re-split goes by key range and the groups are
         // aggregated in directly indexed shared-memory tables (no key compares, no inserts)
         long long lo, hi;
         rc = nqe_minmax_i64(ctx, (const unsigned long long *)gc->values, left->nrows, &lo, &hi);
+        if (rc == NQE_OK) {
+            group_minmax[0] = lo;
+            group_minmax[1] = hi;
+            have_group_minmax = true;
+        }
         if (rc == NQE_OK && lo <= hi) {
             const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
             const unsigned long long per_part = (range + nqe_dense_parts(ctx, range) - 1) / nqe_dense_parts(ctx, range);
@@ -2044,7 +2090,9 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     uint32_t *split_status = (uint32_t *)(ctx->d_scratch + 20); // the split's own status word: the build uses words 1..4
     // dense unique build keys: a direct table (JoinTable::direct) -- no first split, the probe rows are read in place
     bool direct = false;
-    if (rc == NQE_OK) rc = build_table_direct(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, &direct);
+    if (rc == NQE_OK)
+        rc = build_table_direct(ctx, left, left_key, &jp.jt, only_group_from_build && allow_rowpay ? group_column : -1, &direct,
+                                have_group_minmax ? group_minmax : nullptr);
     if (rc == NQE_OK && paged && !direct) {
         const size_t table_bytes = (((size_t)((double)left->nrows / 0.5) + 16) & ~(size_t)1) * 16; // = build_table's capacity
         int P1 = (int)((table_bytes + l2_budget - 1) / l2_budget);

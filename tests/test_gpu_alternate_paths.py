@@ -30,6 +30,8 @@ CASES = [
     # collisions fall back to the hashed table); switched off, the dense-key inputs go through the hashed / paged paths
     ({"NQE_JOIN_DIRECT_MIN_ROWS": "1"}, "hash_join or join_aggregate or golden_readme or multi_batch or run_sql"),
     ({"NQE_JOIN_DIRECT": "0"}, "direct_table"),
+    ({"NQE_JOIN_DIRECT_NARROW": "0"}, "direct_table"),   # 8-byte slots
+    ({"NQE_JOIN_DIRECT_STAGED": "0"}, "hash_join_direct_table"),  # the general probe kernel over the direct table
     ({"NQE_JA_DIRECT_SHAPE": "1"}, "join_aggregate_direct_table"),
     ({"NQE_JA_DIRECT_SHAPE": "2"}, "join_aggregate_direct_table"),
     ({"NQE_JA_DIRECT_SHAPE": "3"}, "join_aggregate_direct_table"),
