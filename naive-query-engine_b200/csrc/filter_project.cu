@@ -9,6 +9,7 @@
 // tiles (tile ids come from an atomic ticket, so a predecessor is always
 // resident).  Because ranks inside one ballot are consecutive, each warp store
 // writes one contiguous run of the compacted output.
+#include <chrono>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -599,6 +600,14 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
                                       const nqe_expr *projs, int32_t n_projs, nqe_table **out) {
     if (!ctx || !in || !out) return NQE_ERR_INVALID_ARG;
     if (n_projs < 0 || n_projs > 16) return nqe_fail(ctx, NQE_ERR_INVALID_ARG, "n_projs must be in [0,16]");
+    // NQE_FP_PROF=1: where the host side of one call spends its time (averages every 25 calls, stderr)
+    static int prof = -1;
+    if (prof < 0) prof = getenv("NQE_FP_PROF") ? 1 : 0;
+    static double acc[6];
+    static int acc_n = 0;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (prof) tp[0] = now();
     cudaSetDevice(ctx->device);
     *out = nullptr;
     const int64_t n = in->nrows;
@@ -648,6 +657,7 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
     if (predicate) list.push_back(predicate);
     for (int i = 0; i < n_projs; i++) list.push_back(&projs[i]);
     NQE_TRY(nqe_compile_exprs(ctx, in, list.data(), (int32_t)list.size(), &ps, info));
+    if (prof) tp[1] = now();
     const int first = predicate ? 1 : 0;
     if (predicate && info[0].result_dtype != NQE_BOOL)
         return nqe_fail(ctx, NQE_ERR_PANIC, "selection predicate is not Boolean (downcast_ref::<BooleanArray>().unwrap())");
@@ -702,6 +712,7 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
         if (rc == NQE_OK && cudaMemsetAsync(lb, 0, (size_t)(num_tiles + 1) * 8, ctx->stream) != cudaSuccess) rc = NQE_ERR_CUDA;
         fp.tile_state = (unsigned long long *)lb;
     }
+    if (prof) tp[2] = now();
     OpTimer timer(ctx);
     bool jit_used = false;
     static int jit_nulls = -1; // knob NQE_JIT_NULLS=0: nullable inputs go to the interpreter kernels
@@ -748,6 +759,7 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
     if (rc == NQE_OK) {
         timer.mark_end();
         cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (prof) tp[3] = now();
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
             rc = nqe_fail(ctx, NQE_ERR_CUDA, "filter_project kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -755,12 +767,24 @@ extern "C" int32_t nqe_filter_project(nqe_ctx *ctx, const nqe_table *in, const n
         if (predicate) out_rows = n ? (int64_t)ctx->h_scratch[0] : 0;
         rc = status_to_error(ctx, (uint32_t)ctx->h_scratch[1]);
     }
+    if (prof) tp[4] = now();
     timer.stop();
+    if (prof) tp[5] = now();
     for (int i = 0; i < n_projs; i++) {
         nqe_dev_free(ctx, bool_bytes[i]);
         nqe_dev_free(ctx, valid_bytes[i]);
     }
     nqe_dev_free(ctx, lb);
+    if (prof) {
+        tp[6] = now();
+        for (int i = 0; i < 6; i++) acc[i] += tp[i + 1] - tp[i];
+        if (++acc_n == 25) {
+            fprintf(stderr, "nqe_filter_project host us: compile %.1f | alloc+memset %.1f | launch+memcpy enqueue %.1f | sync wait %.1f | timer.stop %.1f | frees %.1f\n",
+                    acc[0] / 25, acc[1] / 25, acc[2] / 25, acc[3] / 25, acc[4] / 25, acc[5] / 25);
+            for (double &a : acc) a = 0;
+            acc_n = 0;
+        }
+    }
     if (rc != NQE_OK) {
         nqe_table_free(t);
         return rc;
