@@ -182,3 +182,4 @@ constexpr unsigned NQE_GP2_DENSE_MAX_WIDTH = 3072; // = GA_SLOTS
 // sm_count / P CTAs per partition).  Knob NQE_DENSE_PARTS overrides.
 int nqe_dense_parts(nqe_ctx *ctx, unsigned long long range);
 int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi);
+int32_t nqe_minmax2_i64(nqe_ctx *ctx, const unsigned long long *a, const unsigned long long *b, int64_t n, long long *mm);

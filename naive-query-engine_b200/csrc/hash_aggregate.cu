@@ -614,21 +614,33 @@ int nqe_dense_parts(nqe_ctx *ctx, unsigned long long range) {
 }
 
 int32_t nqe_minmax_i64(nqe_ctx *ctx, const unsigned long long *col, int64_t n, long long *lo, long long *hi) {
-    *lo = 0;
-    *hi = -1;
+    long long mm[4];
+    NQE_TRY(nqe_minmax2_i64(ctx, col, nullptr, n, mm));
+    *lo = mm[0];
+    *hi = mm[1];
+    return NQE_OK;
+}
+
+// signed min / max of one or two 8-byte columns of the same length with ONE host synchronisation: mm = {lo a, hi a, lo b, hi b}
+int32_t nqe_minmax2_i64(nqe_ctx *ctx, const unsigned long long *a, const unsigned long long *b, int64_t n, long long *mm) {
+    mm[0] = mm[2] = 0;
+    mm[1] = mm[3] = -1;
     if (n <= 0) return NQE_OK;
     long long *d = (long long *)(ctx->d_scratch + 10);
-    const long long init[2] = {LLONG_MAX, LLONG_MIN};
+    const long long init[4] = {LLONG_MAX, LLONG_MIN, LLONG_MAX, LLONG_MIN};
     NQE_CUDA(ctx, cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     int grid = ctx->sm_count * 8;
     if ((int64_t)grid * 256 > n) grid = (int)((n + 255) / 256);
-    minmax_i64_kernel<<<grid, 256, 0, ctx->stream>>>((const long long *)col, n, d);
+    minmax_i64_kernel<<<grid, 256, 0, ctx->stream>>>((const long long *)a, n, d);
     ctx->launches++;
-    long long h[2];
+    if (b) {
+        minmax_i64_kernel<<<grid, 256, 0, ctx->stream>>>((const long long *)b, n, d + 2);
+        ctx->launches++;
+    }
+    long long h[4];
     NQE_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     NQE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *lo = h[0];
-    *hi = h[1];
+    for (int i = 0; i < (b ? 4 : 2); i++) mm[i] = h[i];
     return NQE_OK;
 }
 

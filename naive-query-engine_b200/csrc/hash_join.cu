@@ -838,7 +838,8 @@ struct DirectEmitParams {
     int32_t nl, nr, left_key, right_key;
     const unsigned long long *right[DE_MAX]; // probe-side columns
     unsigned long long *out[2 * DE_MAX];
-    unsigned long long *rowwords;            // per probe row: the table's row word (EMPTY_ROW: no match), written by pass 1
+    unsigned long long *rowwords;            // per probe row: the table's row word (EMPTY_ROW: no match), written by pass 1;
+                                             // with a narrow table the stream is narrow too: the 4-byte slot as it is
     unsigned long long *chunk_count, *out_count;
     int32_t num_tiles, tiles_per_chunk, stages, pad;
 };
@@ -868,7 +869,11 @@ __global__ void __launch_bounds__(HJ_THREADS) join_direct_probe_kernel(const __g
 #pragma unroll
         for (int j = 0; j < K; j++) {
             cnt += brow[j] != EMPTY_ROW;
-            if ((live >> j) & 1u) st_ef(p.rowwords + base + (int64_t)j * T, brow[j], ef);
+            if (!((live >> j) & 1u)) continue;
+            if (p.jt.narrow) // the slot again (row words of a narrow table are pay_lo + a 32-bit value)
+                ((unsigned int *)p.rowwords)[base + (int64_t)j * T] = brow[j] == EMPTY_ROW ? 0xffffffffu : (unsigned int)(brow[j] - (unsigned long long)p.jt.pay_lo);
+            else
+                st_ef(p.rowwords + base + (int64_t)j * T, brow[j], ef);
         }
     }
 #pragma unroll
@@ -884,13 +889,14 @@ __global__ void __launch_bounds__(HJ_THREADS) join_direct_probe_kernel(const __g
 
 // NL build-side columns (the key, and for NL == 2 the one column whose values ride in the table), NR probe-side columns:
 // compile-time, so that every column loop unrolls and the stores need one address computation each.
-template <int K, int NL, int NR>
+template <int K, int NL, int NR, bool N32>
 __global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const __grid_constant__ DirectEmitParams p) {
     constexpr int T = HJ_THREADS, TILE = T * K;
+    constexpr int STAGE_WORDS = NR * TILE + (N32 ? TILE / 2 : TILE); // 8-byte words of one stage: NR columns + the row words
     static_assert(K * HJ_WARPS == 32, "one (row group, warp) count per lane");
     extern __shared__ __align__(128) unsigned char de_smem[];
     unsigned long long *full = (unsigned long long *)de_smem, *empty = full + 8; // [stages] each
-    unsigned long long *ring = (unsigned long long *)(de_smem + 128);            // [stages][NR + 1][TILE]: probe columns, row words
+    unsigned long long *ring = (unsigned long long *)(de_smem + 128);            // [stages][STAGE_WORDS]: probe columns, row words
     __shared__ unsigned int s_cnt[2][K * HJ_WARPS];
     __shared__ unsigned long long s_part[HJ_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -917,11 +923,12 @@ __global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const _
     for (int w = 0; w < HJ_WARPS; w++) base += s_part[w];
     const unsigned long long ef = pj_policy();
     auto issue = [&](int64_t tile, int stage) { // thread 0
-        nqe_mbar_arrive_expect_tx(full + stage, (uint32_t)(NR + 1) * TILE * 8u);
+        nqe_mbar_arrive_expect_tx(full + stage, (uint32_t)STAGE_WORDS * 8u);
 #pragma unroll
         for (int c = 0; c < NR; c++)
-            nqe_bulk_g2s(ring + ((size_t)stage * (NR + 1) + c) * TILE, p.right[c] + tile * TILE, TILE * 8u, full + stage, ef);
-        nqe_bulk_g2s(ring + ((size_t)stage * (NR + 1) + NR) * TILE, p.rowwords + tile * TILE, TILE * 8u, full + stage, ef);
+            nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + c * TILE, p.right[c] + tile * TILE, TILE * 8u, full + stage, ef);
+        if (N32) nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + NR * TILE, (const unsigned int *)p.rowwords + tile * TILE, TILE * 4u, full + stage, ef);
+        else nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + NR * TILE, p.rowwords + tile * TILE, TILE * 8u, full + stage, ef);
     };
     if (tid == 0)
         for (int s = 0; s < S; s++)
@@ -931,22 +938,26 @@ __global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const _
     uint32_t parity = 0;
     for (int64_t tile = t0; tile < t1; tile++, it++) {
         const bool staged = tile < full_tiles;
-        const unsigned long long *st = ring + (size_t)stage * (NR + 1) * TILE + tid;
+        const unsigned long long *st = ring + (size_t)stage * STAGE_WORDS + tid;
         const int64_t e0 = tile * TILE + tid;
         unsigned long long key[K], brow[K];
+        auto widen = [&](unsigned int w) { return w == 0xffffffffu ? EMPTY_ROW : (unsigned long long)w + (unsigned long long)p.jt.pay_lo; };
         if (staged) {
             nqe_mbar_wait(full + stage, parity);
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 key[j] = st[p.right_key * TILE + j * T];
-                brow[j] = st[NR * TILE + j * T];
+                if (N32) brow[j] = widen(((const unsigned int *)(ring + (size_t)stage * STAGE_WORDS + NR * TILE))[j * T + tid]);
+                else brow[j] = st[NR * TILE + j * T];
             }
         } else {
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const int64_t e = e0 + (int64_t)j * T;
                 key[j] = e < p.n_probe ? ld_stream_u64(p.right[p.right_key] + e) : 0ull;
-                brow[j] = e < p.n_probe ? ld_stream_u64(p.rowwords + e) : EMPTY_ROW;
+                if (e >= p.n_probe) brow[j] = EMPTY_ROW;
+                else if (N32) brow[j] = widen(((const unsigned int *)p.rowwords)[e]);
+                else brow[j] = ld_stream_u64(p.rowwords + e);
             }
         }
         unsigned off[K];
@@ -1011,11 +1022,11 @@ __global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const _
     if (blockIdx.x == gridDim.x - 1 && tid == 0) *p.out_count = base;
 }
 
-template <int NL, int NR>
-int32_t join_direct_emit_launch(nqe_ctx *ctx, DirectEmitParams &de) {
+template <int NL, int NR, bool N32>
+int32_t join_direct_emit_launch_n(nqe_ctx *ctx, DirectEmitParams &de) {
     de.stages = NR <= 1 ? 3 : 2;
-    const size_t smem = 128 + (size_t)de.stages * (NR + 1) * HJ_K * HJ_THREADS * 8;
-    auto dk = join_direct_emit_kernel<HJ_K, NL, NR>;
+    const size_t smem = 128 + (size_t)de.stages * (NR * 8 + (N32 ? 4 : 8)) * HJ_K * HJ_THREADS;
+    auto dk = join_direct_emit_kernel<HJ_K, NL, NR, N32>;
     NQE_CUDA(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int docc = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, dk, HJ_THREADS, smem);
@@ -1028,6 +1039,10 @@ int32_t join_direct_emit_launch(nqe_ctx *ctx, DirectEmitParams &de) {
     ctx->launches += 2;
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
+}
+template <int NL, int NR>
+int32_t join_direct_emit_launch(nqe_ctx *ctx, DirectEmitParams &de) {
+    return de.jt.narrow ? join_direct_emit_launch_n<NL, NR, true>(ctx, de) : join_direct_emit_launch_n<NL, NR, false>(ctx, de);
 }
 
 // ---- fused join -> group-by aggregate --------------------------------------
@@ -1453,8 +1468,13 @@ int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, Join
     const int64_t nl = left->nrows;
     const DevColumn &kc = left->cols[lk];
     if (!allow || nl < min_rows || nl < 1 || (kc.dtype != NQE_INT64 && kc.dtype != NQE_UINT64)) return NQE_OK;
-    long long lo, hi;
-    NQE_TRY(nqe_minmax_i64(ctx, (const unsigned long long *)kc.values, nl, &lo, &hi));
+    // key range and, when a payload may ride in the table, its range (for 4-byte slots): one pass each, one synchronisation
+    const DevColumn *pcand = rowpay_col >= 0 ? &left->cols[rowpay_col] : nullptr;
+    const bool pay_ok = pcand && !pcand->validity && (pcand->dtype == NQE_INT64 || pcand->dtype == NQE_UINT64 || pcand->dtype == NQE_FLOAT64);
+    const bool want_pay_range = pay_ok && allow_narrow && !pay_minmax && pcand->dtype != NQE_FLOAT64;
+    long long mm[4];
+    NQE_TRY(nqe_minmax2_i64(ctx, (const unsigned long long *)kc.values, want_pay_range ? (const unsigned long long *)pcand->values : nullptr, nl, mm));
+    const long long lo = mm[0], hi = mm[1];
     // as two's-complement offsets from the signed minimum the keys of either dtype fall in [0, range)
     const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo + 1ull;
     if (lo > hi || range == 0 || range > 4ull * (unsigned long long)nl + 1024ull) return NQE_OK; // sparse keys: <= 32 bytes per build row
@@ -1475,9 +1495,7 @@ int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, Join
         if (!jt->rowpay) {
             jt->narrow = nl < (int64_t)0xffffffffu;
         } else if (left->cols[rowpay_col].dtype != NQE_FLOAT64) {
-            long long plo, phi;
-            if (pay_minmax) { plo = pay_minmax[0]; phi = pay_minmax[1]; }
-            else NQE_TRY(nqe_minmax_i64(ctx, jt->rowpay, nl, &plo, &phi));
+            const long long plo = pay_minmax ? pay_minmax[0] : mm[2], phi = pay_minmax ? pay_minmax[1] : mm[3];
             if (plo <= phi && (unsigned long long)phi - (unsigned long long)plo < 0xffffffffull) {
                 jt->narrow = 1;
                 jt->pay_lo = plo;
