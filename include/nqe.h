@@ -203,6 +203,31 @@ int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const nqe_table 
                            int32_t left_key, int32_t right_key, int32_t group_column,
                            const nqe_agg *aggs, int32_t n_aggs, nqe_table **out);
 
+/* ---- several GPUs of one node, ONE process (nqe_ctx_create(devices, n); 8e plans ii and iv) --------
+ * The reference is a single-process engine, so this is the shape its planner can bind: the shards of a table in, one
+ * result out.  A nqe_multi owns one nqe_ctx per member GPU (member i = devices[i]; the same device may be listed more
+ * than once); every member's share of a plan runs on its own host thread, tables move between members as peer copies
+ * over NVLink, results land on member 0.  Tables handed in must have been created through the member's own context
+ * (nqe_multi_ctx).  (One process per GPU over torch.distributed / NCCL: naive-query-engine_b200/distributed.py.) */
+typedef struct nqe_multi nqe_multi;
+int32_t nqe_multi_create(const int32_t *devices, int32_t n, nqe_multi **out);
+void nqe_multi_destroy(nqe_multi *m);
+int32_t nqe_multi_size(const nqe_multi *m);
+nqe_ctx *nqe_multi_ctx(nqe_multi *m, int32_t member);
+const char *nqe_multi_last_error(const nqe_multi *m);
+/* a copy of `src` (any member's table) on member dst_member */
+int32_t nqe_multi_table_copy(nqe_multi *m, const nqe_table *src, int32_t dst_member, nqe_table **out);
+/* HashJoin feeding PhysicalAggregatePlan (hash_join.rs:124-254, aggregate/mod.rs:113-222) with the probe side sharded:
+ * `left` (build side, on any member) is copied to every member, member i joins it with right[i] (NULL = no shard) and
+ * pre-aggregates, the partial states are merged on member 0.  Same arguments and output as nqe_join_aggregate over
+ * the concatenation of the shards (sums within float re-association, group order unspecified). */
+int32_t nqe_multi_join_aggregate(nqe_multi *m, const nqe_table *left, const nqe_table *const *right, int32_t left_key,
+                                 int32_t right_key, int32_t group_column, const nqe_agg *aggs, int32_t n_aggs,
+                                 nqe_table **out);
+/* PhysicalAggregatePlan over sharded input: in[i] on member i (NULL = no shard); group_expr must not be NULL. */
+int32_t nqe_multi_hash_aggregate(nqe_multi *m, const nqe_table *const *in, const nqe_expr *group_expr,
+                                 const nqe_agg *aggs, int32_t n_aggs, nqe_table **out);
+
 /* ---- multi-GPU helper: radix partition on the key ------------------------ */
 /* Splits `in` into n_parts contiguous row ranges by mix64(key) % n_parts (the
  * shuffle step before an all-to-all).  out has the same schema, rows grouped by

@@ -15,7 +15,7 @@ The directory name contains a hyphen; import it with
 alias module at the repository root.
 """
 from ._ffi import LIB_PATH, NqeError, load  # noqa: F401
-from .device import Context, DeviceTable  # noqa: F401
+from .device import Context, DeviceTable, MultiContext  # noqa: F401
 from .physical_plan import (Avg, ColumnExpr, Count, CsvTable, HashJoin, Max, MemTable, Min,  # noqa: F401
                             PhysicalAggregatePlan, PhysicalBinaryExpr, PhysicalCastExpr, PhysicalLimitPlan,
                             PhysicalExpr, PhysicalLiteralExpr, PhysicalOffsetPlan, PhysicalPlan, PhysicalUnaryExpr,

@@ -80,6 +80,15 @@ SYMBOLS = {
     "nqe_hash_aggregate": (C.c_int32, [_P, _P, C.POINTER(Expr), C.POINTER(Agg), C.c_int32, C.POINTER(_P)]),
     "nqe_join_aggregate": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Agg), C.c_int32,
                                        C.POINTER(_P)]),
+    "nqe_multi_create": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(_P)]),
+    "nqe_multi_destroy": (None, [_P]),
+    "nqe_multi_size": (C.c_int32, [_P]),
+    "nqe_multi_ctx": (_P, [_P, C.c_int32]),
+    "nqe_multi_last_error": (C.c_char_p, [_P]),
+    "nqe_multi_table_copy": (C.c_int32, [_P, _P, C.c_int32, C.POINTER(_P)]),
+    "nqe_multi_join_aggregate": (C.c_int32, [_P, _P, C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, C.POINTER(Agg), C.c_int32,
+                                             C.POINTER(_P)]),
+    "nqe_multi_hash_aggregate": (C.c_int32, [_P, C.POINTER(_P), C.POINTER(Expr), C.POINTER(Agg), C.c_int32, C.POINTER(_P)]),
     "nqe_radix_partition": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "nqe_partition_counts": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "nqe_shuffle_scatter": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -12,6 +12,7 @@
 // All value columns are accumulated "as f64" exactly like the reference
 // (sum.rs:44 `val as f64`), NULL keys are dropped (mod.rs:63-71), NULL values
 // skipped, and the output carries no key column.
+#include <atomic>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -981,13 +982,13 @@ extern "C" int32_t nqe_hash_aggregate(nqe_ctx *ctx, const nqe_table *in, const n
             }
         }
         // --- partitioned shared-memory path (gp2_aggregate_kernel): split once, aggregate inside the retry loop
-        static int agg_part = -1;
+        static std::atomic<int> agg_part{-1}; // guard published last: operators may be called from several host threads (multi.cu)
         static int64_t agg_part_min_rows = 0;
-        if (agg_part < 0) {
-            const char *e = getenv("NQE_AGG_PART");
-            agg_part = e ? atoi(e) : 1;
-            e = getenv("NQE_AGG_PART_MIN_ROWS");
+        if (agg_part.load(std::memory_order_acquire) < 0) {
+            const char *e = getenv("NQE_AGG_PART_MIN_ROWS");
             agg_part_min_rows = e ? atoll(e) : ((int64_t)1 << 22);
+            e = getenv("NQE_AGG_PART");
+            agg_part.store(e ? atoi(e) != 0 : 1, std::memory_order_release);
         }
         bool use_part = false;
         PagedStreams streams;

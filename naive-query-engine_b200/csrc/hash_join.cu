@@ -13,6 +13,7 @@
 // tiles (so the output is probe-row-major like the reference's), and writes the joined row
 // straight to its final position: no (outer_pos, inner_pos) index arrays and no separate
 // `take` pass.  Within one probe row, matches are emitted in ascending build-row order.
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -1455,15 +1456,18 @@ int32_t build_table(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *
 int32_t build_table_direct(nqe_ctx *ctx, const nqe_table *left, int32_t lk, JoinTable *jt, int rowpay_col, bool *done,
                            const long long *pay_minmax = nullptr) {
     *done = false;
-    static int allow = -1, allow_narrow = 1;
+    // (knob blocks with several variables publish their guard LAST, with release / acquire order: the multi-GPU entry
+    // points call the operators from one host thread per member)
+    static std::atomic<int> allow{-1};
+    static int allow_narrow = 1;
     static int64_t min_rows = 0;
-    if (allow < 0) {
-        const char *e = getenv("NQE_JOIN_DIRECT");
-        allow = e ? atoi(e) : 1;
-        e = getenv("NQE_JOIN_DIRECT_MIN_ROWS");
+    if (allow.load(std::memory_order_acquire) < 0) {
+        const char *e = getenv("NQE_JOIN_DIRECT_MIN_ROWS");
         min_rows = e ? atoll(e) : 16384;
         e = getenv("NQE_JOIN_DIRECT_NARROW"); // 0: always 8-byte slots
         allow_narrow = e ? atoi(e) : 1;
+        e = getenv("NQE_JOIN_DIRECT");
+        allow.store(e ? atoi(e) != 0 : 1, std::memory_order_release);
     }
     const int64_t nl = left->nrows;
     const DevColumn &kc = left->cols[lk];
@@ -1550,17 +1554,18 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
     NQE_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64 * sizeof(uint64_t), ctx->stream));
     ProbeParams pp;
     memset(&pp, 0, sizeof pp);
-    static int allow_part = -1, allow_rowpay = 1;
+    static std::atomic<int> allow_part{-1};
+    static int allow_rowpay = 1;
     static size_t l2_budget = 0, part_min = 0;
-    if (allow_part < 0) {
-        const char *e = getenv("NQE_JOIN_PART");
-        allow_part = e ? atoi(e) : 1;
-        e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
+    if (allow_part.load(std::memory_order_acquire) < 0) {
+        const char *e = getenv("NQE_JOIN_PART_MB"); // slot range of one partition, MiB
         l2_budget = (size_t)(e ? atoi(e) : 48) << 20; // measured 12 / 24 / 48 / 96 MiB: 3.98 / 3.73 / 3.63 / 3.80 ms (1e8 x 1e7)
         e = getenv("NQE_JOIN_PART_MIN_MB"); // tables up to this size are probed directly
         part_min = (size_t)(e ? atoi(e) : 48) << 20;
         e = getenv("NQE_JOIN_ROWPAY");
         allow_rowpay = e ? atoi(e) : 1;
+        e = getenv("NQE_JOIN_PART");
+        allow_part.store(e ? atoi(e) != 0 : 1, std::memory_order_release);
     }
     pp.n_probe = right->nrows;
     // the partitioned probe (below) will run if the build keys turn out unique; with a single non-key build column its
@@ -2047,16 +2052,17 @@ extern "C" int32_t nqe_join_aggregate(nqe_ctx *ctx, const nqe_table *left, const
     // no payload collision" is known before the build, and the first split depends only on the table's SIZE: it is
     // started on the auxiliary stream and runs beside the build (if the build then disqualifies the plan the split is
     // simply dropped).
-    static int allow_paged = -1;
+    static std::atomic<int> allow_paged{-1};
     static size_t l2_budget = 0;
-    if (allow_paged < 0) {
-        const char *e = getenv("NQE_JOINAGG_PAGED");
-        allow_paged = e ? atoi(e) : 1;
+    if (allow_paged.load(std::memory_order_acquire) < 0) {
+        const char *e;
         // slot range of one partition of the first split.  Measured (1e8 x 1e7, whole operator, two runs each): 48 MiB
         // (7 partitions) 4.29 / 12 MiB 4.40 / 8 MiB 4.38 / 6 MiB (54 partitions) 4.09 / 4 MiB 4.17 / 3 MiB 4.44 ms: every
         // range is L2-resident; with few partitions the split's shared-memory counters are hot
         e = getenv("NQE_JA_PART_MB");
         l2_budget = (size_t)(e && atoi(e) > 0 ? atoi(e) : 6) << 20;
+        e = getenv("NQE_JOINAGG_PAGED");
+        allow_paged.store(e ? atoi(e) != 0 : 1, std::memory_order_release);
     }
     const DevColumn *gc = only_group_from_build && allow_rowpay ? &left->cols[group_column] : nullptr;
     bool paged = allow_paged && gc && !gc->validity && jp.n_probe >= join_part_min_rows() && ap.n_states > 0 && left->nrows > 0;

@@ -11,6 +11,7 @@
 // Applies when no referenced column has a validity bitmap and no literal is NULL;
 // everything else runs on the pre-compiled interpreter kernels.  If libnvrtc is
 // not present the interpreter kernels are used as well (NQE_JIT=0 forces that).
+#include <atomic>
 #include <dlfcn.h>
 #include <nvrtc.h>
 
@@ -559,15 +560,14 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         if (D < 1 || D > 8) D = 4;
     }
     // TMA-ring variant: knobs NQE_JIT_IMPL=tma|ca, NQE_JIT_TMA_K / _SP / _SW / _LAG / _WALKERS / _LBW / _OCC
-    static int impl = -1, TK = 8, SP = 2, SW = 2, LAG = 4, WALKERS = 2, lbw = 1, prof = 0;
-    if (impl < 0) {
+    static std::atomic<int> impl_guard{-1}; // published last: operators may be called from several host threads (multi.cu)
+    static int TK = 8, SP = 2, SW = 2, LAG = 4, WALKERS = 2, lbw = 1, prof = 0;
+    if (impl_guard.load(std::memory_order_acquire) < 0) {
         auto knob = [](const char *name, int dflt, int lo, int hi) {
             const char *e = getenv(name);
             const int v = e ? atoi(e) : dflt;
             return v < lo || v > hi ? dflt : v;
         };
-        const char *e = getenv("NQE_JIT_IMPL");
-        impl = (e && !strcmp(e, "ca")) ? 0 : 1;
         // defaults = best of the B200 sweeps in profiles/filter_project_sweeps_r01.md
         TK = knob("NQE_JIT_TMA_K", 8, 1, 16);
         if (TK & (TK - 1)) TK = 8;
@@ -577,7 +577,10 @@ static int32_t jit_filter_project_impl(nqe_ctx *ctx, const nqe_table *in, const 
         WALKERS = knob("NQE_JIT_TMA_WALKERS", 2, 1, 4);
         lbw = knob("NQE_JIT_TMA_LBW", 1, 1, 16); // look-back window: 32*lbw tiles per L2 round trip
         prof = getenv("NQE_JIT_PROF") ? 1 : 0;
+        const char *e = getenv("NQE_JIT_IMPL");
+        impl_guard.store((e && !strcmp(e, "ca")) ? 0 : 1, std::memory_order_release);
     }
+    const int impl = impl_guard.load(std::memory_order_relaxed);
     bool tma = allow_tma && impl == 1 && predicate && n_pred_cols > 0;
     const size_t n_slots = g.col_of_slot.size();
     uint32_t pstage = 0, ptx = 0, wstage = 0, wtx = 0;

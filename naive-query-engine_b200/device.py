@@ -73,6 +73,62 @@ class Context:
             self.h = None
 
 
+class MultiContext:
+    """nqe_multi: several GPUs of one node driven from this one process (include/nqe.h).  `members[i]` is a Context
+    borrowed from the nqe_multi (do not close it); tables for member i are created through `members[i]`."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = _ffi.load()
+        arr = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.nqe_multi_create(arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise NqeError(rc, "nqe_multi_create failed: no usable CUDA device (the CUDA path is the only path)")
+        self.h = h
+        self.members: List[Context] = []
+        for i in range(len(devices)):
+            c = Context.__new__(Context)
+            c.lib, c.h, c.device = self.lib, C.c_void_p(self.lib.nqe_multi_ctx(h, i)), devices[i]
+            self.members.append(c)
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise NqeError(rc, self.lib.nqe_multi_last_error(self.h).decode())
+
+    def copy(self, table: "DeviceTable", member: int) -> "DeviceTable":
+        h = C.c_void_p()
+        self.check(self.lib.nqe_multi_table_copy(self.h, table.h, member, C.byref(h)))
+        return DeviceTable(self.members[member], h, table.names)
+
+    def _handles(self, tables):
+        return (C.c_void_p * len(self.members))(*[t.h if t is not None else None for t in tables])
+
+    def join_aggregate(self, left: "DeviceTable", right: Sequence[Optional["DeviceTable"]], left_key: int, right_key: int,
+                       group_column: int, aggs: Sequence[tuple], names: Sequence[str]) -> "DeviceTable":
+        """broadcast-build join -> group-by: `left` on any member, right[i] = member i's probe shard (or None);
+        aggs = [(op, column of the joined schema)]; the result lives on member 0"""
+        a = (_ffi.Agg * len(aggs))(*[_ffi.Agg(op, c) for op, c in aggs])
+        h = C.c_void_p()
+        self.check(self.lib.nqe_multi_join_aggregate(self.h, left.h, self._handles(right), left_key, right_key, group_column, a,
+                                                     len(aggs), C.byref(h)))
+        return DeviceTable(self.members[0], h, names)
+
+    def hash_aggregate(self, shards: Sequence[Optional["DeviceTable"]], group_expr, aggs: Sequence[tuple],
+                       names: Sequence[str]) -> "DeviceTable":
+        """group-by over sharded input (shards[i] on member i): `group_expr` is a lowered _ffi.Expr"""
+        a = (_ffi.Agg * len(aggs))(*[_ffi.Agg(op, c) for op, c in aggs])
+        h = C.c_void_p()
+        self.check(self.lib.nqe_multi_hash_aggregate(self.h, self._handles(shards), C.pointer(group_expr), a, len(aggs), C.byref(h)))
+        return DeviceTable(self.members[0], h, names)
+
+    def close(self):
+        if self.h:
+            self.lib.nqe_multi_destroy(self.h)
+            self.h = None
+            for c in self.members:
+                c.h = None
+
+
 def _normalise(arr: pa.Array) -> pa.Array:
     if isinstance(arr, pa.ChunkedArray):
         arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
@@ -213,7 +269,8 @@ class DeviceTable:
 
     def free(self):
         if self.h:
-            self.ctx.lib.nqe_table_free(self.h)
+            if self.ctx.h:  # a table that outlives its (closed) context is dropped, not freed through a dangling nqe_ctx
+                self.ctx.lib.nqe_table_free(self.h)
             self.h = None
 
     def __del__(self):
