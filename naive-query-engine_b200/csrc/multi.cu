@@ -102,15 +102,23 @@ int32_t merge_partials(nqe_multi *m, const PartialPlan &pl, std::vector<nqe_tabl
     cudaSetDevice(c0->device);
     std::vector<nqe_table *> on0;
     int32_t rc = NQE_OK;
-    for (size_t i = 0; i < part.size() && rc == NQE_OK; i++) {
-        if (!part[i]) continue;
-        if (part[i]->ctx == c0) {
-            on0.push_back(part[i]);
-            part[i] = nullptr;
-        } else {
-            nqe_table *moved = nullptr;
-            rc = nqe_multi_table_copy(m, part[i], 0, &moved);
-            if (rc == NQE_OK) on0.push_back(moved);
+    { // the partial tables are small (one row per group): all peer copies at once, one host thread each
+        std::vector<nqe_table *> moved(part.size(), nullptr);
+        std::vector<int32_t> crc(part.size(), NQE_OK);
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < part.size(); i++)
+            if (part[i] && part[i]->ctx != c0) th.emplace_back([&, i] { crc[i] = nqe_multi_table_copy(m, part[i], 0, &moved[i]); });
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < part.size(); i++) {
+            if (!part[i]) continue;
+            if (part[i]->ctx == c0) {
+                on0.push_back(part[i]);
+                part[i] = nullptr;
+            } else if (crc[i] != NQE_OK) {
+                rc = crc[i];
+            } else {
+                on0.push_back(moved[i]);
+            }
         }
     }
     nqe_table *all = nullptr, *merged = nullptr;

@@ -37,6 +37,9 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(nq.NqeError) as e:
         nq.Context(0)
     assert e.value.kind == "CudaError"
+    with pytest.raises(nq.NqeError) as e:  # the multi-GPU entry has no fallback either
+        nq.MultiContext([0, 0])
+    assert e.value.kind == "CudaError"
 
 
 def test_product_never_imports_oracle():
