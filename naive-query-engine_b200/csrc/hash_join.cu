@@ -1278,9 +1278,9 @@ int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, cons
     return NQE_OK;
 }
 // knob NQE_JA_PROBE_SHAPE: 0 (default) = 256 threads x 2 rows (512-row pieces, 6 CTAs/SM at 40 registers), 1 = 512 x 4
-// (half pages, 2 CTAs/SM), 2 = 1024 x 4 (whole pages, 1 CTA/SM), 3 = 256 x 4 with 5 CTAs/SM (51 registers), 4 = 256 x 4
-// (quarter pages, 4 CTAs/SM).  Measured 1e8 x 1e7, whole operator: 4.69 / 4.92 / 4.95 / 5.00 / 4.84 ms: the kernel waits
-// on L2 round trips, more resident warps beat more rows per thread.
+// (half pages, 2 CTAs/SM).  Measured 1e8 x 1e7, whole operator, with the shapes that were removed again (1024 x 4 at one
+// CTA/SM, 256 x 4 at 5 and at 4 CTAs/SM): 4.69 / 4.92 / 4.95 / 5.00 / 4.84 ms: the kernel waits on L2 round trips, more
+// resident warps beat more rows per thread.
 int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
                                 long long dense_lo, uint32_t dense_width) {
     static int shape = -1;
@@ -1290,9 +1290,6 @@ int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const Page
     }
     switch (shape) {
     case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2, dense_lo, dense_width);
-    case 2: return ja_probe_scatter_launch_shape<1024, 4, 1>(ctx, in, out, jt, P2, dense_lo, dense_width);
-    case 3: return ja_probe_scatter_launch_shape<256, 4, 5>(ctx, in, out, jt, P2, dense_lo, dense_width);
-    case 4: return ja_probe_scatter_launch_shape<256, 4, 4>(ctx, in, out, jt, P2, dense_lo, dense_width);
     default: return ja_probe_scatter_launch_shape<256, 2, 6>(ctx, in, out, jt, P2, dense_lo, dense_width);
     }
 }
@@ -1356,31 +1353,11 @@ int32_t ja_direct_scatter_launch_shape(nqe_ctx *ctx, const PsSplitArgs &a, const
     NQE_CUDA(ctx, cudaGetLastError());
     return NQE_OK;
 }
-// knob NQE_JA_DIRECT_SHAPE: 0 (default) = 256 threads x 8 rows, 4 CTAs/SM (the plain split's shape), 1 = 256 x 4, 6 CTAs/SM,
-// 2 = 512 x 8, 2 CTAs/SM, 3 = 256 x 8, 3 CTAs/SM
+// one shape: 256 threads x 8 rows, 4 CTAs per SM (the plain split's); 256 x 4 at 6 CTAs, 512 x 8 at 2 and 256 x 8 at 3 CTAs per
+// SM measured within noise of it (2.40 .. 2.50 ms for the whole operator), as did the L2 policy combinations
 int32_t ja_direct_scatter_launch(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
                                  long long dense_lo, uint32_t dense_width) {
-    static int shape = -1;
-    if (shape < 0) {
-        const char *e = getenv("NQE_JA_DIRECT_SHAPE");
-        shape = e ? atoi(e) : 0;
-    }
-    static int cm = -1; // knob NQE_JA_DIRECT_CACHE: L2 policies (see the kernel), default 3; applies to the default shape
-    if (cm < 0) {
-        const char *e = getenv("NQE_JA_DIRECT_CACHE");
-        cm = e ? atoi(e) & 3 : 3;
-    }
-    if (shape == 0 && cm != 3) {
-        if (cm == 0) return ja_direct_scatter_launch_shape<256, 8, 4, 0>(ctx, a, out, jt, P2, dense_lo, dense_width);
-        if (cm == 1) return ja_direct_scatter_launch_shape<256, 8, 4, 1>(ctx, a, out, jt, P2, dense_lo, dense_width);
-        return ja_direct_scatter_launch_shape<256, 8, 4, 2>(ctx, a, out, jt, P2, dense_lo, dense_width);
-    }
-    switch (shape) {
-    case 1: return ja_direct_scatter_launch_shape<256, 4, 6>(ctx, a, out, jt, P2, dense_lo, dense_width);
-    case 2: return ja_direct_scatter_launch_shape<512, 8, 2>(ctx, a, out, jt, P2, dense_lo, dense_width);
-    case 3: return ja_direct_scatter_launch_shape<256, 8, 3>(ctx, a, out, jt, P2, dense_lo, dense_width);
-    default: return ja_direct_scatter_launch_shape<256, 8, 4>(ctx, a, out, jt, P2, dense_lo, dense_width);
-    }
+    return ja_direct_scatter_launch_shape<256, 8, 4, 3>(ctx, a, out, jt, P2, dense_lo, dense_width);
 }
 
 // smallest probe side that takes the partitioned / paged paths (knob NQE_JOIN_PART_MIN_ROWS; tests and the
@@ -1911,16 +1888,8 @@ extern "C" int32_t nqe_hash_join(nqe_ctx *ctx, const nqe_table *left, const nqe_
                     }
                     nqe_dev_free(ctx, rw); // stream-ordered: after the two passes
                 } else {
-                static int cm = -1; // knob NQE_JOIN_DIRECT_CACHE: L2 policies of the direct probe (see the kernel), default 3
-                if (cm < 0) {
-                    const char *e = getenv("NQE_JOIN_DIRECT_CACHE");
-                    cm = e ? atoi(e) & 3 : 3;
-                }
-                auto kern = !pp.jt.direct ? join_probe_kernel<false, 0>
-                            : cm == 3     ? join_probe_kernel<true, 3>
-                            : cm == 2     ? join_probe_kernel<true, 2>
-                            : cm == 1     ? join_probe_kernel<true, 1>
-                                          : join_probe_kernel<true, 0>;
+                // over a direct table: table reads evict_last, plain streams (measured best of the four policy combinations)
+                auto kern = pp.jt.direct ? join_probe_kernel<true, 2> : join_probe_kernel<false, 0>;
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HJ_THREADS, 0);
                 int grid = ctx->sm_count * (occ > 0 ? occ : 1);

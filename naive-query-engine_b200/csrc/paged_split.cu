@@ -40,18 +40,8 @@ int nqe_ps_split_shape() {
     if (shape < 0) {
         const char *e = getenv("NQE_PS_SPLIT_SHAPE");
         shape = e ? atoi(e) : 0;
-        if (shape < 0 || shape > 4) shape = 0;
+        if (shape < 0 || shape > 1) shape = 0;
     }
     return shape;
 }
 
-// knob NQE_PS_SPLIT_TMA: 0 = plain loads, 1 = bulk-copy staged input, 256 x 8 rows, 3 CTAs/SM; 2 = 512 x 8, 1 CTA/SM; 3 = 256 x 4, 5 CTAs/SM
-int nqe_ps_split_tma() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("NQE_PS_SPLIT_TMA");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 3) v = 0;
-    }
-    return v;
-}

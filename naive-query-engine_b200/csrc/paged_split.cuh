@@ -213,9 +213,9 @@ struct PartByRange {
 };
 
 // Tile shapes of the split kernel (knob NQE_PS_SPLIT_SHAPE): 0 (default) = 256 threads x 8 rows (2048-row tiles,
-// 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM), 2 = 1024 x 4 (4096-row tiles, 1 CTA/SM), 3 = 256 x 8 with 5
-// CTAs/SM (51 registers), 4 = 256 x 4 (1024-row tiles, 6 CTAs/SM).  Measured, group-by of 1e8 rows into 148
-// partitions, whole operator: 1.95-1.98 / 1.98 / 2.24 / 2.08 / 2.46 ms.
+// 4 CTAs/SM), 1 = 512 x 8 (4096-row tiles, 2 CTAs/SM).  Measured, group-by of 1e8 rows into 148 partitions, whole
+// operator, with the shapes that were removed again (1024 x 4 at one CTA/SM, 256 x 8 at 5 CTAs/SM, 256 x 4 at 6):
+// 1.95-1.98 / 1.98 / 2.24 / 2.08 / 2.46 ms.
 template <bool KEYEXPR, typename Part, int T, int K, int MINB>
 __global__ void __launch_bounds__(T, MINB)
 ps_split_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, const Part part,
@@ -251,83 +251,9 @@ ps_split_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, co
     }
 }
 
-// The same split with the input tile STAGED by cp.async.bulk: thread 0 issues the two bulk copies (keys, values) of the
-// CTA's next tile as soon as the current tile's rows are in registers (right after the scatter's first barrier), so the
-// DRAM latency of a tile's loads is hidden behind the previous tile's scan / staging / write-out instead of by other CTAs.
-// Bare NULL-free key column, 16-byte aligned columns; a ragged last tile is read with plain loads.
-template <typename Part, int T, int K, int MINB>
-__global__ void __launch_bounds__(T, MINB)
-ps_split_tma_kernel(const __grid_constant__ PagedStreams ps, const PsSplitArgs a, const Part part) {
-    constexpr int TILE = T * K;
-    extern __shared__ __align__(128) unsigned char ps_smem_raw[];
-    unsigned long long *in_keys = (unsigned long long *)ps_smem_raw, *in_vals = in_keys + TILE;
-    PsScatterSmem<T, K> &sm = *reinterpret_cast<PsScatterSmem<T, K> *>(ps_smem_raw + 2 * TILE * 8);
-    unsigned long long *full = (unsigned long long *)(ps_smem_raw + 2 * TILE * 8 + sizeof(PsScatterSmem<T, K>));
-    if (threadIdx.x == 0) {
-        nqe_mbar_init(full, 1);
-        nqe_mbar_init_fence();
-    }
-    ps_scatter_init(sm);
-    const int64_t num_tiles = (a.n + TILE - 1) / TILE, full_tiles = a.n / TILE;
-    auto issue = [&](int64_t tile) { // thread 0
-        if (tile >= full_tiles) return;
-        nqe_mbar_arrive_expect_tx(full, 2u * TILE * 8u);
-        const unsigned long long pol = nqe_policy_evict_first();
-        nqe_bulk_g2s(in_keys, a.keys + tile * TILE, TILE * 8u, full, pol);
-        nqe_bulk_g2s(in_vals, a.vals + tile * TILE, TILE * 8u, full, pol);
-    };
-    if (threadIdx.x == 0) issue(blockIdx.x);
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        unsigned long long key[K], val[K];
-        int pid[K];
-        uint32_t live = 0;
-        if (tile < full_tiles) {
-            nqe_mbar_wait(full, it & 1u);
-            it++;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                key[j] = in_keys[j * T + threadIdx.x];
-                val[j] = ps_as_f64_bits(a.val_dtype, in_vals[j * T + threadIdx.x]);
-            }
-            live = K >= 32 ? 0xffffffffu : (1u << K) - 1u;
-        } else {
-            const int64_t e0 = tile * TILE + threadIdx.x;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                const bool in = e0 + (int64_t)j * T < a.n;
-                key[j] = in ? ld_stream_u64(a.keys + e0 + (int64_t)j * T) : 0ull;
-                val[j] = in ? ps_as_f64_bits(a.val_dtype, ld_stream_u64(a.vals + e0 + (int64_t)j * T)) : 0ull;
-                if (in) live |= 1u << j;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < K; j++) pid[j] = part(key[j]);
-        const int64_t next = tile + gridDim.x;
-        ps_scatter_tile<T, K>(ps, sm, key, val, pid, live, [&]() {
-            if (threadIdx.x == 0) issue(next); // the whole CTA has read the staged tile: refill the buffer
-        });
-    }
-}
-
+// (A variant with the input tile staged by cp.async.bulk copies was measured -- NQE_PS_SPLIT_TMA in round 2 -- and gave
+// nothing, 1.50 vs 1.50 ms for the whole group-by: the split is not latency-bound.  Removed.)
 int nqe_ps_split_shape(); // paged_split.cu: knob NQE_PS_SPLIT_SHAPE
-int nqe_ps_split_tma();   // paged_split.cu: knob NQE_PS_SPLIT_TMA
-
-template <typename Part, int T, int K, int MINB>
-static int32_t ps_split_tma_launch_shape(nqe_ctx *ctx, const PagedStreams &ps, const PsSplitArgs &a, const Part &part) {
-    auto kern = ps_split_tma_kernel<Part, T, K, MINB>;
-    const size_t smem = (size_t)2 * T * K * 8 + sizeof(PsScatterSmem<T, K>) + 16;
-    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t tiles = (a.n + (int64_t)T * K - 1) / ((int64_t)T * K);
-    int grid = ctx->sm_count * MINB;
-    if (grid > tiles) grid = (int)tiles;
-    if (grid < 1) return NQE_OK;
-    kern<<<grid, T, smem, ctx->stream>>>(ps, a, part);
-    ctx->launches++;
-    NQE_CUDA(ctx, cudaGetLastError());
-    return NQE_OK;
-}
-
 template <bool KEYEXPR, typename Part, int T, int K, int MINB>
 static int32_t ps_split_launch_shape(nqe_ctx *ctx, const PagedStreams &ps, const PsSplitArgs &a, const Part &part,
                                      const DevProgramSet &prog, uint32_t *status) {
@@ -347,18 +273,8 @@ static int32_t ps_split_launch_shape(nqe_ctx *ctx, const PagedStreams &ps, const
 template <bool KEYEXPR, typename Part>
 static int32_t ps_split_launch(nqe_ctx *ctx, const PagedStreams &ps, const PsSplitArgs &a, const Part &part,
                                const DevProgramSet &prog, uint32_t *status) {
-    if (!KEYEXPR && nqe_ps_split_tma() && ((uintptr_t)a.keys & 15) == 0 && ((uintptr_t)a.vals & 15) == 0) {
-        switch (nqe_ps_split_tma()) {
-        case 2: return ps_split_tma_launch_shape<Part, 512, 8, 1>(ctx, ps, a, part);
-        case 3: return ps_split_tma_launch_shape<Part, 256, 4, 5>(ctx, ps, a, part);
-        default: return ps_split_tma_launch_shape<Part, 256, 8, 3>(ctx, ps, a, part);
-        }
-    }
     switch (nqe_ps_split_shape()) {
     case 1: return ps_split_launch_shape<KEYEXPR, Part, 512, 8, 2>(ctx, ps, a, part, prog, status);
-    case 2: return ps_split_launch_shape<KEYEXPR, Part, 1024, 4, 1>(ctx, ps, a, part, prog, status);
-    case 3: return ps_split_launch_shape<KEYEXPR, Part, 256, 8, 5>(ctx, ps, a, part, prog, status);
-    case 4: return ps_split_launch_shape<KEYEXPR, Part, 256, 4, 6>(ctx, ps, a, part, prog, status);
     default: return ps_split_launch_shape<KEYEXPR, Part, 256, 8, 4>(ctx, ps, a, part, prog, status);
     }
 }

@@ -24,17 +24,12 @@ CASES = [
     ({"NQE_AGG_DENSE": "0"}, "group_by_one_value or group_by_dense or paged or group_key"),
     ({"NQE_JOIN_PART_MIN_ROWS": "1000", "NQE_JOIN_PART_MIN_MB": "0"}, "hash_join or join_aggregate or golden_readme"),
     ({"NQE_JA_PROBE_SHAPE": "1", "NQE_PS_SPLIT_SHAPE": "1"}, "paged or group_by_one_value or group_key"),
-    ({"NQE_JA_PROBE_SHAPE": "2", "NQE_PS_SPLIT_SHAPE": "2"}, "paged or group_by_one_value or group_key"),
-    ({"NQE_JA_PROBE_SHAPE": "4", "NQE_PS_SPLIT_SHAPE": "4"}, "paged or group_by_one_value or group_key"),
     # direct join table (dense unique build keys): on every small join of the suite (duplicates, sparse keys and payload
     # collisions fall back to the hashed table); switched off, the dense-key inputs go through the hashed / paged paths
     ({"NQE_JOIN_DIRECT_MIN_ROWS": "1"}, "hash_join or join_aggregate or golden_readme or multi_batch or run_sql"),
     ({"NQE_JOIN_DIRECT": "0"}, "direct_table"),
     ({"NQE_JOIN_DIRECT_NARROW": "0"}, "direct_table"),   # 8-byte slots
     ({"NQE_JOIN_DIRECT_STAGED": "0"}, "hash_join_direct_table"),  # the general probe kernel over the direct table
-    ({"NQE_JA_DIRECT_SHAPE": "1"}, "join_aggregate_direct_table"),
-    ({"NQE_JA_DIRECT_SHAPE": "2"}, "join_aggregate_direct_table"),
-    ({"NQE_JA_DIRECT_SHAPE": "3"}, "join_aggregate_direct_table"),
 ]
 
 
