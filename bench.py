@@ -731,7 +731,93 @@ def run_workloads(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hb
     # ---- configs[4]: join + group-by across ranks
     if world > 1:
         res["distributed_join_group_by"] = distributed_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, world)
+        res["multi_abi_join_group_by"] = multi_abi_join_group_by(args, nq, pp, torch, dist, synth, rank, world)
     return res
+
+
+def multi_abi_join_group_by(args, nq, pp, torch, dist, synth, rank, world):
+    """The configs[4] shape once more through the SINGLE-PROCESS entry of the C ABI (nqe_multi_join_aggregate,
+    csrc/multi.cu: what the single-process reference would bind): rank 0 drives all `world` GPUs from its one process
+    -- build side broadcast by peer copies, one host thread per member -- while the other ranks wait at a barrier.
+    A failure here is reported in the JSON, it does not take the run down."""
+    torch.cuda.empty_cache()
+    dist.barrier()
+    torch.cuda.synchronize()
+    out = None
+    # the other ranks must wait on the HOST: an NCCL barrier is a kernel spinning on their GPUs, which rank 0 is about to
+    # use (measured: 18.8 ms per call with the peers inside dist.barrier(), 3.3 ms with them asleep)
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        try:
+            out = _multi_abi_leg(args, nq, pp, torch, synth, world)
+        except Exception as e:  # noqa: BLE001 -- reported, not raised: the other ranks are waiting for the key below
+            out = {"error": repr(e)[:300]}
+        torch.cuda.set_device(0)
+        store.set("nqe_multi_abi_leg_done", "1")
+    else:
+        store.wait(["nqe_multi_abi_leg_done"])
+    dist.barrier()
+    return out
+
+
+def _multi_abi_leg(args, nq, pp, torch, synth, world):
+    I64, F64 = 2, 4
+    nb, npr = args.build_rows, args.multi_probe_rows
+    m = nq.MultiContext(list(range(world)))
+    col, lit, sv = nq.ColumnExpr.try_create, nq.PhysicalLiteralExpr.create, nq.ScalarValue
+    try:
+        shards, keep = [], []
+        cnt = torch.zeros(N_GROUPS, dtype=torch.int64, device="cuda:0")
+        sm = torch.zeros(N_GROUPS, dtype=torch.float64, device="cuda:0")
+        for i, c in enumerate(m.members):
+            torch.cuda.set_device(i)
+            t, b = device_table(nq, torch, c, synth.join_probe_table(nb), i * npr, npr, [I64, F64])
+            shards.append(t)
+            keep.append(b)
+            g = torch.remainder(b[0], N_GROUPS)  # every probe row matches build row k = fk, whose group is fk mod 1e5
+            cnt += torch.bincount(g, minlength=N_GROUPS).to("cuda:0")
+            sm += torch.bincount(g, weights=b[1].view(torch.float64), minlength=N_GROUPS).to("cuda:0")
+            del g
+        torch.cuda.set_device(0)
+        st0 = torch.cuda.Stream(device=0)
+        m.members[0].set_stream(st0.cuda_stream)
+        lt0, lb0 = device_table(nq, torch, m.members[0], synth.join_build_table(nb), 0, nb, [I64])
+        left = pp._filter_project(lt0, None, [col(None, 0), nq.PhysicalBinaryExpr.create(col(None, 0), "Modulos", lit(sv.Int64(N_GROUPS)))],
+                                  ["k", "a"])
+        aggs = [(5, 0), (0, 3), (1, 3), (3, 3), (4, 3)]  # group key, count / sum / min / max of b (joined schema k, a, fk, b)
+        names = ["key", "count", "sum", "min", "max"]
+        wall, dev = [], []
+        parity = None
+        for it in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(st0)
+            out = m.join_aggregate(left, shards, 0, 0, 1, aggs, names)
+            e1.record(st0)
+            e1.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+            dev.append(e0.elapsed_time(e1))
+            if it == 0:
+                tab = out.to_arrow()
+                key = torch.as_tensor(tab.column(0).to_numpy(), device="cuda:0")
+                o = torch.argsort(key)
+                gc = torch.as_tensor(tab.column(1).to_numpy().astype("int64"), device="cuda:0")[o]
+                gs = torch.as_tensor(tab.column(2).to_numpy(), device="cuda:0")[o]
+                parity = bool(tab.num_rows == N_GROUPS and torch.equal(key[o], torch.arange(N_GROUPS, device="cuda:0")) and
+                              torch.equal(gc, cnt) and bool(((gs - sm).abs() <= 1e-9 * sm.abs().clamp(min=1.0) * 10).all()))
+            groups = out.num_rows
+            out.free()
+        wall, dev = sorted(wall[2:]), sorted(dev[2:])
+        res = {"workload": f"hash-join + group-by, {npr} probe rows/GPU on {world} GPUs driven from ONE process through nqe_multi_join_aggregate",
+               "ms_per_call_median": dev[len(dev) // 2], "ms_per_call_best": dev[0], "wall_ms_per_call_median": wall[len(wall) // 2],
+               "value": world * npr / (dev[len(dev) // 2] / 1e3), "unit": "rows/s", "groups": groups, "parity_ok": parity,
+               "timing": "CUDA events on member 0's stream around the blocking call (its first and last operations run there); wall clock beside it"}
+        left.free(); lt0.free()
+        for t in shards:
+            t.free()
+        return res
+    finally:
+        m.close()
 
 
 def distributed_join_group_by(args, nq, pp, torch, dist, ctx, stream, synth, rank, world):
