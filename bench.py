@@ -714,6 +714,26 @@ def run_workloads(args, nq, pp, torch, dist, ctx, stream, synth, rank, world, hb
     rt2.free()
     del rb2
     torch.cuda.empty_cache()
+    # sparse keys: the same two queries with every key multiplied by 1 000 003, so the build keys are unique but NOT dense
+    # and the direct (key - min) join table does not apply: the hashed table, the partitioned probe / the paged plan
+    SPREAD = 1_000_003
+    with torch.cuda.stream(stream):
+        mul = lambda c: nq.PhysicalBinaryExpr.create(col(None, c), "Multiply", lit(sv.Int64(SPREAD)))
+        lts = pp._filter_project(lt, None, [mul(0), col(None, 1)], ["k", "a"])
+        rts = pp._filter_project(rt, None, [mul(0), col(None, 1)], ["fk", "b"])
+    js = nq.HashJoin.create(Src(lts), Src(rts), [("k", "fk")], "Inner")
+    bench_plan("hash_join_sparse_keys", "the configs[3] join with sparse unique build keys (k * 1000003): hashed table, partitioned probe",
+               js, 16.0 * nb + 16.0 * n + 32.0 * n, n)
+    res["hash_join_sparse_keys"]["parity_ok"] = res["hash_join_sparse_keys"]["out_rows"] == n
+    keep = {}
+    bench_plan("join_group_by_sparse_keys", "the fused join -> group-by with the same sparse keys: hashed table, paged plan",
+               nq.PhysicalAggregatePlan.create([col("a", None)], AGG5(3), js), 16.0 * nb + 16.0 * n, n, keep)
+    with torch.cuda.stream(stream):
+        grp = torch.remainder(rb[0], N_GROUPS)
+    res["join_group_by_sparse_keys"]["parity_ok"] = result_check(keep.pop("t"), grp, rb[1])
+    del grp
+    lts.free(); rts.free()
+    torch.cuda.empty_cache()
     # e2e through the host API (join: 3.2 GB of joined rows come back to the host)
     hl, hr = host_copy([lb0[0], torch.remainder(lb0[0], N_GROUPS)]), host_copy(rb)
 
