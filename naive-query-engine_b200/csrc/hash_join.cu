@@ -816,235 +816,7 @@ join_probe_kernel(const __grid_constant__ ProbeParams pp) {
     }
 }
 
-// ---- direct table, plain 8-byte columns: probe pass + staged emit pass -------------------------------------------
-// join_probe_kernel above is one pass with a decoupled look-back, and it is slow on 1e8 rows (2.3 ms where the traffic is
-// worth 0.8 ms) for two reasons that were measured one by one (profiles/README_r02.md):
-//  * the look-back: all ~600 resident tiles are in the same phase, so a tile's walk crosses hundreds of unresolved
-//    predecessors (37 % of the stall samples sit at the barrier behind the walking warp);
-//  * random table reads and heavy store traffic in ONE kernel: a kernel with the reads alone takes 0.88 ms, with the
-//    stores alone 0.81 ms (5.9 TB/s), with both 2.31 ms -- the table reads queue behind the SM's outstanding stores in the
-//    memory pipeline and every tile waits for them at its barrier.  L2 policies (evict_first streams, evict_last table,
-//    a persisting set-aside) change nothing.
-// So the work is cut where the dependency is: every CTA owns a CONTIGUOUS chunk of tiles;
-//   pass 1 (join_direct_probe_kernel) reads the keys, probes the table, writes the row words as a stream and counts
-//          the chunk's matches -- random reads, almost no stores, no barriers;
-//   pass 2 (join_direct_emit_kernel) starts at the sum of the earlier chunks' counts and walks its chunk with a running
-//          base: the probe-side columns and the row-word stream of its next tiles are in flight as cp.async.bulk
-//          copies into a shared-memory ring, ranks come from ballots (a row has 0 or 1 match), one barrier per tile,
-//          no global loads in the loop at all.
-constexpr int DE_MAX = 4; // columns per side
-struct DirectEmitParams {
-    JoinTable jt;
-    int64_t n_probe;
-    int32_t nl, nr, left_key, right_key;
-    const unsigned long long *right[DE_MAX]; // probe-side columns
-    unsigned long long *out[2 * DE_MAX];
-    unsigned long long *rowwords;            // per probe row: the table's row word (EMPTY_ROW: no match), written by pass 1;
-                                             // with a narrow table the stream is narrow too: the 4-byte slot as it is
-    unsigned long long *chunk_count, *out_count;
-    int32_t num_tiles, tiles_per_chunk, stages, pad;
-};
-
-template <int K>
-__global__ void __launch_bounds__(HJ_THREADS) join_direct_probe_kernel(const __grid_constant__ DirectEmitParams p) {
-    constexpr int T = HJ_THREADS, TILE = T * HJ_K, STEP = T * K;
-    __shared__ unsigned int s_warp[HJ_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t t0 = (int64_t)blockIdx.x * p.tiles_per_chunk;
-    const int64_t t1 = t0 + p.tiles_per_chunk < p.num_tiles ? t0 + p.tiles_per_chunk : p.num_tiles;
-    const int64_t r0 = t0 * TILE, r1 = t1 * TILE < p.n_probe ? t1 * TILE : p.n_probe;
-    const unsigned long long *keys = p.right[p.right_key];
-    const unsigned long long ef = pj_policy();
-    unsigned int cnt = 0;
-    for (int64_t base = r0 + tid; base < r1; base += STEP) {
-        unsigned long long key[K], brow[K];
-        uint64_t slot[K];
-        uint32_t live = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int64_t e = base + (int64_t)j * T;
-            key[j] = e < r1 ? ld_ef(keys + e, ef) : 0ull;
-            if (e < r1) live |= 1u << j;
-        }
-        probe_direct<K, false>(p.jt, key, live, brow, slot);
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            cnt += brow[j] != EMPTY_ROW;
-            if (!((live >> j) & 1u)) continue;
-            if (p.jt.narrow) // the slot again (row words of a narrow table are pay_lo + a 32-bit value)
-                ((unsigned int *)p.rowwords)[base + (int64_t)j * T] = brow[j] == EMPTY_ROW ? 0xffffffffu : (unsigned int)(brow[j] - (unsigned long long)p.jt.pay_lo);
-            else
-                st_ef(p.rowwords + base + (int64_t)j * T, brow[j], ef);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) s_warp[warp] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long total = 0;
-        for (int w = 0; w < HJ_WARPS; w++) total += s_warp[w];
-        p.chunk_count[blockIdx.x] = total;
-    }
-}
-
-// NL build-side columns (the key, and for NL == 2 the one column whose values ride in the table), NR probe-side columns:
-// compile-time, so that every column loop unrolls and the stores need one address computation each.
-template <int K, int NL, int NR, bool N32>
-__global__ void __launch_bounds__(HJ_THREADS, 4) join_direct_emit_kernel(const __grid_constant__ DirectEmitParams p) {
-    constexpr int T = HJ_THREADS, TILE = T * K;
-    constexpr int STAGE_WORDS = NR * TILE + (N32 ? TILE / 2 : TILE); // 8-byte words of one stage: NR columns + the row words
-    static_assert(K * HJ_WARPS == 32, "one (row group, warp) count per lane");
-    extern __shared__ __align__(128) unsigned char de_smem[];
-    unsigned long long *full = (unsigned long long *)de_smem, *empty = full + 8; // [stages] each
-    unsigned long long *ring = (unsigned long long *)(de_smem + 128);            // [stages][STAGE_WORDS]: probe columns, row words
-    __shared__ unsigned int s_cnt[2][K * HJ_WARPS];
-    __shared__ unsigned long long s_part[HJ_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = p.stages;
-    const int64_t full_tiles = p.n_probe / TILE;
-    const int64_t t0 = (int64_t)blockIdx.x * p.tiles_per_chunk;
-    const int64_t t1 = t0 + p.tiles_per_chunk < p.num_tiles ? t0 + p.tiles_per_chunk : p.num_tiles;
-    if (tid == 0) {
-        for (int s = 0; s < S; s++) {
-            nqe_mbar_init(full + s, 1);
-            nqe_mbar_init(empty + s, HJ_WARPS);
-        }
-        nqe_mbar_init_fence();
-    }
-    // first output row of this chunk: the matches of all earlier chunks
-    unsigned long long base = 0;
-    for (int i = tid; i < (int)blockIdx.x; i += T) base += p.chunk_count[i];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
-    if (lane == 0) s_part[warp] = base;
-    __syncthreads();
-    base = 0;
-#pragma unroll
-    for (int w = 0; w < HJ_WARPS; w++) base += s_part[w];
-    const unsigned long long ef = pj_policy();
-    auto issue = [&](int64_t tile, int stage) { // thread 0
-        nqe_mbar_arrive_expect_tx(full + stage, (uint32_t)STAGE_WORDS * 8u);
-#pragma unroll
-        for (int c = 0; c < NR; c++)
-            nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + c * TILE, p.right[c] + tile * TILE, TILE * 8u, full + stage, ef);
-        if (N32) nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + NR * TILE, (const unsigned int *)p.rowwords + tile * TILE, TILE * 4u, full + stage, ef);
-        else nqe_bulk_g2s(ring + (size_t)stage * STAGE_WORDS + NR * TILE, p.rowwords + tile * TILE, TILE * 8u, full + stage, ef);
-    };
-    if (tid == 0)
-        for (int s = 0; s < S; s++)
-            if (t0 + s < t1 && t0 + s < full_tiles) issue(t0 + s, s);
-    uint32_t it = 0;
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int64_t tile = t0; tile < t1; tile++, it++) {
-        const bool staged = tile < full_tiles;
-        const unsigned long long *st = ring + (size_t)stage * STAGE_WORDS + tid;
-        const int64_t e0 = tile * TILE + tid;
-        unsigned long long key[K], brow[K];
-        auto widen = [&](unsigned int w) { return w == 0xffffffffu ? EMPTY_ROW : (unsigned long long)w + (unsigned long long)p.jt.pay_lo; };
-        if (staged) {
-            nqe_mbar_wait(full + stage, parity);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                key[j] = st[p.right_key * TILE + j * T];
-                if (N32) brow[j] = widen(((const unsigned int *)(ring + (size_t)stage * STAGE_WORDS + NR * TILE))[j * T + tid]);
-                else brow[j] = st[NR * TILE + j * T];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                const int64_t e = e0 + (int64_t)j * T;
-                key[j] = e < p.n_probe ? ld_stream_u64(p.right[p.right_key] + e) : 0ull;
-                if (e >= p.n_probe) brow[j] = EMPTY_ROW;
-                else if (N32) brow[j] = widen(((const unsigned int *)p.rowwords)[e]);
-                else brow[j] = ld_stream_u64(p.rowwords + e);
-            }
-        }
-        unsigned off[K];
-        uint32_t emit = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const bool m = brow[j] != EMPTY_ROW;
-            const unsigned b = __ballot_sync(0xffffffffu, m);
-            off[j] = __popc(b & ((1u << lane) - 1u));
-            if (lane == 0) s_cnt[it & 1u][j * HJ_WARPS + warp] = __popc(b);
-            if (m) emit |= 1u << j;
-        }
-        __syncthreads();
-        // every warp scans the 32 (row group, warp) counts for itself: no second barrier
-        const unsigned mine = s_cnt[it & 1u][lane];
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const unsigned excl = incl - mine, total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-        for (int j = 0; j < K; j++) off[j] += __shfl_sync(0xffffffffu, excl, j * HJ_WARPS + warp);
-#pragma unroll
-        for (int c = 0; c < NL; c++) {
-            unsigned long long *out = p.out[c] + base;
-            const bool is_key = NL == 1 || c == p.left_key; // the build key matched: its value is the probe key
-#pragma unroll
-            for (int j = 0; j < K; j++)
-                if ((emit >> j) & 1u) st_ef(out + off[j], is_key ? key[j] : brow[j], ef);
-        }
-#pragma unroll
-        for (int c = 0; c < NR; c++) {
-            unsigned long long *out = p.out[NL + c] + base;
-            unsigned long long v[K];
-            if (staged) {
-#pragma unroll
-                for (int j = 0; j < K; j++) v[j] = st[c * TILE + j * T];
-            } else {
-#pragma unroll
-                for (int j = 0; j < K; j++) v[j] = ((emit >> j) & 1u) ? (unsigned long long)ld_stream_u64(p.right[c] + e0 + (int64_t)j * T) : 0ull;
-            }
-#pragma unroll
-            for (int j = 0; j < K; j++)
-                if ((emit >> j) & 1u) st_ef(out + off[j], v[j], ef);
-        }
-        base += total;
-        if (staged) { // hand the stage back; thread 0 refills it with the tile S steps ahead
-            __syncwarp();
-            if (lane == 0) nqe_mbar_arrive(empty + stage);
-            if (tid == 0 && tile + S < t1 && tile + S < full_tiles) {
-                nqe_mbar_wait(empty + stage, parity);
-                issue(tile + S, stage);
-            }
-        }
-        if (++stage == S) {
-            stage = 0;
-            parity ^= 1u;
-        }
-    }
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) *p.out_count = base;
-}
-
-template <int NL, int NR, bool N32>
-int32_t join_direct_emit_launch_n(nqe_ctx *ctx, DirectEmitParams &de) {
-    de.stages = NR <= 1 ? 3 : 2;
-    const size_t smem = 128 + (size_t)de.stages * (NR * 8 + (N32 ? 4 : 8)) * HJ_K * HJ_THREADS;
-    auto dk = join_direct_emit_kernel<HJ_K, NL, NR, N32>;
-    NQE_CUDA(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int docc = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, dk, HJ_THREADS, smem);
-    int chunks = ctx->sm_count * (docc > 0 ? docc : 1); // one wave of CTAs, a contiguous chunk of tiles each
-    if (chunks > de.num_tiles) chunks = de.num_tiles;
-    de.tiles_per_chunk = (de.num_tiles + chunks - 1) / chunks;
-    chunks = (de.num_tiles + de.tiles_per_chunk - 1) / de.tiles_per_chunk;
-    join_direct_probe_kernel<8><<<chunks, HJ_THREADS, 0, ctx->stream>>>(de);
-    dk<<<chunks, HJ_THREADS, smem, ctx->stream>>>(de);
-    ctx->launches += 2;
-    NQE_CUDA(ctx, cudaGetLastError());
-    return NQE_OK;
-}
-template <int NL, int NR>
-int32_t join_direct_emit_launch(nqe_ctx *ctx, DirectEmitParams &de) {
-    return de.jt.narrow ? join_direct_emit_launch_n<NL, NR, true>(ctx, de) : join_direct_emit_launch_n<NL, NR, false>(ctx, de);
-}
+#include "hash_join_direct.cuh" // direct table: probe pass + staged emit pass
 
 // ---- fused join -> group-by aggregate --------------------------------------
 struct JoinAggParams {
@@ -1143,222 +915,7 @@ join_aggregate_kernel(const __grid_constant__ JoinAggParams jp, const __grid_con
     }
 }
 
-// ---- Fused join -> group-by over paged streams ------------------------------------------------------------------
-// The direct kernel above makes one DRAM-random slot access per probe row into a table far larger than the L2
-// (11.6 GB of DRAM traffic per 1e8 rows where the inputs are 1.76 GB) plus the L2-bound group-table updates.  When the
-// build keys are unique and the group key rides in the slots (JoinTable::rowpay) the work is reorganised into three
-// streaming passes over 16-byte rows (paged_split.cuh):
-//   1. ps_split_kernel<PartBySlotRange>: (fk, value) rows split by the top bits of the key's hash = ranges of table
-//      slots of <= 48 MiB;
-//   2. ja_probe_scatter_kernel: pages are swept partition after partition (every CTA takes every gridDim-th page of
-//      the concatenated page list, so the whole grid works inside one slot range at a time and the range stays in L2);
-//      a probe row becomes (group key, value) and is split again, by group-key hash, into the group-by's partitions;
-//   3. gp2_aggregate_kernel (hash_aggregate.cu): shared-memory aggregation of every partition.
-// Unmatched probe rows simply vanish in pass 2 (inner join).
-struct PartBySlotRange { // partition = top of the hash = contiguous range of table slots (join_slot_of is monotone in the hash)
-    uint64_t P;
-    __device__ __forceinline__ int operator()(unsigned long long key) const { return (int)__umul64hi(nqe_mix64(key), P); }
-};
-
-// A CTA works on PIECES of T * K rows (a quarter, a half or a whole page) through one cp.async.bulk-filled buffer:
-// the rows go into registers, the buffer is handed back to thread 0 -- the elected producer -- which issues the copy
-// of the CTA's next piece at once, so it flies while the CTA probes and scatters.  Several small CTAs per SM overlap
-// each other's phases (bulk-copy wait, L2 probe latency, the scatter's barriers and its global cursor round trip).
-template <int T, int K>
-struct JpSmem {
-    ulonglong2 piece[T * K];
-    PsScatterSmem<T, K> sc;
-    PsPageBuf buf;
-    unsigned int pstart[PS_MAX_PARTS + 8]; // first page of every input partition in the concatenated page list
-};
-
-// piece i of the concatenated page list -> (partition, page, first row inside the page, rows); *p is a running cursor
-template <int PIECE>
-__device__ __forceinline__ unsigned jp_locate(const PagedStreams &in, const unsigned int *pstart, unsigned i, int *p, unsigned *q,
-                                              unsigned *row0) {
-    constexpr unsigned PER_PAGE = PS_PAGE_ROWS / PIECE;
-    const unsigned w = i / PER_PAGE;
-    int pp = *p;
-    while (pp + 1 < in.P && w >= pstart[pp + 1]) pp++;
-    *p = pp;
-    *q = w - pstart[pp];
-    *row0 = (i % PER_PAGE) * PIECE;
-    const unsigned fill = ps_page_rows(in, pp, *q);
-    return fill <= *row0 ? 0u : (fill - *row0 < (unsigned)PIECE ? fill - *row0 : (unsigned)PIECE);
-}
-
-template <int T, int K, int MINB>
-__global__ void __launch_bounds__(T, MINB)
-ja_probe_scatter_kernel(const __grid_constant__ PagedStreams in, const __grid_constant__ PagedStreams out, const JoinTable jt,
-                        uint32_t P2, long long dense_lo, uint32_t dense_width) {
-    constexpr int PIECE = T * K;
-    extern __shared__ __align__(128) unsigned char jp_smem_raw[];
-    JpSmem<T, K> &sm = *reinterpret_cast<JpSmem<T, K> *>(jp_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t dense_magic = dense_width ? ps_div_magic(dense_width) : 0u;
-    if (tid == 0) {
-        unsigned acc = 0;
-        for (int p = 0; p < in.P; p++) {
-            sm.pstart[p] = acc;
-            acc += (unsigned)((in.cursor[p] + PS_PAGE_ROWS - 1) >> PS_PAGE_SHIFT);
-        }
-        sm.pstart[in.P] = acc;
-    }
-    ps_pagebuf_init(sm.buf, T / 32);
-    ps_scatter_init(sm.sc); // __syncthreads inside
-    const unsigned total = sm.pstart[in.P] * (PS_PAGE_ROWS / PIECE);
-    // thread 0 walks the piece list one step ahead of the CTA (pn, in, next piece with rows)
-    int pn = 0;
-    unsigned nxt = blockIdx.x; // next piece to issue
-    auto issue_next = [&]() {  // thread 0: issue the copy of the next non-empty piece at or after `nxt`
-        while (nxt < total) {
-            unsigned q, row0;
-            const unsigned rows = jp_locate<PIECE>(in, sm.pstart, nxt, &pn, &q, &row0);
-            nxt += gridDim.x;
-            if (!rows) continue;
-            const unsigned pte = in.pt[(size_t)pn * in.pt_stride + q];
-            nqe_mbar_arrive_expect_tx(&sm.buf.full, rows * 16u);
-            const ulonglong2 *src = in.pool + ((size_t)(pte - 1u) << PS_PAGE_SHIFT) + row0;
-            for (unsigned off = 0; off < rows; off += 1024u) {
-                const unsigned len = rows - off < 1024u ? rows - off : 1024u;
-                nqe_bulk_g2s(sm.piece + off, src + off, len * 16u, &sm.buf.full, nqe_policy_evict_first());
-            }
-            return;
-        }
-    };
-    if (tid == 0) issue_next();
-    int p = 0;
-    uint32_t it = 0;
-    for (unsigned i = blockIdx.x; i < total; i += gridDim.x) {
-        unsigned q, row0;
-        const unsigned rows = jp_locate<PIECE>(in, sm.pstart, i, &p, &q, &row0);
-        if (!rows) continue; // CTA-uniform
-        nqe_mbar_wait(&sm.buf.full, it & 1u);
-        unsigned long long key[K], val[K];
-        uint32_t live = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const unsigned idx = j * T + tid;
-            ulonglong2 r = make_ulonglong2(0ull, 0ull);
-            if (idx < rows) { r = sm.piece[idx]; live |= 1u << j; }
-            key[j] = r.x;
-            val[j] = r.y;
-        }
-        __syncwarp();
-        if (lane == 0) nqe_mbar_arrive(&sm.buf.empty);
-        if (tid == 0) {
-            nqe_mbar_wait(&sm.buf.empty, it & 1u);
-            issue_next();
-        }
-        it++;
-        unsigned long long grp[K];
-        uint64_t slot[K];
-        probe_first<K>(jt, key, live, grp, slot); // unique build keys: the first match is the only one
-        int pid[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
-            // dense group keys (their exact range is known from the build side): partition = key range, else key hash
-            pid[j] = dense_width ? (int)ps_div((uint32_t)(grp[j] - (unsigned long long)dense_lo), dense_width, dense_magic)
-                                 : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
-            if (!((live >> j) & 1u)) pid[j] = 0;
-        }
-        ps_scatter_tile<T, K>(out, sm.sc, grp, val, pid, live);
-    }
-}
-
-template <int T, int K, int MINB>
-int32_t ja_probe_scatter_launch_shape(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
-                                      long long dense_lo, uint32_t dense_width) {
-    auto kern = ja_probe_scatter_kernel<T, K, MINB>;
-    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpSmem<T, K>)));
-    kern<<<ctx->sm_count * MINB, T, sizeof(JpSmem<T, K>), ctx->stream>>>(in, out, jt, P2, dense_lo, dense_width);
-    ctx->launches++;
-    NQE_CUDA(ctx, cudaGetLastError());
-    return NQE_OK;
-}
-// knob NQE_JA_PROBE_SHAPE: 0 (default) = 256 threads x 2 rows (512-row pieces, 6 CTAs/SM at 40 registers), 1 = 512 x 4
-// (half pages, 2 CTAs/SM).  Measured 1e8 x 1e7, whole operator, with the shapes that were removed again (1024 x 4 at one
-// CTA/SM, 256 x 4 at 5 and at 4 CTAs/SM): 4.69 / 4.92 / 4.95 / 5.00 / 4.84 ms: the kernel waits on L2 round trips, more
-// resident warps beat more rows per thread.
-int32_t ja_probe_scatter_launch(nqe_ctx *ctx, const PagedStreams &in, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
-                                long long dense_lo, uint32_t dense_width) {
-    static int shape = -1;
-    if (shape < 0) {
-        const char *e = getenv("NQE_JA_PROBE_SHAPE");
-        shape = e ? atoi(e) : 0;
-    }
-    switch (shape) {
-    case 1: return ja_probe_scatter_launch_shape<512, 4, 2>(ctx, in, out, jt, P2, dense_lo, dense_width);
-    default: return ja_probe_scatter_launch_shape<256, 2, 6>(ctx, in, out, jt, P2, dense_lo, dense_width);
-    }
-}
-
-// The same pass over a DIRECT table (dense unique build keys): the table is probed in place -- 8 bytes per key of the
-// range, mostly L2-resident -- so the probe rows are read straight from their columns, no first split: a probe row
-// (fk, value) becomes (group key, value as f64) and goes into the group-by's partitions.
-// CM: bit 0 = the streams (probe rows in, pages out) carry evict_first, bit 1 = the table reads carry evict_last
-template <int T, int K, int MINB, int CM>
-__global__ void __launch_bounds__(T, MINB)
-ja_direct_scatter_kernel(const __grid_constant__ PagedStreams out, const PsSplitArgs a, const JoinTable jt, uint32_t P2,
-                         long long dense_lo, uint32_t dense_width) {
-    constexpr int TILE = T * K;
-    extern __shared__ __align__(16) unsigned char jd_smem_raw[];
-    PsScatterSmem<T, K> &sm = *reinterpret_cast<PsScatterSmem<T, K> *>(jd_smem_raw);
-    ps_scatter_init(sm);
-    const uint32_t dense_magic = dense_width ? ps_div_magic(dense_width) : 0u;
-    const int64_t num_tiles = (a.n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t e0 = tile * TILE + threadIdx.x;
-        unsigned long long key[K], val[K], grp[K];
-        uint64_t slot[K];
-        int pid[K];
-        uint32_t live = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            if (e0 + (int64_t)j * T < a.n) live |= 1u << j;
-        const unsigned long long ef = (CM & 1) ? pj_policy() : 0ull;
-        auto ld_in = [&](const unsigned long long *p) { return (CM & 1) ? ld_ef(p, ef) : (unsigned long long)ld_stream_u64(p); };
-#pragma unroll
-        for (int j = 0; j < K; j++) key[j] = ((live >> j) & 1u) ? ld_in(a.keys + e0 + (int64_t)j * T) : 0ull;
-        probe_direct<K, (CM & 2) != 0>(jt, key, live, grp, slot);
-#pragma unroll
-        for (int j = 0; j < K; j++) val[j] = ((live >> j) & 1u) ? ps_as_f64_bits(a.val_dtype, ld_in(a.vals + e0 + (int64_t)j * T)) : 0ull;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            if (grp[j] == EMPTY_ROW) live &= ~(1u << j);
-            pid[j] = dense_width ? (int)ps_div((uint32_t)(grp[j] - (unsigned long long)dense_lo), dense_width, dense_magic)
-                                 : (int)__umulhi((uint32_t)(nqe_mix64(grp[j]) >> 32), P2);
-            if (!((live >> j) & 1u)) pid[j] = 0;
-        }
-        ps_scatter_tile<T, K, PsNoHook, (CM & 1) != 0>(out, sm, grp, val, pid, live);
-    }
-}
-
-// (A software-pipelined variant -- probe rows through a ring of cp.async.bulk stages, the next tile's table reads issued
-// before this tile's page stores -- was measured and is slower in every shape tried: whole operator 2.71 .. 3.62 ms
-// against 2.14 ms; the smaller tiles it needs cost more cursor atomics and barriers than the overlap wins back.)
-template <int T, int K, int MINB, int CM = 3>
-int32_t ja_direct_scatter_launch_shape(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
-                                       long long dense_lo, uint32_t dense_width) {
-    auto kern = ja_direct_scatter_kernel<T, K, MINB, CM>;
-    const size_t smem = sizeof(PsScatterSmem<T, K>);
-    NQE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t tiles = (a.n + (int64_t)T * K - 1) / ((int64_t)T * K);
-    int grid = ctx->sm_count * MINB;
-    if (grid > tiles) grid = (int)tiles;
-    if (grid < 1) return NQE_OK;
-    kern<<<grid, T, smem, ctx->stream>>>(out, a, jt, P2, dense_lo, dense_width);
-    ctx->launches++;
-    NQE_CUDA(ctx, cudaGetLastError());
-    return NQE_OK;
-}
-// one shape: 256 threads x 8 rows, 4 CTAs per SM (the plain split's); 256 x 4 at 6 CTAs, 512 x 8 at 2 and 256 x 8 at 3 CTAs per
-// SM measured within noise of it (2.40 .. 2.50 ms for the whole operator), as did the L2 policy combinations
-int32_t ja_direct_scatter_launch(nqe_ctx *ctx, const PsSplitArgs &a, const PagedStreams &out, const JoinTable &jt, uint32_t P2,
-                                 long long dense_lo, uint32_t dense_width) {
-    return ja_direct_scatter_launch_shape<256, 8, 4, 3>(ctx, a, out, jt, P2, dense_lo, dense_width);
-}
+#include "hash_join_paged.cuh" // fused join -> group-by over paged streams
 
 // smallest probe side that takes the partitioned / paged paths (knob NQE_JOIN_PART_MIN_ROWS; tests and the
 // compute-sanitizer runs lower it so that those kernels run on small inputs)
